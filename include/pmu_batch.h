@@ -1,0 +1,129 @@
+/*
+ * pmu_batch.h — C ABI of the B200 batched synchrophasor estimator (type-generic core).
+ *
+ * Plain pointers and sizes only; no CUDA or torch types in any signature.  Every
+ * libpmu_estimator*.so exports these entry points next to the drop-in
+ * pmu_init / pmu_estimate / pmu_deinit / pmu_dump_frame of pmu_estimator.h.
+ *
+ * What each one replaces in the reference (chemsallioua/SynchroPMU, paths relative to the
+ * reference tree):
+ *   pmub_create / pmub_create_ini  <- pmu_init            src/pmu_estimator.c:92-167
+ *                                     config_estimator    src/pmu_estimator.c:327-384
+ *   pmub_validate                  <- check_config_validity src/pmu_estimator.c:386-449
+ *   pmub_parse_ini                 <- config_from_file    src/pmu_estimator.c:451-484
+ *                                     (+ libs/iniparser line rules, iniparser.c:620-700)
+ *   pmub_estimate[_async]          <- pmu_estimate        src/pmu_estimator.c:170-271,
+ *                                     once per (instance, channel) of the batch
+ *   pmub_destroy                   <- pmu_deinit          src/pmu_estimator.c:274-303
+ *   pmub_reset / get_state / set_state <- the ROCOF members of pmu_context
+ *                                     (RocoFEstimationStates, src/pmu_estimator.h:100-107)
+ *
+ * There is NO CPU fallback: creation fails (-1) without a CUDA device, and estimation
+ * only ever runs the sm_100a kernel.
+ *
+ * Return convention: 0 = ok, -1 = error (message on stderr and in pmub_last_error()),
+ * like the reference (src/pmu_estimator.c:96-105, 176-180).
+ */
+#ifndef PMU_BATCH_H
+#define PMU_BATCH_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMUB_F32 4 /* float_p = float  : windows, mid_fracsec and frames are float  */
+#define PMUB_F64 8 /* float_p = double : ... are double                              */
+
+typedef struct pmub_batch pmub_batch;
+
+/* estimator_config (src/pmu_estimator.h:30-43) with the float type fixed to double so
+ * one struct serves both builds; values are rounded to float_p on creation. */
+typedef struct {
+    unsigned n_cycles;
+    unsigned f0;
+    unsigned frame_rate;
+    unsigned fs;
+    unsigned n_bins;
+    unsigned P;
+    unsigned Q;
+    unsigned iter_eipdft;
+    double interf_trig;
+    double rocof_thresh[3];
+    double rocof_low_pass_coeffs[3];
+} pmub_config;
+
+typedef struct {
+    unsigned win_len;      /* n_cycles * fs / f0                                         */
+    unsigned n_bins;
+    unsigned n_instances;
+    unsigned n_channels;
+    int dtype;             /* PMUB_F32 / PMUB_F64                                        */
+    int device;
+    double df;             /* fs / win_len                                               */
+    double norm_factor;    /* sequential Hann sum, src/pmu_estimator.c:549-560           */
+    /* how the kernel was specialised for this configuration */
+    int dft_radix;         /* M: in-register real-FFT codelet size                       */
+    int dft_bins;          /* KC: rectangular bins accumulated per lane                  */
+    int n_stages;          /* shared-memory ring depth                                   */
+    int stage_bytes;
+    int slabs_per_window;
+    int load_mode;         /* 0 = TMA bulk copies, 1 = per-element cp.async              */
+    int grid;              /* CTAs launched for a full batch                             */
+    int block;             /* threads per CTA                                            */
+    int smem_bytes;        /* dynamic shared memory per CTA                              */
+    double bytes_per_estimate; /* algorithmic HBM bytes per (window x channel)           */
+} pmub_info;
+
+/* ---- host logic (no GPU needed) ------------------------------------------------ */
+int pmub_validate(const pmub_config *cfg);
+int pmub_parse_ini(const char *ini_path, pmub_config *out);
+const char *pmub_last_error(void);
+
+/* ---- lifecycle ----------------------------------------------------------------- */
+/* device < 0: use the calling thread's current CUDA device. */
+int pmub_create(pmub_batch **out, const pmub_config *cfg, int dtype, unsigned n_instances,
+                unsigned n_channels, int device);
+int pmub_create_ini(pmub_batch **out, const char *ini_path, int dtype, unsigned n_instances,
+                    unsigned n_channels, int device);
+int pmub_destroy(pmub_batch *b);
+int pmub_get_info(const pmub_batch *b, pmub_info *out);
+
+/* ---- the hot path -------------------------------------------------------------- */
+/* One frame for every (instance, channel):
+ *   windows     float_p [n_instances][n_channels][win_len]
+ *   mid_fracsec float_p [n_instances]
+ *   frames      float_p [n_instances][n_channels][4] = {amp, ph, freq, rocof}
+ *               (= pmu_frame[n_instances][n_channels], src/pmu_estimator.h:45-56)
+ * Each pointer may be host memory or device memory (detected).  Host inputs are copied
+ * in chunks overlapped with the kernel.  Synchronous: results are complete on return. */
+int pmub_estimate(pmub_batch *b, const void *windows, const void *mid_fracsec, void *frames);
+/* Device pointers only; enqueues on the batch's stream and returns immediately. */
+int pmub_estimate_async(pmub_batch *b, const void *d_windows, const void *d_mid_fracsec,
+                        void *d_frames);
+int pmub_sync(pmub_batch *b);
+/* Run on the caller's CUDA stream (cudaStream_t passed as void*); NULL = own stream. */
+int pmub_set_stream(pmub_batch *b, void *cuda_stream);
+/* Kernels launched by this batch so far. */
+long long pmub_launch_count(const pmub_batch *b);
+
+/* ---- ROCOF state (checkpoint / resume) ------------------------------------------ */
+int pmub_reset(pmub_batch *b); /* freq_old = f0, delay line = 0, state = 0 (:141-147) */
+/* host arrays of n_instances * n_channels entries each */
+int pmub_get_state(pmub_batch *b, double *freq_old, double *dl0, double *dl1, unsigned char *state);
+int pmub_set_state(pmub_batch *b, const double *freq_old, const double *dl0, const double *dl1,
+                   const unsigned char *state);
+
+/* ---- parity / debug observability ------------------------------------------------ */
+/* After pmub_set_debug(b, 1) every estimate also records, per (instance, channel):
+ *   flags    int    : bits 0-15 = peak bin km of the first ipDFT, bit 16 = interference
+ *                     iterations were triggered
+ *   spectrum double [n_bins][2] : the Hann-windowed DFT bins (what pmue_fft_r yields,
+ *                     src/pmu_estimator.c:200)
+ * fetched (to host arrays, either may be NULL) by pmub_get_debug. */
+int pmub_set_debug(pmub_batch *b, int enable);
+int pmub_get_debug(pmub_batch *b, int *flags, double *spectrum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMU_BATCH_H */

@@ -1,0 +1,286 @@
+"""ctypes binding of the C ABI in include/pmu_batch.h (the batched entry).
+
+This is plumbing over ``libpmu_estimator*.so``; all arithmetic happens in the CUDA
+kernel.  There is no Python or CPU estimation path here: if the shared library is
+missing or no CUDA device is present, construction raises.
+
+Host-side mirror of the reference's operator interface for this path:
+``BatchEstimator.estimate`` == ``pmu_estimate`` (reference src/pmu_estimator.c:170-271)
+applied to ``n_instances x n_channels`` windows at once.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_DIR = PKG / "lib"
+CSRC = PKG / "csrc"
+
+PMUB_F32, PMUB_F64 = 4, 8
+
+
+class CoreConfig(C.Structure):
+    """``pmub_config`` — estimator_config (reference src/pmu_estimator.h:30-43) in doubles."""
+
+    _fields_ = [
+        ("n_cycles", C.c_uint), ("f0", C.c_uint), ("frame_rate", C.c_uint), ("fs", C.c_uint),
+        ("n_bins", C.c_uint), ("P", C.c_uint), ("Q", C.c_uint), ("iter_eipdft", C.c_uint),
+        ("interf_trig", C.c_double), ("rocof_thresh", C.c_double * 3),
+        ("rocof_low_pass_coeffs", C.c_double * 3),
+    ]
+
+    @classmethod
+    def from_dict(cls, cfg: dict) -> "CoreConfig":
+        c = cls()
+        for k in ("n_cycles", "f0", "frame_rate", "fs", "n_bins", "P", "Q"):
+            setattr(c, k, int(cfg[k]))
+        c.iter_eipdft = 1 if cfg.get("iter_eipdft", 0) else 0
+        c.interf_trig = float(cfg["interf_trig"])
+        c.rocof_thresh = (C.c_double * 3)(*cfg["rocof_thresh"])
+        c.rocof_low_pass_coeffs = (C.c_double * 3)(*cfg["rocof_low_pass_coeffs"])
+        return c
+
+    def to_dict(self) -> dict:
+        return dict(n_cycles=self.n_cycles, f0=self.f0, frame_rate=self.frame_rate, fs=self.fs,
+                    n_bins=self.n_bins, P=self.P, Q=self.Q, iter_eipdft=int(self.iter_eipdft),
+                    interf_trig=self.interf_trig, rocof_thresh=list(self.rocof_thresh),
+                    rocof_low_pass_coeffs=list(self.rocof_low_pass_coeffs))
+
+
+class BatchInfo(C.Structure):
+    """``pmub_info``."""
+
+    _fields_ = [
+        ("win_len", C.c_uint), ("n_bins", C.c_uint), ("n_instances", C.c_uint), ("n_channels", C.c_uint),
+        ("dtype", C.c_int), ("device", C.c_int), ("df", C.c_double), ("norm_factor", C.c_double),
+        ("dft_radix", C.c_int), ("dft_bins", C.c_int), ("n_stages", C.c_int), ("stage_bytes", C.c_int),
+        ("slabs_per_window", C.c_int), ("load_mode", C.c_int), ("grid", C.c_int), ("block", C.c_int),
+        ("smem_bytes", C.c_int), ("bytes_per_estimate", C.c_double),
+    ]
+
+
+def lib_path(dtype=np.float64, n_channels: int = 1) -> Path:
+    """The ABI variant for (float_p, NUM_CHANLS); the pmub_* core is identical in all of them."""
+    name = "libpmu_estimator"
+    if np.dtype(dtype) == np.float32:
+        name += "_f32"
+    if n_channels == 6:
+        name += "_c6"
+    elif n_channels != 1:
+        raise ValueError("prebuilt drop-in variants exist for NUM_CHANLS 1 and 6")
+    return LIB_DIR / f"{name}.so"
+
+
+def build_library(verbose: bool = False) -> None:
+    """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    jobs = str(max(2, min(8, os.cpu_count() or 2)))
+    subprocess.run(["make", "-C", str(CSRC), "-j", jobs], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+
+
+_LIB = None
+
+
+def load_library(path: Path | None = None) -> C.CDLL:
+    """dlopen libpmu_estimator.so and declare the pmub_* prototypes.  Raises if absent."""
+    global _LIB
+    if path is None and _LIB is not None:
+        return _LIB
+    p = Path(path) if path else lib_path()
+    if not p.exists():
+        raise FileNotFoundError(
+            f"{p} not built - run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the estimator)")
+    lib = C.CDLL(str(p))
+    vp, ip = C.c_void_p, C.c_int
+    lib.pmub_last_error.restype = C.c_char_p
+    lib.pmub_validate.argtypes = [C.POINTER(CoreConfig)]
+    lib.pmub_parse_ini.argtypes = [C.c_char_p, C.POINTER(CoreConfig)]
+    lib.pmub_create.argtypes = [C.POINTER(vp), C.POINTER(CoreConfig), ip, C.c_uint, C.c_uint, ip]
+    lib.pmub_create_ini.argtypes = [C.POINTER(vp), C.c_char_p, ip, C.c_uint, C.c_uint, ip]
+    lib.pmub_destroy.argtypes = [vp]
+    lib.pmub_get_info.argtypes = [vp, C.POINTER(BatchInfo)]
+    lib.pmub_estimate.argtypes = [vp, vp, vp, vp]
+    lib.pmub_estimate_async.argtypes = [vp, vp, vp, vp]
+    lib.pmub_sync.argtypes = [vp]
+    lib.pmub_set_stream.argtypes = [vp, vp]
+    lib.pmub_launch_count.argtypes = [vp]
+    lib.pmub_launch_count.restype = C.c_longlong
+    lib.pmub_reset.argtypes = [vp]
+    lib.pmub_get_state.argtypes = [vp, vp, vp, vp, vp]
+    lib.pmub_set_state.argtypes = [vp, vp, vp, vp, vp]
+    lib.pmub_set_debug.argtypes = [vp, ip]
+    lib.pmub_get_debug.argtypes = [vp, vp, vp]
+    for fn in ("pmub_validate", "pmub_parse_ini", "pmub_create", "pmub_create_ini", "pmub_destroy",
+               "pmub_get_info", "pmub_estimate", "pmub_estimate_async", "pmub_sync", "pmub_set_stream",
+               "pmub_reset", "pmub_get_state", "pmub_set_state", "pmub_set_debug", "pmub_get_debug"):
+        getattr(lib, fn).restype = ip
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def last_error(lib=None) -> str:
+    lib = lib or load_library()
+    return (lib.pmub_last_error() or b"").decode(errors="replace")
+
+
+def validate(cfg: dict) -> bool:
+    """check_config_validity (reference src/pmu_estimator.c:386-449).  Host only."""
+    return load_library().pmub_validate(C.byref(CoreConfig.from_dict(cfg))) == 0
+
+
+def parse_ini(path: str) -> dict | None:
+    """config_from_file (reference src/pmu_estimator.c:451-484).  Host only."""
+    c = CoreConfig()
+    if load_library().pmub_parse_ini(os.fsencode(path), C.byref(c)) != 0:
+        return None
+    return c.to_dict()
+
+
+def _ptr(x) -> int:
+    """Address of a numpy array (host) or a torch tensor (host or CUDA)."""
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    raise TypeError(type(x))
+
+
+class BatchEstimator:
+    """``n_instances`` independent estimators x ``n_channels`` channels on one GPU.
+
+    ``estimate(windows, mid_fracsec)`` takes windows ``[n_instances, n_channels, win_len]``
+    and ``mid_fracsec [n_instances]`` as numpy arrays (host) or torch tensors (host or
+    CUDA) of the batch dtype and returns frames ``[n_instances, n_channels, 4]`` =
+    ``(amp, ph, freq, rocof)`` in the same kind of container.  ROCOF state for every
+    (instance, channel) stays resident in HBM between calls.
+    """
+
+    def __init__(self, cfg, n_instances: int, n_channels: int = 1, dtype=np.float64, device: int = -1,
+                 lib: C.CDLL | None = None):
+        self.lib = lib or load_library()
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise TypeError("dtype must be float64 or float32")
+        self.n_instances, self.n_channels = int(n_instances), int(n_channels)
+        h = C.c_void_p()
+        code = PMUB_F64 if self.dtype == np.float64 else PMUB_F32
+        if isinstance(cfg, (str, os.PathLike)):
+            rc = self.lib.pmub_create_ini(C.byref(h), os.fsencode(cfg), code, self.n_instances,
+                                          self.n_channels, device)
+        else:
+            rc = self.lib.pmub_create(C.byref(h), C.byref(CoreConfig.from_dict(cfg)), code,
+                                      self.n_instances, self.n_channels, device)
+        if rc != 0 or not h.value:
+            raise RuntimeError(f"pmub_create failed: {last_error(self.lib)}")
+        self._h = h
+        info = BatchInfo()
+        self.lib.pmub_get_info(self._h, C.byref(info))
+        self.info = info
+        self.win_len = int(info.win_len)
+        self.n_bins = int(info.n_bins)
+
+    # -- lifecycle ----------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.pmub_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: {last_error(self.lib)}")
+
+    # -- hot path -----------------------------------------------------------
+    def estimate(self, windows, mid_fracsec, out=None):
+        """Synchronous estimate; host or device containers (see class docstring)."""
+        n, c = self.n_instances, self.n_channels
+        is_torch = hasattr(windows, "data_ptr")
+        if is_torch:
+            import torch
+
+            tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+            assert windows.dtype == tdt and windows.is_contiguous() and windows.numel() == n * c * self.win_len
+            assert mid_fracsec.dtype == tdt and mid_fracsec.is_contiguous() and mid_fracsec.numel() == n
+            if out is None:
+                out = torch.empty((n, c, 4), dtype=tdt, device=windows.device)
+        else:
+            windows = np.ascontiguousarray(windows, dtype=self.dtype)
+            mid_fracsec = np.ascontiguousarray(mid_fracsec, dtype=self.dtype)
+            assert windows.size == n * c * self.win_len and mid_fracsec.size == n
+            if out is None:
+                out = np.empty((n, c, 4), dtype=self.dtype)
+        self._check(self.lib.pmub_estimate(self._h, _ptr(windows), _ptr(mid_fracsec), _ptr(out)), "pmub_estimate")
+        return out
+
+    def estimate_async(self, d_windows, d_mid_fracsec, d_out) -> None:
+        """Device tensors only; enqueue on the batch stream and return."""
+        self._check(self.lib.pmub_estimate_async(self._h, _ptr(d_windows), _ptr(d_mid_fracsec), _ptr(d_out)),
+                    "pmub_estimate_async")
+
+    def sync(self) -> None:
+        self._check(self.lib.pmub_sync(self._h), "pmub_sync")
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        """Run on the caller's CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+        self._check(self.lib.pmub_set_stream(self._h, C.c_void_p(cuda_stream or 0)), "pmub_set_stream")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.pmub_launch_count(self._h))
+
+    # -- ROCOF state (checkpoint / resume) ------------------------------------
+    def reset(self) -> None:
+        self._check(self.lib.pmub_reset(self._h), "pmub_reset")
+
+    def get_state(self) -> dict:
+        n = self.n_instances * self.n_channels
+        st = dict(freq_old=np.empty(n), dl0=np.empty(n), dl1=np.empty(n), state=np.empty(n, dtype=np.uint8))
+        self._check(self.lib.pmub_get_state(self._h, st["freq_old"].ctypes.data, st["dl0"].ctypes.data,
+                                            st["dl1"].ctypes.data, st["state"].ctypes.data), "pmub_get_state")
+        return st
+
+    def set_state(self, st: dict) -> None:
+        a = {k: np.ascontiguousarray(st[k], dtype=np.uint8 if k == "state" else np.float64) for k in
+             ("freq_old", "dl0", "dl1", "state")}
+        self._check(self.lib.pmub_set_state(self._h, a["freq_old"].ctypes.data, a["dl0"].ctypes.data,
+                                            a["dl1"].ctypes.data, a["state"].ctypes.data), "pmub_set_state")
+
+    # -- parity observability -----------------------------------------------
+    def set_debug(self, enable: bool = True) -> None:
+        self._check(self.lib.pmub_set_debug(self._h, 1 if enable else 0), "pmub_set_debug")
+
+    def get_debug(self):
+        """-> (km [n_inst, n_ch], triggered [n_inst, n_ch] bool, spectrum [n_inst, n_ch, n_bins] complex)."""
+        n = self.n_instances * self.n_channels
+        flags = np.empty(n, dtype=np.int32)
+        spec = np.empty((n, self.n_bins, 2))
+        self._check(self.lib.pmub_get_debug(self._h, flags.ctypes.data, spec.ctypes.data), "pmub_get_debug")
+        shape = (self.n_instances, self.n_channels)
+        return ((flags & 0xFFFF).reshape(shape), ((flags >> 16) & 1).astype(bool).reshape(shape),
+                (spec[..., 0] + 1j * spec[..., 1]).reshape(shape + (self.n_bins,)))
+
+
+def shard_instances(n_instances: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Contiguous block of instances owned by ``rank``: rank r owns
+    ``[r*n/G, (r+1)*n/G)``.  No collective is needed on the hot path."""
+    lo = n_instances * rank // world_size
+    hi = n_instances * (rank + 1) // world_size
+    return lo, hi

@@ -1,0 +1,444 @@
+// pmu_core.cu — device-side estimator object and the type-generic C ABI (pmu_batch.h).
+//
+// Owns everything pmu_init malloc'ed in the reference (src/pmu_estimator.c:110-160) — now
+// device tables and per-stream ROCOF state resident in HBM — and launches the fused
+// kernel of pmu_kernel.cuh.  No CPU estimation path exists here: without a CUDA device
+// pmub_create fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "pmu_host.hpp"
+#include "pmu_kernel.cuh"
+
+using pmu::set_error;
+
+#define CUDA_OK(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            set_error(std::string("[pmu] CUDA ERROR: ") + cudaGetErrorString(e__) + " at " #expr); \
+            return -1;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+struct pmub_batch {
+    pmub_config cfg;
+    int dtype;
+    unsigned n_inst, C;
+    int device;
+    pmu::Derived d;
+    pmu::Plan plan;
+    long long n_windows;
+    int num_sms;
+    // device memory
+    pmu_c *dU, *dV, *dT;
+    double *st_fold, *st_dl0, *st_dl1;
+    unsigned char* st_state;
+    unsigned char* d_windows;   // staging for host inputs (lazy)
+    unsigned char* d_mid;
+    unsigned char* d_out;       // frames [n][4] float_p, then export [n][4] double
+    int* d_dbg;
+    double* d_spec;
+    bool debug, mirror;
+    // small-batch pinned staging
+    unsigned char* h_in;
+    unsigned char* h_out;
+    size_t h_in_bytes, h_out_bytes;
+    cudaStream_t stream[2];
+    cudaStream_t user_stream;
+    bool has_user_stream;
+    long long launches;
+    KernelArgs args;
+};
+
+// ---- kernel dispatch: one translation unit per float_p width (pmu_launch.cuh) ----------
+int pmu_launch_f64(int M, int KC, const KernelArgs& a, int grid, int block, int smem, cudaStream_t s);
+int pmu_launch_f32(int M, int KC, const KernelArgs& a, int grid, int block, int smem, cudaStream_t s);
+
+static int grid_for(const pmub_batch* b, long long n)
+{
+    static const int forced = getenv("PMU_GRID") ? atoi(getenv("PMU_GRID")) : 0;
+    if (forced > 0) return forced;
+    long long g = (n + 7) / 8;
+    if (g > b->num_sms) g = b->num_sms;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// Launch the kernel over windows [w0, w1) of the batch (w0 on an instance boundary).
+static int launch_range(pmub_batch* b, long long w0, long long w1, const void* d_windows_base,
+                        const void* d_mid_base, void* d_frames_base, double* d_export_base, cudaStream_t s)
+{
+    if (w1 <= w0) return 0;
+    KernelArgs a = b->args;
+    const size_t sz = (size_t)b->dtype;
+    a.windows = (const unsigned char*)d_windows_base + (size_t)w0 * b->d.N * sz;
+    a.mid = (const unsigned char*)d_mid_base + (size_t)(w0 / b->C) * sz;
+    a.frames = (unsigned char*)d_frames_base + (size_t)w0 * 4 * sz;
+    a.st_fold = b->st_fold + w0;
+    a.st_dl0 = b->st_dl0 + w0;
+    a.st_dl1 = b->st_dl1 + w0;
+    a.st_state = b->st_state + w0;
+    a.n_windows = w1 - w0;
+    a.dbg = b->debug ? b->d_dbg + w0 : nullptr;
+    a.spec_out = b->debug ? b->d_spec + (size_t)w0 * b->cfg.n_bins * 2 : nullptr;
+    a.state_export = d_export_base ? d_export_base + (size_t)w0 * 4 : nullptr;
+    // TMA bulk copies need 16-byte aligned sources; otherwise per-element cp.async
+    const bool ok16 = b->plan.aligned16 && (((uintptr_t)a.windows) % 16 == 0);
+    a.load_mode = ok16 ? PMU_LOAD_BULK : PMU_LOAD_ELEM;
+    static const int force_elem = getenv("PMU_FORCE_ELEM_LOAD") ? atoi(getenv("PMU_FORCE_ELEM_LOAD")) : 0;
+    if (force_elem) a.load_mode = PMU_LOAD_ELEM;
+    const int grid = grid_for(b, a.n_windows);
+    const int block = PMU_WARP * (1 + b->plan.n_cons);
+    int rc = (b->dtype == PMUB_F64) ? pmu_launch_f64(b->plan.M, b->plan.KC, a, grid, block, b->plan.smem_bytes, s)
+                                    : pmu_launch_f32(b->plan.M, b->plan.KC, a, grid, block, b->plan.smem_bytes, s);
+    if (rc == 0) b->launches++;
+    return rc;
+}
+
+static bool is_device_ptr(const void* p)
+{
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static cudaStream_t main_stream(pmub_batch* b) { return b->has_user_stream ? b->user_stream : b->stream[0]; }
+
+static int free_batch(pmub_batch* b)
+{
+    if (!b) return 0;
+    cudaSetDevice(b->device);
+    cudaFree(b->dU); cudaFree(b->dV); cudaFree(b->dT);
+    cudaFree(b->st_fold); cudaFree(b->st_dl0); cudaFree(b->st_dl1); cudaFree(b->st_state);
+    cudaFree(b->d_windows); cudaFree(b->d_mid); cudaFree(b->d_out);
+    cudaFree(b->d_dbg); cudaFree(b->d_spec);
+    if (b->h_in) cudaFreeHost(b->h_in);
+    if (b->h_out) cudaFreeHost(b->h_out);
+    for (int i = 0; i < 2; ++i)
+        if (b->stream[i]) cudaStreamDestroy(b->stream[i]);
+    delete b;
+    return 0;
+}
+
+extern "C" {
+
+const char* pmub_last_error(void) { return pmu::last_error(); }
+int pmub_validate(const pmub_config* cfg)
+{
+    if (!cfg) { set_error("[pmu_init] ERROR: NULL configuration"); return -1; }
+    return pmu::validate(*cfg);
+}
+int pmub_parse_ini(const char* ini_path, pmub_config* out)
+{
+    if (!ini_path || !out) { set_error("[pmu_init] ERROR: NULL argument"); return -1; }
+    return pmu::parse_ini(ini_path, out);
+}
+
+int pmub_reset(pmub_batch* b)
+{
+    if (!b) return -1;
+    CUDA_OK(cudaSetDevice(b->device));
+    const size_t n = (size_t)b->n_windows;
+    std::vector<double> f0(n, (double)b->cfg.f0);  // freq_old = f0, src/pmu_estimator.c:145
+    cudaStream_t s = main_stream(b);
+    CUDA_OK(cudaMemcpyAsync(b->st_fold, f0.data(), n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemsetAsync(b->st_dl0, 0, n * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(b->st_dl1, 0, n * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(b->st_state, 0, n, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_instances, unsigned n_channels, int device)
+{
+    if (!out || !cfg) { set_error("[pmu_init] ERROR: NULL argument"); return -1; }
+    *out = nullptr;
+    if (dtype != PMUB_F32 && dtype != PMUB_F64) { set_error("[pmu_init] ERROR: dtype must be PMUB_F32 or PMUB_F64"); return -1; }
+    if (n_instances < 1 || n_channels < 1) { set_error("[pmu_init] ERROR: number of channels/instances must be at least 1"); return -1; }
+    if (pmu::validate(*cfg)) return -1;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        set_error("[pmu_init] ERROR: no CUDA device available - this library has no CPU estimation path");
+        return -1;
+    }
+    if (device < 0) CUDA_OK(cudaGetDevice(&device));
+    if (device >= ndev) { set_error("[pmu_init] ERROR: CUDA device index out of range"); return -1; }
+    CUDA_OK(cudaSetDevice(device));
+    int cc_major = 0, max_smem = 0, num_sms = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+    if (cc_major != 10) {
+        set_error("[pmu_init] ERROR: the estimator kernels are built for sm_100a (B200) only");
+        return -1;
+    }
+
+    pmub_batch* b = new pmub_batch();
+    memset(b, 0, sizeof *b);
+    b->cfg = *cfg;
+    b->dtype = dtype;
+    b->n_inst = n_instances;
+    b->C = n_channels;
+    b->device = device;
+    b->num_sms = num_sms;
+    b->n_windows = (long long)n_instances * n_channels;
+    b->d = pmu::derive(*cfg, dtype);
+    if (pmu::make_plan(*cfg, dtype, max_smem, &b->plan)) { delete b; return -1; }
+
+    std::vector<pmu_c> U, V, T;
+    pmu::build_tables(b->plan, b->d.N, &U, &V, &T);
+    auto fail = [&]() { free_batch(b); return -1; };
+#define CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_error(std::string("[pmu_init] CUDA ERROR: ") + cudaGetErrorString(e__) + " at " #expr); return fail(); } } while (0)
+    CK(cudaMalloc(&b->dU, U.size() * sizeof(pmu_c)));
+    CK(cudaMalloc(&b->dV, V.size() * sizeof(pmu_c)));
+    CK(cudaMalloc(&b->dT, T.size() * sizeof(pmu_c)));
+    CK(cudaMemcpy(b->dU, U.data(), U.size() * sizeof(pmu_c), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->dV, V.data(), V.size() * sizeof(pmu_c), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->dT, T.data(), T.size() * sizeof(pmu_c), cudaMemcpyHostToDevice));
+    const size_t n = (size_t)b->n_windows;
+    CK(cudaMalloc(&b->st_fold, n * sizeof(double)));
+    CK(cudaMalloc(&b->st_dl0, n * sizeof(double)));
+    CK(cudaMalloc(&b->st_dl1, n * sizeof(double)));
+    CK(cudaMalloc(&b->st_state, n));
+    CK(cudaMalloc(&b->d_out, n * 4 * (size_t)dtype + n * 4 * sizeof(double)));
+    CK(cudaMalloc(&b->d_mid, (size_t)n_instances * dtype));
+    CK(cudaStreamCreateWithFlags(&b->stream[0], cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&b->stream[1], cudaStreamNonBlocking));
+    // small batches (the single-instance pmu_estimate path) go through pinned staging
+    const size_t in_bytes = n * b->d.N * (size_t)dtype + (size_t)n_instances * dtype;
+    if (in_bytes <= (size_t)(4 << 20)) {
+        b->h_in_bytes = in_bytes;
+        b->h_out_bytes = n * 4 * (size_t)dtype + n * 4 * sizeof(double);
+        CK(cudaMallocHost(&b->h_in, b->h_in_bytes));
+        CK(cudaMallocHost(&b->h_out, b->h_out_bytes));
+        CK(cudaMalloc(&b->d_windows, n * b->d.N * (size_t)dtype));
+    }
+#undef CK
+
+    // kernel arguments that never change
+    KernelArgs& a = b->args;
+    memset(&a, 0, sizeof a);
+    PostParams& pp = a.post;
+    const pmu::Derived& d = b->d;
+    pp.K = (int)cfg->n_bins; pp.P = (int)cfg->P; pp.Q = (int)cfg->Q; pp.iter_en = cfg->iter_eipdft ? 1 : 0;
+    pp.jlo = b->plan.jlo; pp.jhi = b->plan.jhi; pp.C = (int)n_channels; pp.f0 = (int)cfg->f0;
+    pp.df = d.df; pp.S = d.S; pp.invS = d.invS; pp.eps = d.eps; pp.invN = 1.0 / (double)d.N;
+    {
+        const long double pi = 3.14159265358979323846264338327950288L;
+        pp.c3q = (double)(-0.25L * cosl(pi / (long double)d.N));  // cos(pi C3) = -cos(pi/N)
+        pp.s3q = (double)(0.25L * sinl(pi / (long double)d.N));   // sin(pi C3) =  sin(pi/N)
+    }
+    pp.frame_rate = (double)cfg->frame_rate;
+    pp.thr0 = d.thr[0]; pp.thr1 = d.thr[1]; pp.thr2 = d.thr[2];
+    pp.lp0 = d.lp[0]; pp.lp1 = d.lp[1]; pp.lp2 = d.lp[2];
+    pp.trig = b->dT;
+    a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
+    a.n_stage = b->plan.n_stage; a.stage_bytes = b->plan.stage_bytes; a.n_cons = b->plan.n_cons;
+    a.n_raw = b->plan.n_raw; a.raw_stride = b->plan.raw_stride; a.n_post = b->plan.n_post;
+    a.n_u = b->plan.n_u; a.scratch_global = 0;
+    a.off_ctrl = b->plan.off_ctrl; a.off_U = b->plan.off_U; a.off_V = b->plan.off_V; a.off_trig = b->plan.off_trig;
+    a.off_raw = b->plan.off_raw; a.off_post = b->plan.off_post; a.off_stage = b->plan.off_stage;
+    a.U = b->dU; a.V = b->dV; a.trig = b->dT; a.scratch = nullptr;
+
+    if (pmub_reset(b)) { free_batch(b); return -1; }
+    *out = b;
+    return 0;
+}
+
+int pmub_create_ini(pmub_batch** out, const char* ini_path, int dtype, unsigned n_instances, unsigned n_channels, int device)
+{
+    pmub_config cfg;
+    if (pmub_parse_ini(ini_path, &cfg)) return -1;
+    return pmub_create(out, &cfg, dtype, n_instances, n_channels, device);
+}
+
+int pmub_destroy(pmub_batch* b)
+{
+    if (!b) { set_error("[pmu_deinit] ERROR: NULL batch"); return -1; }
+    return free_batch(b);
+}
+
+int pmub_get_info(const pmub_batch* b, pmub_info* o)
+{
+    if (!b || !o) return -1;
+    memset(o, 0, sizeof *o);
+    o->win_len = b->d.N; o->n_bins = b->cfg.n_bins; o->n_instances = b->n_inst; o->n_channels = b->C;
+    o->dtype = b->dtype; o->device = b->device; o->df = b->d.df; o->norm_factor = b->d.S;
+    o->dft_radix = b->plan.M; o->dft_bins = b->plan.KC; o->n_stages = b->plan.n_stage;
+    o->stage_bytes = b->plan.stage_bytes; o->slabs_per_window = b->plan.nslab;
+    o->load_mode = b->plan.aligned16 ? PMU_LOAD_BULK : PMU_LOAD_ELEM;
+    o->grid = grid_for(b, b->n_windows); o->block = PMU_WARP * (1 + b->plan.n_cons);
+    o->smem_bytes = b->plan.smem_bytes;
+    o->bytes_per_estimate = pmu::bytes_per_estimate(b->d.N, b->dtype, b->C);
+    return 0;
+}
+
+int pmub_set_stream(pmub_batch* b, void* cuda_stream)
+{
+    if (!b) return -1;
+    b->has_user_stream = cuda_stream != nullptr;
+    b->user_stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+long long pmub_launch_count(const pmub_batch* b) { return b ? b->launches : 0; }
+
+int pmub_sync(pmub_batch* b)
+{
+    if (!b) return -1;
+    CUDA_OK(cudaSetDevice(b->device));
+    if (b->has_user_stream) CUDA_OK(cudaStreamSynchronize(b->user_stream));
+    CUDA_OK(cudaStreamSynchronize(b->stream[0]));
+    CUDA_OK(cudaStreamSynchronize(b->stream[1]));
+    return 0;
+}
+
+int pmub_estimate_async(pmub_batch* b, const void* d_windows, const void* d_mid, void* d_frames)
+{
+    if (!b || !d_windows || !d_mid || !d_frames) { set_error("[pmu_estimate] ERROR: NULL argument"); return -1; }
+    CUDA_OK(cudaSetDevice(b->device));
+    return launch_range(b, 0, b->n_windows, d_windows, d_mid, d_frames, nullptr, main_stream(b));
+}
+
+int pmub_estimate(pmub_batch* b, const void* windows, const void* mid, void* frames)
+{
+    if (!b || !windows || !mid || !frames) { set_error("[pmu_estimate] ERROR: NULL argument"); return -1; }
+    CUDA_OK(cudaSetDevice(b->device));
+    const size_t sz = (size_t)b->dtype;
+    const size_t n = (size_t)b->n_windows;
+    const size_t win_bytes = n * b->d.N * sz, mid_bytes = (size_t)b->n_inst * sz, fr_bytes = n * 4 * sz;
+    const bool win_dev = is_device_ptr(windows), mid_dev = is_device_ptr(mid), fr_dev = is_device_ptr(frames);
+    double* d_export = reinterpret_cast<double*>(b->d_out + fr_bytes);
+
+    if (win_dev && mid_dev && fr_dev && !b->mirror) {
+        if (launch_range(b, 0, b->n_windows, windows, mid, frames, nullptr, main_stream(b))) return -1;
+        CUDA_OK(cudaStreamSynchronize(main_stream(b)));
+        return 0;
+    }
+
+    // ---- small batch, host buffers: one pinned round trip (the pmu_estimate path) ----
+    if (b->h_in && !win_dev && !mid_dev && !fr_dev) {
+        cudaStream_t s = main_stream(b);
+        memcpy(b->h_in, windows, win_bytes);
+        memcpy(b->h_in + win_bytes, mid, mid_bytes);
+        CUDA_OK(cudaMemcpyAsync(b->d_windows, b->h_in, win_bytes, cudaMemcpyHostToDevice, s));
+        CUDA_OK(cudaMemcpyAsync(b->d_mid, b->h_in + win_bytes, mid_bytes, cudaMemcpyHostToDevice, s));
+        if (launch_range(b, 0, b->n_windows, b->d_windows, b->d_mid, b->d_out, b->mirror ? d_export : nullptr, s)) return -1;
+        const size_t back = b->mirror ? b->h_out_bytes : fr_bytes;
+        CUDA_OK(cudaMemcpyAsync(b->h_out, b->d_out, back, cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+        memcpy(frames, b->h_out, fr_bytes);
+        return 0;
+    }
+
+    // ---- general path: chunk by instance, copies overlapped with kernels on two streams ----
+    if (!win_dev && !b->d_windows) CUDA_OK(cudaMalloc(&b->d_windows, win_bytes));
+    const unsigned char* dW = win_dev ? (const unsigned char*)windows : b->d_windows;
+    const unsigned char* dM = mid_dev ? (const unsigned char*)mid : b->d_mid;
+    unsigned char* dF = fr_dev ? (unsigned char*)frames : b->d_out;
+    int n_chunks = 1;
+    if (!win_dev) {
+        const size_t target = 32u << 20;  // ~32 MiB of samples per chunk
+        n_chunks = (int)((win_bytes + target - 1) / target);
+        if (n_chunks < 1) n_chunks = 1;
+        if (n_chunks > 64) n_chunks = 64;
+        if ((unsigned)n_chunks > b->n_inst) n_chunks = (int)b->n_inst;
+    }
+    if (!mid_dev) CUDA_OK(cudaMemcpyAsync(b->d_mid, mid, mid_bytes, cudaMemcpyHostToDevice, main_stream(b)));
+    if (!mid_dev && !b->has_user_stream) CUDA_OK(cudaStreamSynchronize(main_stream(b)));
+    for (int c = 0; c < n_chunks; ++c) {
+        cudaStream_t s = b->has_user_stream ? b->user_stream : b->stream[c & 1];
+        const long long i0 = (long long)b->n_inst * c / n_chunks, i1 = (long long)b->n_inst * (c + 1) / n_chunks;
+        const long long w0 = i0 * b->C, w1 = i1 * b->C;
+        if (!win_dev)
+            CUDA_OK(cudaMemcpyAsync(b->d_windows + (size_t)w0 * b->d.N * sz, (const unsigned char*)windows + (size_t)w0 * b->d.N * sz,
+                                    (size_t)(w1 - w0) * b->d.N * sz, cudaMemcpyHostToDevice, s));
+        if (launch_range(b, w0, w1, dW, dM, dF, b->mirror ? d_export : nullptr, s)) return -1;
+        if (!fr_dev)
+            CUDA_OK(cudaMemcpyAsync((unsigned char*)frames + (size_t)w0 * 4 * sz, dF + (size_t)w0 * 4 * sz, (size_t)(w1 - w0) * 4 * sz,
+                                    cudaMemcpyDeviceToHost, s));
+    }
+    return pmub_sync(b);
+}
+
+int pmub_get_state(pmub_batch* b, double* freq_old, double* dl0, double* dl1, unsigned char* state)
+{
+    if (!b) return -1;
+    CUDA_OK(cudaSetDevice(b->device));
+    if (pmub_sync(b)) return -1;
+    const size_t n = (size_t)b->n_windows;
+    if (freq_old) CUDA_OK(cudaMemcpy(freq_old, b->st_fold, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (dl0) CUDA_OK(cudaMemcpy(dl0, b->st_dl0, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (dl1) CUDA_OK(cudaMemcpy(dl1, b->st_dl1, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (state) CUDA_OK(cudaMemcpy(state, b->st_state, n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int pmub_set_state(pmub_batch* b, const double* freq_old, const double* dl0, const double* dl1, const unsigned char* state)
+{
+    if (!b) return -1;
+    CUDA_OK(cudaSetDevice(b->device));
+    if (pmub_sync(b)) return -1;
+    const size_t n = (size_t)b->n_windows;
+    if (freq_old) CUDA_OK(cudaMemcpy(b->st_fold, freq_old, n * sizeof(double), cudaMemcpyHostToDevice));
+    if (dl0) CUDA_OK(cudaMemcpy(b->st_dl0, dl0, n * sizeof(double), cudaMemcpyHostToDevice));
+    if (dl1) CUDA_OK(cudaMemcpy(b->st_dl1, dl1, n * sizeof(double), cudaMemcpyHostToDevice));
+    if (state) CUDA_OK(cudaMemcpy(b->st_state, state, n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int pmub_set_debug(pmub_batch* b, int enable)
+{
+    if (!b) return -1;
+    CUDA_OK(cudaSetDevice(b->device));
+    if (enable && !b->d_dbg) {
+        const size_t n = (size_t)b->n_windows;
+        CUDA_OK(cudaMalloc(&b->d_dbg, n * sizeof(int)));
+        CUDA_OK(cudaMalloc(&b->d_spec, n * b->cfg.n_bins * 2 * sizeof(double)));
+        CUDA_OK(cudaMemset(b->d_dbg, 0, n * sizeof(int)));
+        CUDA_OK(cudaMemset(b->d_spec, 0, n * b->cfg.n_bins * 2 * sizeof(double)));
+    }
+    b->debug = enable != 0;
+    return 0;
+}
+
+int pmub_get_debug(pmub_batch* b, int* flags, double* spectrum)
+{
+    if (!b || !b->d_dbg) { set_error("[pmu] ERROR: debug recording is not enabled"); return -1; }
+    CUDA_OK(cudaSetDevice(b->device));
+    if (pmub_sync(b)) return -1;
+    const size_t n = (size_t)b->n_windows;
+    if (flags) CUDA_OK(cudaMemcpy(flags, b->d_dbg, n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (spectrum) CUDA_OK(cudaMemcpy(spectrum, b->d_spec, n * b->cfg.n_bins * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+/* Mirror of the ROCOF state for the single-instance drop-in API: after a synchronous
+ * pmub_estimate with host buffers, pmub_mirror() points at [n][4] doubles
+ * {freq_old, dl0, dl1, state}.  Internal to libpmu_estimator (used by pmu_capi.c). */
+int pmub_set_mirror(pmub_batch* b, int enable)
+{
+    if (!b) return -1;
+    if (enable && !b->h_out) { set_error("[pmu] ERROR: state mirroring needs a small batch"); return -1; }
+    b->mirror = enable != 0;
+    return 0;
+}
+const double* pmub_mirror(const pmub_batch* b)
+{
+    if (!b || !b->mirror) return nullptr;
+    return reinterpret_cast<const double*>(b->h_out + (size_t)b->n_windows * 4 * (size_t)b->dtype);
+}
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+// pmu_dft.cuh — output-pruned real DFT of one sample window, lane-parallel.
+//
+// Replaces the reference's pmue_fft_r -> dft_r (src/pmu_estimator.c:487-546: a
+// recursive radix-2 FFT of ALL N bins for power-of-two N, a direct n_bins x N DFT
+// otherwise) and the time-domain Hann multiply (:184-191).  Only bins 0..n_bins-1 are
+// ever read by the estimator (:589-592, :212-221), so with N = L*M (M a small power of
+// two) we compute, for the KC lowest bins of the RECTANGULAR-window spectrum,
+//
+//     X[k] = sum_{a<L} W_N^{a k} * Y_a[k mod M],      Y_a = real DFT_M( x[a + L b], b<M )
+//
+// Lane l of a warp owns the residues a = l + 32 i.  Per residue it runs an M-point real
+// FFT codelet in registers (compile-time twiddles), multiplies by the lane-uniform
+// twiddle W_N^{32 i k} (shared-memory broadcast) and accumulates; after the last residue
+// the sum is rotated by the lane twiddle W_N^{l k}.  The 32 partial spectra are then
+// summed by a transposing butterfly (pmu_kernel.cu).  The Hann window is applied
+// afterwards in the frequency domain, exact for the periodic Hann of :556:
+//     Xw[k] = X[k]/2 - (X[k-1] + X[k+1])/4,   X[-1] = conj X[1],
+// which is why KC must cover n_bins + 1 bins.  The same code is the mixed-radix path for
+// non-power-of-two windows (3072 = 192*16, 600 = 75*8, odd N: M = 1 = direct DFT).
+#pragma once
+
+#include "pmu_math.cuh"
+
+// ---- compile-time loop ---------------------------------------------------------
+template <int I>
+struct IC {
+    static constexpr int value = I;
+};
+template <int B, int E, class F>
+PMU_HD void static_for(F&& f)
+{
+    if constexpr (B < E) {
+        f(IC<B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+// cos(2 pi k/16), k = 0..15
+PMU_HD constexpr double cos16(int k)
+{
+    constexpr double c1 = 0.92387953251128675613, c2 = 0.70710678118654752440, c3 = 0.38268343236508977173;
+    switch (k & 15) {
+        case 0: return 1.0;
+        case 1: case 15: return c1;
+        case 2: case 14: return c2;
+        case 3: case 13: return c3;
+        case 4: case 12: return 0.0;
+        case 5: case 11: return -c3;
+        case 6: case 10: return -c2;
+        case 7: case 9: return -c1;
+        default: return -1.0;
+    }
+}
+PMU_HD constexpr double sin16(int k) { return cos16(k - 4); }
+
+// (tr, ti) = W_M^K * (orr, oi),  W_M = exp(-2 pi i / M), M | 16; trivial twiddles cost nothing.
+template <int K, int M>
+PMU_HD void tw_mul(double orr, double oi, double* tr, double* ti)
+{
+    constexpr int k16 = (K * (16 / M)) & 15;
+    if constexpr (k16 == 0) { *tr = orr; *ti = oi; }
+    else if constexpr (k16 == 4) { *tr = oi; *ti = -orr; }        // -i
+    else if constexpr (k16 == 8) { *tr = -orr; *ti = -oi; }       // -1
+    else if constexpr (k16 == 12) { *tr = -oi; *ti = orr; }       // +i
+    else {
+        constexpr double wr = cos16(k16), wi = -sin16(k16);
+        *tr = wr * orr - wi * oi;
+        *ti = wr * oi + wi * orr;
+    }
+}
+
+// Real-input FFT codelet: x[0..M) -> bins 0..M/2 (re[], im[]).  Radix-2 decimation in
+// time on real data, conjugate symmetry of the half-size transforms used throughout.
+template <int M>
+struct RFFT {
+    static_assert(M == 1 || M == 2 || M == 4 || M == 8 || M == 16, "codelet sizes");
+    PMU_HD static void run(const double* x, double* re, double* im)
+    {
+        if constexpr (M == 1) {
+            re[0] = x[0]; im[0] = 0.0;
+        } else if constexpr (M == 2) {
+            re[0] = x[0] + x[1]; im[0] = 0.0;
+            re[1] = x[0] - x[1]; im[1] = 0.0;
+        } else {
+            constexpr int H = M / 2;
+            double ev[H], od[H];
+            static_for<0, H>([&](auto i) {
+                ev[i.value] = x[2 * i.value];
+                od[i.value] = x[2 * i.value + 1];
+            });
+            double er[H / 2 + 1], ei[H / 2 + 1], qr[H / 2 + 1], qi[H / 2 + 1];
+            RFFT<H>::run(ev, er, ei);
+            RFFT<H>::run(od, qr, qi);
+            static_for<0, H + 1>([&](auto kc) {
+                constexpr int k = kc.value;
+                constexpr int kk = (k <= H / 2) ? k : H - k;
+                constexpr bool cj = (k > H / 2);
+                // E[0], E[H/2], O[0], O[H/2] are real by symmetry: drop their zero parts
+                constexpr bool real_in = (kk == 0) || (2 * kk == H);
+                double Er = er[kk], Ei = real_in ? 0.0 : (cj ? -ei[kk] : ei[kk]);
+                double Or = qr[kk], Oi = real_in ? 0.0 : (cj ? -qi[kk] : qi[kk]);
+                if constexpr (real_in) {
+                    constexpr int k16 = (k * (16 / M)) & 15;
+                    if constexpr (k16 == 0) { re[k] = Er + Or; im[k] = 0.0; }
+                    else if constexpr (k16 == 8) { re[k] = Er - Or; im[k] = 0.0; }
+                    else if constexpr (k16 == 4) { re[k] = Er; im[k] = -Or; }
+                    else {
+                        constexpr double wr = cos16(k16), wi = -sin16(k16);
+                        re[k] = Er + wr * Or; im[k] = wi * Or;
+                    }
+                } else {
+                    double tr, ti;
+                    tw_mul<k, M>(Or, Oi, &tr, &ti);
+                    re[k] = Er + tr; im[k] = Ei + ti;
+                }
+            });
+        }
+    }
+};
+
+// Bin k (compile-time) of the M-periodic, conjugate-symmetric codelet output.
+template <int K, int M>
+PMU_HD void ysel(const double* re, const double* im, double* yr, double* yi, bool* is_real)
+{
+    constexpr int r = K % M;
+    constexpr int idx = (r <= M / 2) ? r : M - r;
+    constexpr bool cj = (r > M / 2);
+    *yr = re[idx];
+    *yi = cj ? -im[idx] : im[idx];
+    *is_real = (idx == 0) || (2 * idx == M);
+}
+
+// Accumulate one residue: acc[k] (+)= U[k] * Y[k mod M], k < KC.
+//   FIRST : U == 1 for every k (i == 0), acc is initialised instead of accumulated.
+//   u     : lane-uniform twiddles W_N^{32 i k} (broadcast loads), ignored when FIRST.
+template <int M, int KC, bool FIRST>
+PMU_HD void accumulate_residue(const double* x, const pmu_c* u, double* ar, double* ai)
+{
+    double re[M / 2 + 1], im[M / 2 + 1];
+    RFFT<M>::run(x, re, im);
+    static_for<0, KC>([&](auto kc) {
+        constexpr int k = kc.value;
+        double yr, yi;
+        bool rl;
+        ysel<k, M>(re, im, &yr, &yi, &rl);
+        constexpr int r = k % M;
+        constexpr bool is_real = (r == 0) || (2 * r == M) || (M == 1);
+        if constexpr (FIRST) {
+            ar[k] = yr;
+            ai[k] = is_real ? 0.0 : yi;
+        } else if constexpr (k == 0) {
+            ar[0] += yr;  // W^0 = 1, Y[0] real
+        } else {
+            pmu_c w = u[k];
+            if constexpr (is_real) {
+                ar[k] += w.x * yr;
+                ai[k] += w.y * yr;
+            } else {
+                ar[k] += w.x * yr - w.y * yi;
+                ai[k] += w.x * yi + w.y * yr;
+            }
+        }
+    });
+}
+
+// Rotate the lane's partial spectrum by its own twiddle V[k] = W_N^{lane k}.
+template <int KC>
+PMU_HD void rotate_lane(const pmu_c* v, int v_stride, double* ar, double* ai)
+{
+    static_for<1, KC>([&](auto kc) {
+        constexpr int k = kc.value;
+        pmu_c w = v[k * v_stride];
+        double r = ar[k] * w.x - ai[k] * w.y;
+        double i = ar[k] * w.y + ai[k] * w.x;
+        ar[k] = r;
+        ai[k] = i;
+    });
+}
+
+// Hann window in the frequency domain: windowed bin k from rectangular bins k-1, k, k+1
+// (rect[-1] = conj rect[1]).  raw = interleaved re,im of the rectangular bins 0..K.
+PMU_HD pmu_c hann_combine(const double* raw, int k)
+{
+    double lr, li;
+    if (k == 0) { lr = raw[2]; li = -raw[3]; }
+    else { lr = raw[2 * (k - 1)]; li = raw[2 * (k - 1) + 1]; }
+    pmu_c o;
+    o.x = 0.5 * raw[2 * k] - 0.25 * (lr + raw[2 * (k + 1)]);
+    o.y = 0.5 * raw[2 * k + 1] - 0.25 * (li + raw[2 * (k + 1) + 1]);
+    return o;
+}

@@ -1,0 +1,355 @@
+// pmu_host.cpp — see pmu_host.hpp.
+#include "pmu_host.hpp"
+
+#include <ctype.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+
+namespace pmu {
+
+static thread_local std::string g_err;
+
+void set_error(const std::string& msg)
+{
+    g_err = msg;
+    // LOGGING_LEVEL ERROR behaviour of the reference (src/pmu_estimator.c:38-42)
+    fprintf(stderr, "%s\n", msg.c_str());
+}
+const char* last_error() { return g_err.c_str(); }
+
+// ---- check_config_validity, src/pmu_estimator.c:386-449 (same order of checks) ----
+int validate(const pmub_config& c)
+{
+    char buf[320];
+    if (c.f0 != 50 && c.f0 != 60) {
+        snprintf(buf, sizeof buf, "[pmu_init] ERROR: nominal frequency: %u not correctly set, (allowed values 50 or 60)", c.f0);
+        set_error(buf);
+        return -1;
+    }
+    if (c.n_cycles == 0 || c.n_cycles > 50) {
+        snprintf(buf, sizeof buf, "[pmu_init] ERROR: window length: %u cycles is not correctly set, must be in 1..50", c.n_cycles);
+        set_error(buf);
+        return -1;
+    }
+    if (c.fs == 0 || fmod((double)c.fs, (double)c.f0) != 0.0) {
+        snprintf(buf, sizeof buf, "[pmu_init] ERROR: sample rate: %u is not correctly set, must be a positive multiple of f0: %u", c.fs, c.f0);
+        set_error(buf);
+        return -1;
+    }
+    if (c.frame_rate == 0) {
+        snprintf(buf, sizeof buf, "[pmu_init] ERROR: frame rate: %u is not correctly set, must be positive", c.frame_rate);
+        set_error(buf);
+        return -1;
+    }
+    const unsigned half = (c.n_cycles * c.fs / c.f0) / 2;  // unsigned arithmetic, :411
+    if (c.n_bins < c.n_cycles + 2 || c.n_bins > half) {
+        snprintf(buf, sizeof buf,
+                 "[pmu_init] ERROR: number of dft bins: %u is not correctly set, must be >= (number of cycles + 2): %u and <= half the window length: %u",
+                 c.n_bins, c.n_cycles + 2, half);
+        set_error(buf);
+        return -1;
+    }
+    if (c.P == 0) {
+        set_error("[pmu_init] ERROR: ipdft iterations: 0 is not correctly set, must be positive");
+        return -1;
+    }
+    if (!(c.interf_trig > 0) || c.interf_trig > 1) {
+        snprintf(buf, sizeof buf, "[pmu_init] ERROR: interference threshold: %f is not correctly set, must be in ]0,1]", c.interf_trig);
+        set_error(buf);
+        return -1;
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (!(c.rocof_thresh[i] > 0)) {
+            snprintf(buf, sizeof buf, "[pmu_init] ERROR: rocof threshold %d: %f is not set, must be positive", i + 1, c.rocof_thresh[i]);
+            set_error(buf);
+            return -1;
+        }
+    }
+    return 0;
+}
+
+// ---- .ini reader with the line rules of the reference's vendored iniparser ------------
+// (libs/iniparser/iniparser.c:620-700 iniparser_line, :714-820 iniparser_load,
+//  :491-566 getint/getdouble/getboolean).  Any syntax error rejects the whole file.
+static std::string strip(const std::string& s)
+{
+    size_t b = 0, e = s.size();
+    while (b < e && isspace((unsigned char)s[b])) ++b;
+    while (e > b && isspace((unsigned char)s[e - 1])) --e;
+    return s.substr(b, e - b);
+}
+static std::string lower(std::string s)
+{
+    for (auto& ch : s) ch = (char)tolower((unsigned char)ch);
+    return s;
+}
+
+static int load_ini(const char* path, std::map<std::string, std::string>* dict)
+{
+    FILE* in = fopen(path, "r");
+    if (!in) {
+        set_error(std::string("[pmu_init] ERROR: cannot open ini file: ") + path);
+        return -1;
+    }
+    std::string section, pending;
+    char raw[2048];
+    int lineno = 0, errs = 0;
+    while (fgets(raw, sizeof raw, in)) {
+        ++lineno;
+        std::string line = pending + raw;
+        pending.clear();
+        while (!line.empty() && (line.back() == '\n' || isspace((unsigned char)line.back()))) line.pop_back();
+        if (!line.empty() && line.back() == '\\') {  // multi-line value
+            line.pop_back();
+            pending = line;
+            continue;
+        }
+        line = strip(line);
+        if (line.empty() || line[0] == '#' || line[0] == ';') continue;
+        if (line[0] == '[' && line.back() == ']') {
+            size_t close = line.find(']');
+            section = lower(strip(line.substr(1, close - 1)));
+            continue;
+        }
+        size_t eq = line.find('=');
+        if (eq == std::string::npos || eq == 0) {
+            fprintf(stderr, "ini: syntax error in %s (%d):\n-> %s\n", path, lineno, line.c_str());
+            ++errs;
+            continue;
+        }
+        std::string key = lower(strip(line.substr(0, eq)));
+        std::string rest = line.substr(eq + 1);
+        size_t p = 0;
+        while (p < rest.size() && isspace((unsigned char)rest[p])) ++p;
+        std::string val;
+        if (p < rest.size() && (rest[p] == '"' || rest[p] == '\'')) {
+            const char qc = rest[p];
+            size_t q = rest.find(qc, p + 1);
+            if (q != std::string::npos && q > p + 1) {
+                val = rest.substr(p + 1, q - p - 1);  // quoted: kept verbatim
+            } else {
+                // "" / '' or an unterminated quote: handled like an unquoted value
+                size_t stop = rest.find_first_of(";#", p);
+                val = strip(rest.substr(p, stop == std::string::npos ? std::string::npos : stop - p));
+                if (val == "\"\"" || val == "''") val.clear();
+            }
+        } else {
+            size_t stop = rest.find_first_of(";#", p);
+            val = strip(rest.substr(p, stop == std::string::npos ? std::string::npos : stop - p));
+        }
+        (*dict)[section + ":" + key] = val;
+    }
+    fclose(in);
+    if (errs) {
+        set_error(std::string("[pmu_init] ERROR: cannot parse file: ") + path);
+        return -1;
+    }
+    return 0;
+}
+
+static long ini_int(const std::map<std::string, std::string>& d, const char* k)
+{
+    auto it = d.find(k);
+    return it == d.end() ? 0 : strtol(it->second.c_str(), nullptr, 0);
+}
+static double ini_double(const std::map<std::string, std::string>& d, const char* k)
+{
+    auto it = d.find(k);
+    return it == d.end() ? 0.0 : atof(it->second.c_str());
+}
+static int ini_bool(const std::map<std::string, std::string>& d, const char* k)
+{
+    auto it = d.find(k);
+    if (it == d.end() || it->second.empty()) return 0;
+    const char ch = it->second[0];
+    return (ch == 'y' || ch == 'Y' || ch == '1' || ch == 't' || ch == 'T') ? 1 : 0;
+}
+
+// config_from_file, src/pmu_estimator.c:451-484 (missing keys read as 0 and are then
+// rejected by validate()).
+int parse_ini(const char* path, pmub_config* out)
+{
+    std::map<std::string, std::string> d;
+    if (load_ini(path, &d)) return -1;
+    memset(out, 0, sizeof *out);
+    out->n_cycles = (unsigned)(int)ini_int(d, "signal:n_cycles");
+    out->fs = (unsigned)(int)ini_int(d, "signal:sample_rate");
+    out->f0 = (unsigned)(int)ini_int(d, "signal:nominal_freq");
+    out->frame_rate = (unsigned)(int)ini_int(d, "synchrophasor:frame_rate");
+    out->n_bins = (unsigned)(int)ini_int(d, "synchrophasor:number_of_dft_bins");
+    out->P = (unsigned)(int)ini_int(d, "synchrophasor:ipdft_iterations");
+    out->Q = (unsigned)(int)ini_int(d, "synchrophasor:iter_e_ipdft_iterations");
+    out->interf_trig = ini_double(d, "synchrophasor:interference_threshold");
+    out->iter_eipdft = (unsigned)ini_bool(d, "synchrophasor:iter_e_ipdft_enable");
+    out->rocof_thresh[0] = ini_double(d, "rocof:threshold_1");
+    out->rocof_thresh[1] = ini_double(d, "rocof:threshold_2");
+    out->rocof_thresh[2] = ini_double(d, "rocof:threshold_3");
+    out->rocof_low_pass_coeffs[0] = ini_double(d, "rocof:low_pass_filter_1");
+    out->rocof_low_pass_coeffs[1] = ini_double(d, "rocof:low_pass_filter_2");
+    out->rocof_low_pass_coeffs[2] = ini_double(d, "rocof:low_pass_filter_3");
+    return 0;
+}
+
+// ---- derived constants -----------------------------------------------------------------
+template <typename T>
+static double hann_sum(unsigned n)  // hann(), src/pmu_estimator.c:549-560: sequential sum in float_p
+{
+    T sum = 0;
+    for (unsigned i = 0; i < n; ++i) {
+        T w = (T)(0.5 * (1 - cos(2 * M_PI * i / n)));
+        sum += w;
+    }
+    return (double)sum;
+}
+
+Derived derive(const pmub_config& c, int dtype)
+{
+    Derived d;
+    d.N = win_len(c);
+    if (dtype == PMUB_F32) {
+        d.df = (double)((float)c.fs / (float)d.N);             // :366 in float_p
+        d.S = hann_sum<float>(d.N);
+        d.invS = (double)(float)(1.0 / d.S);                   // :160
+        d.eps = (double)(float)c.interf_trig;
+        for (int i = 0; i < 3; ++i) {
+            d.thr[i] = (double)(float)c.rocof_thresh[i];
+            d.lp[i] = (double)(float)c.rocof_low_pass_coeffs[i];
+        }
+    } else {
+        d.df = (double)c.fs / (double)d.N;
+        d.S = hann_sum<double>(d.N);
+        d.invS = 1.0 / d.S;
+        d.eps = c.interf_trig;
+        for (int i = 0; i < 3; ++i) {
+            d.thr[i] = c.rocof_thresh[i];
+            d.lp[i] = c.rocof_low_pass_coeffs[i];
+        }
+    }
+    return d;
+}
+
+// ---- launch plan -------------------------------------------------------------------------
+static int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+static int env_int(const char* name, int dflt)
+{
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
+{
+    Plan p;
+    memset(&p, 0, sizeof p);
+    const int N = (int)win_len(c);
+    const int K = (int)c.n_bins;
+    const int s = dtype;
+    p.Kp = K + 1;
+    if (p.Kp <= 8) p.KC = 8;
+    else if (p.Kp <= 12) p.KC = 12;
+    else if (p.Kp <= 16) p.KC = 16;
+    else if (p.Kp <= 24) p.KC = 24;
+    else {
+        set_error("[pmu_init] ERROR: number of dft bins > 23 is not supported by this build of the CUDA estimator");
+        return -1;
+    }
+    // codelet size: largest supported power of two dividing N that still leaves >= 32 residues
+    const int cand[4] = {16, 8, 4, 1};
+    p.M = 1;
+    for (int m : cand)
+        if (N % m == 0 && (N / m >= 32 || m == 1)) { p.M = m; break; }
+    p.L = N / p.M;
+
+    const int stage_target = env_int("PMU_STAGE_BYTES", 16384);
+    if (N * s <= stage_target) {
+        p.W = p.L;
+        p.nslab = 1;
+        p.stage_bytes = align_up(N * s, 128);
+    } else {
+        int w = stage_target / (p.M * s) / 32 * 32;
+        if (w < 32) w = 32;
+        if (w > p.L) w = align_up(p.L, 32);
+        p.W = w;
+        p.nslab = (p.L + w - 1) / w;
+        p.stage_bytes = align_up(p.M * w * s, 128);
+        if (p.nslab == 1) p.W = p.L, p.stage_bytes = align_up(N * s, 128);
+    }
+    p.aligned16 = ((N * s) % 16 == 0) && (p.nslab == 1 || ((p.L * s) % 16 == 0 && (p.W * s) % 16 == 0));
+
+    p.n_cons = env_int("PMU_CONSUMER_WARPS", PMU_MAX_CONSUMERS);
+    if (p.n_cons < 1) p.n_cons = 1;
+    if (p.n_cons > PMU_MAX_CONSUMERS) p.n_cons = PMU_MAX_CONSUMERS;
+    p.n_raw = env_int("PMU_RAW_BUFFERS", 4);
+    if (p.n_raw < 2) p.n_raw = 2;
+    if (p.n_raw > PMU_MAX_RAW) p.n_raw = PMU_MAX_RAW;
+    p.n_post = env_int("PMU_POST_SLOTS", 4);
+    if (p.n_post < 1) p.n_post = 1;
+    if (p.n_post > PMU_MAX_POST) p.n_post = PMU_MAX_POST;
+    p.raw_stride = 2 * p.Kp + 1;  // odd number of doubles: lane-per-window reads stay conflict-free
+    const int n_groups = (p.nslab == 1) ? (p.L + 31) / 32 : (p.nslab - 1) * (p.W / 32) + ((p.L - (p.nslab - 1) * p.W) + 31) / 32;
+    p.n_u = n_groups * p.KC;
+    p.jlo = K + 2;
+    p.jhi = 2 * K + 1;
+
+    int off = 0;
+    p.off_ctrl = off; off += align_up((int)sizeof(CtrlBlock), 128);
+    p.off_U = off;    off += align_up(p.n_u * 16, 128);
+    p.off_V = off;    off += align_up(p.KC * 32 * 16, 128);
+    p.off_trig = off; off += align_up((p.jlo + p.jhi + 1) * 16, 128);
+    p.off_raw = off;  off += align_up(p.n_raw * 32 * p.raw_stride * 8, 128);
+    p.off_post = off; off += align_up(p.n_post * 2 * K * 32 * 16, 128);
+    p.off_stage = off;
+    const int avail = max_smem - off;
+    int ns = avail / p.stage_bytes;
+    const int ns_cap = env_int("PMU_STAGES", PMU_MAX_STAGES);
+    if (ns > ns_cap) ns = ns_cap;
+    if (ns > PMU_MAX_STAGES) ns = PMU_MAX_STAGES;
+    if (ns < 2) {
+        set_error("[pmu_init] ERROR: configuration does not fit the shared-memory budget of the CUDA estimator (window too long or too many bins)");
+        return -1;
+    }
+    p.n_stage = ns;
+    p.smem_bytes = off + ns * p.stage_bytes;
+    *out = p;
+    return 0;
+}
+
+void build_tables(const Plan& p, unsigned N, std::vector<pmu_c>* U, std::vector<pmu_c>* V, std::vector<pmu_c>* trig)
+{
+    const long double two_pi = 2.0L * 3.14159265358979323846264338327950288L;
+    auto w = [&](unsigned long long idx) {  // W_N^idx = exp(-2 pi i idx / N), index reduced exactly
+        unsigned long long r = idx % N;
+        long double ang = two_pi * (long double)r / (long double)N;
+        pmu_c o;
+        o.x = (double)cosl(ang);
+        o.y = (double)(-sinl(ang));
+        return o;
+    };
+    const int n_groups = p.n_u / p.KC;
+    U->resize((size_t)p.n_u);
+    for (int g = 0; g < n_groups; ++g)
+        for (int k = 0; k < p.KC; ++k) (*U)[(size_t)g * p.KC + k] = w(32ull * (unsigned long long)g * (unsigned long long)k);
+    V->resize((size_t)p.KC * 32);
+    for (int k = 0; k < p.KC; ++k)
+        for (int l = 0; l < 32; ++l) (*V)[(size_t)k * 32 + l] = w((unsigned long long)l * (unsigned long long)k);
+    trig->resize((size_t)(p.jlo + p.jhi + 1));
+    for (int j = -p.jlo; j <= p.jhi; ++j) {
+        long double ang = 3.14159265358979323846264338327950288L * (long double)j / (long double)N;
+        pmu_c o;
+        o.x = (double)cosl(ang);
+        o.y = (double)sinl(ang);
+        (*trig)[(size_t)(j + p.jlo)] = o;
+    }
+}
+
+double bytes_per_estimate(unsigned N, int dtype, unsigned n_channels)
+{
+    const double s = dtype;
+    return N * s + 4 * s + 2 * (3 * s + 1) + s / (double)n_channels;
+}
+
+}  // namespace pmu

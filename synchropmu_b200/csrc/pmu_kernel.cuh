@@ -1,0 +1,452 @@
+// pmu_kernel.cuh — the fused, persistent sm_100a estimator kernel.
+//
+// One CTA per SM.  Warp 0 is the PRODUCER: one elected lane streams sample windows from
+// HBM into a ring of shared-memory stages with the TMA engine (cp.async.bulk +
+// mbarrier complete_tx); when windows are not 16-byte granular it falls back to per-element
+// cp.async from all 32 lanes.  Warps 1..NC are CONSUMERS: each claims the next window of
+// the CTA's contiguous range (shared-memory ticket), computes its pruned rectangular DFT
+// from the stage (pmu_dft.cuh), reduces the 32 lane-partials with a transposing shuffle
+// butterfly and drops the K+1 bins into the batch's raw buffer.  The warp that completes
+// a batch of <= 32 consecutive windows becomes its POST-PROCESSOR: lane = window, Hann in
+// the frequency domain, IpDFT / e-IpDFT / interference iterations (pmu_math.cuh), ROCOF
+// state read-modify-write in HBM, frame store.  No block-wide barrier after start-up.
+//
+// Replaces reference src/pmu_estimator.c:170-271 (pmu_estimate) for a whole batch.
+#pragma once
+
+#include <stdint.h>
+
+#include "pmu_dft.cuh"
+
+#define PMU_WARP 32
+// Threads per CTA the kernel is compiled for (a multiple of 128: ptxas budgets registers per
+// 4-warp allocation unit).  256 -> 1 producer + up to 7 consumer warps at <= 255 registers.
+#ifndef PMU_BLOCK_THREADS
+#define PMU_BLOCK_THREADS 256
+#endif
+#define PMU_MAX_CONSUMERS (PMU_BLOCK_THREADS / PMU_WARP - 1)
+#define PMU_MAX_STAGES 16
+#define PMU_MAX_RAW 8
+#define PMU_MAX_POST 8
+
+enum { PMU_LOAD_BULK = 0, PMU_LOAD_ELEM = 1 };
+
+struct KernelArgs {
+    PostParams post;
+    // DFT geometry
+    int N, L, W, nslab, Kp;      // window length, residues (N/M), slab width, slabs per window, n_bins+1
+    int load_mode;               // PMU_LOAD_BULK / PMU_LOAD_ELEM
+    int n_stage, stage_bytes;
+    int n_cons;                  // consumer warps
+    int n_raw, raw_stride;       // raw-bin buffers in the ring, doubles per window slot
+    int n_post;                  // post-processing scratch slots
+    int n_u;                     // entries of U (complex)
+    int scratch_global;          // 1: X/W scratch lives in global memory (large n_bins)
+    // shared-memory layout (byte offsets from the dynamic smem base)
+    int off_ctrl, off_U, off_V, off_trig, off_raw, off_post, off_stage;
+    // tables (global memory; copied to smem by the kernel)
+    const pmu_c* U;              // [ceil(L/32)][KC]   W_N^{32 i k}
+    const pmu_c* V;              // [KC][32]           W_N^{lane k}
+    const pmu_c* trig;           // [jlo + jhi + 1]
+    pmu_c* scratch;              // global X/W scratch when scratch_global
+    // batch
+    const void* windows;         // InT [n_windows][N]
+    const void* mid;             // InT [n_windows / C]
+    void* frames;                // InT [n_windows][4]
+    double* st_fold;             // ROCOF state, one entry per window stream
+    double* st_dl0;
+    double* st_dl1;
+    unsigned char* st_state;
+    long long n_windows;
+    // optional debug / mirror outputs (may be null)
+    int* dbg;                    // [n_windows]  km | flags
+    double* spec_out;            // [n_windows][K][2] Hann-windowed bins
+    double* state_export;        // [n_windows][4]  f_old, dl0, dl1, state after the update
+};
+
+struct CtrlBlock {
+    unsigned long long full[PMU_MAX_STAGES];
+    unsigned long long empty[PMU_MAX_STAGES];
+    int ticket;
+    int batch_cnt[PMU_MAX_RAW];
+    int raw_owner[PMU_MAX_RAW];
+    int post_lock[PMU_MAX_POST];
+};
+
+#if defined(__CUDACC__)
+
+// ---- PTX helpers ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity)
+{
+    uint32_t addr = smem_u32(bar), done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_elem(void* dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(void* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ int ld_volatile_s32(const int* p)
+{
+    return *reinterpret_cast<const volatile int*>(p);
+}
+
+// ---- transposing butterfly: 32 lanes x NV partial sums -> ceil(NV/32) totals per lane ----
+template <int n, int XOR>
+struct ReduceScatter {
+    __device__ __forceinline__ static void run(double* v, int lane, int& base, int& lim)
+    {
+        if constexpr (XOR >= 1) {
+            constexpr int h = (n + 1) / 2;
+            const bool up = (lane & XOR) != 0;
+            static_for<0, h>([&](auto jc) {
+                constexpr int j = jc.value;
+                double lo = v[j];
+                double hi = (j + h < n) ? v[j + h] : 0.0;
+                double send = up ? lo : hi;
+                double keep = up ? hi : lo;
+                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, XOR);
+            });
+            if (up) base += h;
+            else lim = min(lim, base + h);
+            ReduceScatter<h, XOR / 2>::run(v, lane, base, lim);
+        }
+    }
+};
+template <int NV>
+struct ReduceFinal {  // values left per lane after the five exchange steps
+    static constexpr int s1 = (NV + 1) / 2, s2 = (s1 + 1) / 2, s3 = (s2 + 1) / 2, s4 = (s3 + 1) / 2,
+                         value = (s4 + 1) / 2;
+};
+
+// ---- window -> (batch, slot) mapping inside one CTA: balanced batches of <= 32 -----------
+struct BatchMap {
+    int nb, q, rem;  // batches, base size, number of batches with q+1 windows
+    __device__ __forceinline__ void init(int n)
+    {
+        nb = (n + PMU_WARP - 1) / PMU_WARP;
+        if (nb < 1) nb = 1;
+        q = n / nb;
+        rem = n - q * nb;
+    }
+    __device__ __forceinline__ void locate(int t, int* g, int* slot, int* size, int* first) const
+    {
+        int big = rem * (q + 1);
+        if (t < big) {
+            *g = t / (q + 1); *slot = t - *g * (q + 1); *size = q + 1; *first = *g * (q + 1);
+        } else {
+            int u = t - big;
+            int gg = u / q;
+            *g = rem + gg; *slot = u - gg * q; *size = q; *first = big + gg * q;
+        }
+    }
+};
+
+// ---- post-processing of one batch (lane = window) --------------------------------------
+template <typename InT>
+__device__ __noinline__ void post_batch(const KernelArgs& a, const PostParams& pp, unsigned char* smem, int raw_buf,
+                                        int post_slot, long long w_first, int bsz, int batch_id, int lane)
+{
+    CtrlBlock* ctrl = reinterpret_cast<CtrlBlock*>(smem + a.off_ctrl);
+    const int K = pp.K;
+    pmu_c* scratch;
+    if (a.scratch_global)
+        scratch = a.scratch + ((size_t)blockIdx.x * a.n_post + post_slot) * (size_t)(2 * K * PMU_WARP);
+    else
+        scratch = reinterpret_cast<pmu_c*>(smem + a.off_post) + (size_t)post_slot * (2 * K * PMU_WARP);
+    Col X, Wk;
+    X.base = scratch + lane;
+    X.stride = PMU_WARP;
+    Wk.base = scratch + K * PMU_WARP + lane;
+    Wk.stride = PMU_WARP;
+    const bool active = lane < bsz;
+    const long long w = w_first + lane;
+
+    if (active) {
+        const double* row = reinterpret_cast<const double*>(smem + a.off_raw) +
+                            ((size_t)raw_buf * PMU_WARP + lane) * a.raw_stride;
+        for (int k = 0; k < K; ++k) {
+            pmu_c xw = hann_combine(row, k);
+            X.put(k, xw.x, xw.y);
+            if (a.spec_out) {
+                a.spec_out[((size_t)w * K + k) * 2] = xw.x;
+                a.spec_out[((size_t)w * K + k) * 2 + 1] = xw.y;
+            }
+        }
+    }
+    // hand the raw buffer to batch (batch_id + n_raw)
+    __syncwarp();
+    if (lane == 0) {
+        ctrl->batch_cnt[raw_buf] = 0;
+        __threadfence_block();
+        *reinterpret_cast<volatile int*>(&ctrl->raw_owner[raw_buf]) = batch_id + a.n_raw;
+    }
+
+    if (active) {
+        Tone t;
+        int dbg = estimate_tone(pp, X, Wk, &t);
+        RocofState rs;
+        rs.f_old = a.st_fold[w];
+        rs.dl0 = a.st_dl0[w];
+        rs.dl1 = a.st_dl1[w];
+        rs.st = a.st_state[w];
+        double y = rocof_step(pp, t.freq, &rs);
+        a.st_fold[w] = rs.f_old;
+        a.st_dl0[w] = rs.dl0;
+        a.st_dl1[w] = rs.dl1;
+        a.st_state[w] = (unsigned char)rs.st;
+        double mid = (double)reinterpret_cast<const InT*>(a.mid)[w / pp.C];
+        double fr[4];
+        fill_frame(pp, t, y, mid, fr);
+        InT* out = reinterpret_cast<InT*>(a.frames) + (size_t)w * 4;
+        if constexpr (sizeof(InT) == 8) {
+            double2* o2 = reinterpret_cast<double2*>(out);
+            o2[0] = make_double2(fr[0], fr[1]);
+            o2[1] = make_double2(fr[2], fr[3]);
+        } else {
+            *reinterpret_cast<float4*>(out) = make_float4((float)fr[0], (float)fr[1], (float)fr[2], (float)fr[3]);
+        }
+        if (a.dbg) a.dbg[w] = dbg;
+        if (a.state_export) {
+            double2* e2 = reinterpret_cast<double2*>(a.state_export + (size_t)w * 4);
+            e2[0] = make_double2(rs.f_old, rs.dl0);
+            e2[1] = make_double2(rs.dl1, (double)rs.st);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        atomicExch(&ctrl->post_lock[post_slot], 0);
+    }
+}
+
+// ---- the kernel ----------------------------------------------------------------------
+template <typename InT, int M, int KC>
+__global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const __grid_constant__ KernelArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    CtrlBlock* ctrl = reinterpret_cast<CtrlBlock*>(smem + a.off_ctrl);
+    pmu_c* sU = reinterpret_cast<pmu_c*>(smem + a.off_U);
+    pmu_c* sV = reinterpret_cast<pmu_c*>(smem + a.off_V);
+    pmu_c* sT = reinterpret_cast<pmu_c*>(smem + a.off_trig);
+    unsigned char* stages = smem + a.off_stage;
+
+    const int tid = threadIdx.x;
+    const int warp = tid / PMU_WARP;
+    const int lane = tid % PMU_WARP;
+    const int nthreads = blockDim.x;
+
+    // contiguous, balanced range of windows for this CTA
+    const long long w_begin = (a.n_windows * (long long)blockIdx.x) / gridDim.x;
+    const long long w_end = (a.n_windows * (long long)(blockIdx.x + 1)) / gridDim.x;
+    const int n_local = (int)(w_end - w_begin);
+
+    // ---- one-time setup --------------------------------------------------------------
+    if (tid == 0) {
+        const uint32_t full_count = (a.load_mode == PMU_LOAD_BULK) ? 1u : (uint32_t)PMU_WARP;
+        for (int s = 0; s < a.n_stage; ++s) {
+            mbar_init(&ctrl->full[s], full_count);
+            mbar_init(&ctrl->empty[s], 1u);
+        }
+        ctrl->ticket = 0;
+        for (int i = 0; i < PMU_MAX_RAW; ++i) {
+            ctrl->batch_cnt[i] = 0;
+            ctrl->raw_owner[i] = i;
+        }
+        for (int i = 0; i < PMU_MAX_POST; ++i) ctrl->post_lock[i] = 0;
+        mbar_fence_init();
+    }
+    for (int i = tid; i < a.n_u; i += nthreads) sU[i] = a.U[i];
+    for (int i = tid; i < KC * PMU_WARP; i += nthreads) sV[i] = a.V[i];
+    for (int i = tid; i < a.post.jlo + a.post.jhi + 1; i += nthreads) sT[i] = a.trig[i];
+    __syncthreads();
+    if (n_local <= 0) return;
+
+    const size_t win_bytes = (size_t)a.N * sizeof(InT);
+    const unsigned char* gwin = reinterpret_cast<const unsigned char*>(a.windows) + (size_t)w_begin * win_bytes;
+    const int total_slabs = n_local * a.nslab;
+
+    if (warp == 0) {
+        // ================= PRODUCER =================
+        if (a.load_mode == PMU_LOAD_BULK) {
+            if (lane == 0) {
+                for (int i = 0; i < total_slabs; ++i) {
+                    const int st = i % a.n_stage;
+                    const uint32_t par = (uint32_t)((i / a.n_stage) & 1);
+                    mbar_wait(&ctrl->empty[st], par ^ 1u);
+                    const int t = i / a.nslab, sl = i - t * a.nslab;
+                    unsigned char* dst = stages + (size_t)st * a.stage_bytes;
+                    const unsigned char* src = gwin + (size_t)t * win_bytes;
+                    if (a.nslab == 1) {
+                        mbar_expect_tx(&ctrl->full[st], (uint32_t)win_bytes);
+                        bulk_g2s(dst, src, (uint32_t)win_bytes, &ctrl->full[st]);
+                    } else {
+                        const int a_lo = sl * a.W;
+                        const int w_s = min(a.W, a.L - a_lo);
+                        const uint32_t row_bytes = (uint32_t)(w_s * sizeof(InT));
+                        mbar_expect_tx(&ctrl->full[st], row_bytes * M);
+                        for (int b = 0; b < M; ++b)
+                            bulk_g2s(dst + (size_t)b * a.W * sizeof(InT),
+                                     src + ((size_t)a_lo + (size_t)a.L * b) * sizeof(InT), row_bytes, &ctrl->full[st]);
+                    }
+                }
+            }
+        } else {
+            for (int i = 0; i < total_slabs; ++i) {
+                const int st = i % a.n_stage;
+                const uint32_t par = (uint32_t)((i / a.n_stage) & 1);
+                mbar_wait(&ctrl->empty[st], par ^ 1u);
+                const int t = i / a.nslab, sl = i - t * a.nslab;
+                InT* dst = reinterpret_cast<InT*>(stages + (size_t)st * a.stage_bytes);
+                const InT* src = reinterpret_cast<const InT*>(gwin + (size_t)t * win_bytes);
+                const int a_lo = sl * a.W;
+                const int w_s = min(a.W, a.L - a_lo);
+                for (int b = 0; b < M; ++b)
+                    for (int e = lane; e < w_s; e += PMU_WARP)
+                        cp_async_elem<(int)sizeof(InT)>(dst + (size_t)b * a.W + e, src + (size_t)a_lo + (size_t)a.L * b + e);
+                cp_async_mbar_arrive(&ctrl->full[st]);
+            }
+        }
+        return;
+    }
+    if (warp > a.n_cons) return;
+
+    // ================= CONSUMERS =================
+    PostParams pp = a.post;
+    pp.trig = sT;
+    BatchMap bm;
+    bm.init(n_local);
+    const int w_per_it = a.W / PMU_WARP;  // full-slab residue groups (W % 32 == 0 when nslab > 1)
+
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&ctrl->ticket, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_local) break;
+
+        // ---- pruned rectangular DFT of window t ----
+        double acc[2 * KC];  // ar = acc[0..KC), ai = acc[KC..2KC)
+        double* ar = acc;
+        double* ai = acc + KC;
+        bool first = true;
+        for (int sl = 0; sl < a.nslab; ++sl) {
+            const int idx = t * a.nslab + sl;
+            const int st = idx % a.n_stage;
+            const uint32_t par = (uint32_t)((idx / a.n_stage) & 1);
+            mbar_wait(&ctrl->full[st], par);
+            const InT* xs = reinterpret_cast<const InT*>(stages + (size_t)st * a.stage_bytes);
+            const int a_lo = sl * a.W;
+            const int w_s = min(a.W, a.L - a_lo);
+            const int n_it = (w_s + PMU_WARP - 1) / PMU_WARP;
+            for (int ii = 0; ii < n_it; ++ii) {
+                const int a_loc = lane + PMU_WARP * ii;
+                const bool valid = a_loc < w_s;
+                const int a_c = valid ? a_loc : 0;
+                double x[M];
+#pragma unroll
+                for (int b = 0; b < M; ++b) {
+                    double v = (double)xs[b * a.W + a_c];
+                    x[b] = valid ? v : 0.0;
+                }
+                const pmu_c* u = sU + (size_t)(sl * w_per_it + ii) * KC;
+                if (first) {
+                    accumulate_residue<M, KC, true>(x, u, ar, ai);
+                    first = false;
+                } else {
+                    accumulate_residue<M, KC, false>(x, u, ar, ai);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctrl->empty[st]);
+        }
+        rotate_lane<KC>(sV + lane, PMU_WARP, ar, ai);
+
+        // ---- sum the 32 lane partials; lane ends up owning component(s) `base` ----
+        double v[2 * KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            v[2 * k] = ar[k];
+            v[2 * k + 1] = ai[k];
+        }
+        int base = 0, lim = 2 * KC;
+        ReduceScatter<2 * KC, 16>::run(v, lane, base, lim);
+        constexpr int NF = ReduceFinal<2 * KC>::value;
+
+        // ---- deposit into the batch's raw buffer ----
+        int g, slot, bsz, first_t;
+        bm.locate(t, &g, &slot, &bsz, &first_t);
+        const int rb = g % a.n_raw;
+        if (lane == 0) {
+            while (ld_volatile_s32(&ctrl->raw_owner[rb]) != g) __nanosleep(64);
+        }
+        __syncwarp();
+        __threadfence_block();
+        double* row = reinterpret_cast<double*>(smem + a.off_raw) + ((size_t)rb * PMU_WARP + slot) * a.raw_stride;
+        const int lim2 = min(lim, 2 * a.Kp);
+#pragma unroll
+        for (int j = 0; j < NF; ++j)
+            if (base + j < lim2) row[base + j] = v[j];
+        __syncwarp();
+        int done = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            done = atomicAdd(&ctrl->batch_cnt[rb], 1) + 1;
+        }
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done == bsz) {
+            // ---- this warp post-processes batch g ----
+            __threadfence_block();
+            int ps = 0;
+            if (lane == 0) {
+                for (;;) {
+                    bool got = false;
+                    for (int s = 0; s < a.n_post; ++s)
+                        if (atomicCAS(&ctrl->post_lock[s], 0, 1) == 0) { ps = s; got = true; break; }
+                    if (got) break;
+                    __nanosleep(128);
+                }
+            }
+            ps = __shfl_sync(0xffffffffu, ps, 0);
+            post_batch<InT>(a, pp, smem, rb, ps, w_begin + first_t, bsz, g, lane);
+        }
+    }
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,61 @@
+// pmu_launch.cuh — instantiates pmu_fused_kernel for one float_p width (PMU_LAUNCH_T) and
+// every (codelet size M, bins per lane KC) specialisation, and dispatches at run time.
+// Included by pmu_kernels_f64.cu / pmu_kernels_f32.cu so the two widths compile in parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "pmu_host.hpp"
+#include "pmu_kernel.cuh"
+
+namespace {
+
+template <typename T, int M, int KC>
+int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
+{
+    static int configured[64];  // per device: dynamic smem already opted in for this instantiation
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && (dev < 0 || dev >= 64 || configured[dev] != smem)) {
+        e = cudaFuncSetAttribute(pmu_fused_kernel<T, M, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev] = smem;
+    }
+    if (e == cudaSuccess) {
+        pmu_fused_kernel<T, M, KC><<<grid, block, smem, s>>>(a);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        pmu::set_error(std::string("[pmu_estimate] CUDA ERROR launching the estimator kernel: ") + cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
+template <typename T, int M>
+int launch_kc(int KC, const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
+{
+    switch (KC) {
+        case 8: return launch_inst<T, M, 8>(a, grid, block, smem, s);
+        case 12: return launch_inst<T, M, 12>(a, grid, block, smem, s);
+        case 16: return launch_inst<T, M, 16>(a, grid, block, smem, s);
+        case 24: return launch_inst<T, M, 24>(a, grid, block, smem, s);
+    }
+    pmu::set_error("[pmu_estimate] ERROR: unsupported bin-count specialisation");
+    return -1;
+}
+
+template <typename T>
+int launch_m(int M, int KC, const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
+{
+    switch (M) {
+        case 16: return launch_kc<T, 16>(KC, a, grid, block, smem, s);
+        case 8: return launch_kc<T, 8>(KC, a, grid, block, smem, s);
+        case 4: return launch_kc<T, 4>(KC, a, grid, block, smem, s);
+        case 1: return launch_kc<T, 1>(KC, a, grid, block, smem, s);
+    }
+    pmu::set_error("[pmu_estimate] ERROR: unsupported DFT codelet specialisation");
+    return -1;
+}
+
+}  // namespace

@@ -1,0 +1,334 @@
+// pmu_math.cuh — per-window estimator arithmetic (one window per thread/lane).
+//
+// Everything after the DFT in SynchroPMU's pmu_estimate() (reference
+// src/pmu_estimator.c:205-265) restated for a GPU lane: IpDFT, e-IpDFT negative-image
+// compensation, pure-tone synthesis, the interference energy test, the iterative
+// interharmonic estimation, the two-state ROCOF filter and the frame fill.
+//
+// The formulation is NOT the reference's: the Hann-window tone spectrum wf()
+// (macros at src/pmu_estimator.c:59-61, 1 cexp + 6 sin per bin) is evaluated as a
+// sweep over bins with two sincospi() per sweep:
+//
+//   x_k = k - f/df = m + r,  kstar = rint(f/df),  r = kstar - f/df (|r| <= 1/2),  m = k - kstar
+//   sin(pi (x_k + e))   = (-1)^(m+e) sin(pi r)                        e in {-1,0,1}
+//   sin(pi (x_k + e)/N) = sin(pi r/N) cos((m+e) pi/N) + cos(pi r/N) sin((m+e) pi/N)
+//   exp(-i pi C3 x_k) (-1)^m = exp(-i pi C3 r) exp(i pi m/N)            (C3 = 1 - 1/N)
+//   C5 = -exp(+i pi C3)/4, C6 = conj(C5), exp(i pi C3) = -cos(pi/N) + i sin(pi/N)
+//
+// so that wf(k, f, z) = zz * E[m] * ( c3q (I[m-1] + I[m+1]) + I[m]/2 + i s3q (I[m-1] - I[m+1]) )
+// with zz = z * inv_norm * sin(pi r) * exp(-i pi C3 r), E[j] = exp(i pi j/N) from a table
+// and I[j] = 1/sin(pi (r+j)/N) (one new reciprocal per bin).  Anchoring the angle
+// addition at the nearest bin keeps every Dirichlet ratio accurate to a few ulp, also
+// when the tone sits (almost) on a bin; r == 0 gives 0 * inf = NaN exactly where the
+// reference gets sin(0)/sin(0) = NaN.
+//
+// All functions are __host__ __device__ so tests/host_emul can run this exact code on
+// the CPU against the oracle; the shipped library only ever runs it on the GPU.
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define PMU_HD __host__ __device__ __forceinline__
+#include <cuda_runtime.h>
+typedef double2 pmu_c;
+#else
+#define PMU_HD inline
+struct alignas(16) pmu_c {
+    double x, y;
+};
+#endif
+
+#ifndef PMU_PI
+#define PMU_PI 3.14159265358979323846 /* M_PI, reference src/func_stubs.h:33 */
+#endif
+
+PMU_HD void pmu_sincospi(double x, double* s, double* c)
+{
+#if defined(__CUDA_ARCH__)
+    sincospi(x, s, c);
+#else
+    // host emulation only: |x| <= ~0.5 here, argument rounding costs < 1 ulp of pi*x
+    *s = sin(PMU_PI * x);
+    *c = cos(PMU_PI * x);
+#endif
+}
+
+PMU_HD void pmu_sincos(double x, double* s, double* c)
+{
+#if defined(__CUDA_ARCH__)
+    sincos(x, s, c);
+#else
+    *s = sin(x);
+    *c = cos(x);
+#endif
+}
+
+// Read-only parameters of the post-DFT stage (uniform over a batch).
+struct PostParams {
+    int K;         // n_bins
+    int P, Q;      // e-IpDFT passes, interference iterations
+    int iter_en;   // iter_eipdft_enabled
+    int jlo, jhi;  // trig table covers j in [-jlo, jhi]
+    int C;         // channels per instance (mid_fracsec is per instance)
+    int f0;
+    double df;
+    double S, invS;       // norm_factor and 1/norm_factor (src/pmu_estimator.c:150,160)
+    double eps;           // interf_trig
+    double invN;
+    double c3q, s3q;      // cos(pi C3)/4, sin(pi C3)/4
+    double frame_rate;
+    double thr0, thr1, thr2;  // ROCOF thresholds
+    double lp0, lp1, lp2;     // ROCOF low-pass coefficients
+    const pmu_c* trig;    // trig[j + jlo] = (cos(j pi/N), sin(j pi/N))
+};
+
+struct Tone {
+    double amp, ph, freq;
+};
+
+// One sweep of wf(k, f, z) over the bins for a fixed tone (f, z).
+struct Sweep {
+    double zr, zi;  // zz
+    double sr, cr;  // sin(pi r/N), cos(pi r/N)
+    int kstar;
+
+    PMU_HD void init(const PostParams& p, double f, double z_re, double z_im)
+    {
+        double q = f / p.df;  // same division as x = k - f/df (src/pmu_estimator.c:61)
+        double ks = rint(q);
+        const double lim = (double)(p.K + 1);
+        if (!(ks >= -lim)) ks = -lim;  // also catches NaN: keeps table indices in range
+        if (!(ks <= lim)) ks = lim;
+        kstar = (int)ks;
+        double r = ks - q;
+        double spr, cpr;
+        pmu_sincospi(r, &spr, &cpr);
+        pmu_sincospi(r * p.invN, &sr, &cr);
+        // exp(-i pi C3 r) = exp(-i pi r) exp(+i pi r/N)
+        double er = cpr * cr + spr * sr;
+        double ei = cpr * sr - spr * cr;
+        double g = p.invS * spr;
+        zr = (z_re * er - z_im * ei) * g;
+        zi = (z_re * ei + z_im * er) * g;
+    }
+
+    // 1 / sin(pi (r + j)/N)
+    PMU_HD double inv_den(const PostParams& p, int j) const
+    {
+        pmu_c t = p.trig[j + p.jlo];
+        return 1.0 / (sr * t.x + cr * t.y);
+    }
+
+    // value at bin k given I[m-1], I[m], I[m+1]
+    PMU_HD void eval(const PostParams& p, int k, double im1, double i0, double ip1, double* wr, double* wi) const
+    {
+        pmu_c e = p.trig[(k - kstar) + p.jlo];
+        double br = p.c3q * (im1 + ip1) + 0.5 * i0;
+        double bi = p.s3q * (im1 - ip1);
+        double tr = e.x * br - e.y * bi;
+        double ti = e.x * bi + e.y * br;
+        *wr = zr * tr - zi * ti;
+        *wi = zr * ti + zi * tr;
+    }
+};
+
+// Running "first strict maximum + neighbours" over |Y_j|^2
+// (find3LargestIndx, src/pmu_estimator.c:705-720; NaN never wins unless at index 0).
+struct Peak {
+    double best, left, right, prev, yr, yi;
+    int km;
+
+    PMU_HD void first(double v, double re, double im)
+    {
+        best = v; left = v; right = v; prev = v; yr = re; yi = im; km = 0;
+    }
+    PMU_HD void next(int j, double v, double re, double im)
+    {
+        bool up = v > best;
+        if (!up && j == km + 1) right = v;
+        if (up) { left = prev; km = j; best = v; yr = re; yi = im; }
+        prev = v;
+    }
+};
+
+// ipDFT tail (src/pmu_estimator.c:594-623) from the tracked peak.  Returns 1 when
+// |delta| <= 1e-11 (the reference's literal 10e-12, :603).
+PMU_HD int ipdft_finish(const PostParams& p, const Peak& pk, Tone* t)
+{
+    double mk = sqrt(pk.best);
+    double ml = (pk.km == 0) ? mk : sqrt(pk.left);              // kl = km when km == 0 (:718)
+    double mr = (pk.km == p.K - 1) ? ml : sqrt(pk.right);       // kr = km-1 at the last bin (:719)
+    double d = 2 * (mr - ml) / (ml + mr + 2 * mk);              // :598
+    t->freq = (pk.km + d) * p.df;                               // :601
+    double arg = atan2(pk.yi, pk.yr);
+    if (fabs(d) <= 10e-12) {                                    // :603-613
+        t->amp = mk;
+        t->ph = arg;
+        return 1;
+    }
+    double pd = PMU_PI * d;
+    t->amp = mk * fabs((d * d - 1) * pd / sin(pd));             // :616
+    t->ph = arg - pd;                                           // :617
+    return 0;
+}
+
+// Column view of a [K][32] complex array in shared memory (lane = window).
+struct Col {
+    pmu_c* base;  // already offset by the lane
+    int stride;   // elements between consecutive bins
+    PMU_HD pmu_c get(int j) const { return base[j * stride]; }
+    PMU_HD void put(int j, double re, double im) const
+    {
+        pmu_c v; v.x = re; v.y = im;
+        base[j * stride] = v;
+    }
+};
+
+// One ipDFT over Y[j] (COMP=false) or over Y[j] - wf(j, -f, amp e^{-i ph}) (COMP=true,
+// the e_ipDFT inner loop :646-654).  km_out receives the chosen peak bin.
+template <bool COMP>
+PMU_HD int ipdft_pass(const PostParams& p, const Col& Y, const Tone& prev, Tone* out, int* km_out)
+{
+    Sweep sw;
+    double im1 = 0, i0 = 0, ip1 = 0;
+    if (COMP) {
+        double s, c;
+        pmu_sincos(prev.ph, &s, &c);
+        sw.init(p, -prev.freq, prev.amp * c, -prev.amp * s);
+        im1 = sw.inv_den(p, -sw.kstar - 1);
+        i0 = sw.inv_den(p, -sw.kstar);
+    }
+    Peak pk;
+    for (int j = 0; j < p.K; ++j) {
+        pmu_c y = Y.get(j);
+        if (COMP) {
+            double wr, wi;
+            ip1 = sw.inv_den(p, j - sw.kstar + 1);
+            sw.eval(p, j, im1, i0, ip1, &wr, &wi);
+            y.x -= wr;
+            y.y -= wi;
+            im1 = i0;
+            i0 = ip1;
+        }
+        double v = y.x * y.x + y.y * y.y;
+        if (j == 0) pk.first(v, y.x, y.y);
+        else pk.next(j, v, y.x, y.y);
+    }
+    if (km_out) *km_out = pk.km;
+    return ipdft_finish(p, pk, out);
+}
+
+// e_ipDFT (src/pmu_estimator.c:626-664).
+PMU_HD void e_ipdft(const PostParams& p, const Col& Y, Tone* t, int* km_first)
+{
+    Tone cur = *t;
+    if (!ipdft_pass<false>(p, Y, cur, &cur, km_first)) {
+        for (int it = 0; it < p.P; ++it) {
+            Tone nxt;
+            int done = ipdft_pass<true>(p, Y, cur, &nxt, nullptr);
+            cur = nxt;
+            if (done) break;
+        }
+    }
+    *t = cur;
+}
+
+// W[j] = X[j] - pureTone(t)[j]   (pureTone :563-577; Xi/Xf updates :215, :681-684, :692-695)
+// and, when ENERGY, Ed = sum |W[j]|^2, E = sum |X[j]|^2  (:219-220 compute cabs(z*z) = |z|^2).
+template <bool ENERGY>
+PMU_HD void residual(const PostParams& p, const Col& X, const Tone& t, const Col& W, double* Ed, double* E)
+{
+    double s, c;
+    pmu_sincos(t.ph, &s, &c);
+    Sweep sp, sn;
+    sp.init(p, t.freq, t.amp * c, t.amp * s);    // phsr_0 = amp e^{+i ph}
+    sn.init(p, -t.freq, t.amp * c, -t.amp * s);  // phsr_1 = amp e^{-i ph}
+    double pm1 = sp.inv_den(p, -sp.kstar - 1), p0 = sp.inv_den(p, -sp.kstar);
+    double nm1 = sn.inv_den(p, -sn.kstar - 1), n0 = sn.inv_den(p, -sn.kstar);
+    double ed = 0, e = 0;
+    for (int j = 0; j < p.K; ++j) {
+        double pp1 = sp.inv_den(p, j - sp.kstar + 1);
+        double np1 = sn.inv_den(p, j - sn.kstar + 1);
+        double ar, ai, br, bi;
+        sp.eval(p, j, pm1, p0, pp1, &ar, &ai);
+        sn.eval(p, j, nm1, n0, np1, &br, &bi);
+        pm1 = p0; p0 = pp1;
+        nm1 = n0; n0 = np1;
+        pmu_c x = X.get(j);
+        double wr = x.x - (ar + br);
+        double wi = x.y - (ai + bi);
+        W.put(j, wr, wi);
+        if (ENERGY) {
+            ed += wr * wr + wi * wi;
+            e += x.x * x.x + x.y * x.y;
+        }
+    }
+    if (ENERGY) { *Ed = ed; *E = e; }
+}
+
+// Bits of the per-window debug word (exported only through the debug entry point).
+#define PMU_DBG_KM_MASK 0xffff
+#define PMU_DBG_TRIGGERED 0x10000
+
+// Everything between the DFT and the ROCOF stage for one window:
+// src/pmu_estimator.c:205-233 (+ iter_e_ipDFT :666-703).  X holds the Hann-windowed
+// bins, W is scratch of the same shape.  Returns the debug word.
+PMU_HD int estimate_tone(const PostParams& p, const Col& X, const Col& W, Tone* out)
+{
+    Tone f;
+    f.amp = 0; f.ph = 0; f.freq = 0;
+    int km = 0;
+    e_ipdft(p, X, &f, &km);                                  // :205
+    int dbg = km & PMU_DBG_KM_MASK;
+    double Ed = 0, E = 0;
+    if (p.iter_en) residual<true>(p, X, f, W, &Ed, &E);      // :206-222  (W = Xi)
+    if (p.iter_en && Ed > p.eps * E) {                       // :227-229 (NaN compares false)
+        dbg |= PMU_DBG_TRIGGERED;
+        Tone it;
+        it.amp = 0; it.ph = 0; it.freq = 0;
+        for (int i = 0; i < p.Q; ++i) {                      // :675
+            e_ipdft(p, W, &it, nullptr);                     // :679   interference tone from Xi
+            residual<false>(p, X, it, W, nullptr, nullptr);  // :680-684  W = Xf = X - pure(it)
+            e_ipdft(p, W, &f, nullptr);                      // :685   fundamental from Xf
+            if (i + 1 < p.Q)
+                residual<false>(p, X, f, W, nullptr, nullptr);  // :690-695  W = Xi = X - pure(f)
+        }
+    }
+    *out = f;
+    return dbg;
+}
+
+struct RocofState {
+    double f_old, dl0, dl1;
+    int st;
+};
+
+// Two-state ROCOF estimator + first-order low-pass (src/pmu_estimator.c:236-260).
+PMU_HD double rocof_step(const PostParams& p, double freq, RocofState* s)
+{
+    double r = (freq - s->f_old) * p.frame_rate;                                   // :236
+    double rd = (r - s->dl0) * p.frame_rate;                                       // :237
+    if (!s->st && (fabs(r) > p.thr0 || fabs(rd) > p.thr1)) s->st = 1;              // :240
+    if (s->st && fabs(r) < p.thr2) s->st = 0;                                      // :241
+    double y = s->st ? r : (p.lp1 * r + p.lp2 * s->dl0 - p.lp0 * s->dl1);          // :244-253
+    s->f_old = freq;                                                               // :256-260
+    s->dl0 = r;
+    s->dl1 = y;
+    return y;
+}
+
+// wrap_angle (src/pmu_estimator.c:58): ties-to-even rint, range [-pi, pi].
+PMU_HD double wrap_angle_pi(double rad)
+{
+    return rad - 2 * PMU_PI * rint(rad / (2 * PMU_PI));
+}
+
+// Frame fill (src/pmu_estimator.c:263-265).
+PMU_HD void fill_frame(const PostParams& p, const Tone& t, double rocof, double mid_fracsec, double out[4])
+{
+    out[0] = 2 * t.amp / p.S;
+    out[1] = wrap_angle_pi(t.ph - 2 * PMU_PI * p.f0 * mid_fracsec);
+    out[2] = t.freq;
+    out[3] = rocof;
+}

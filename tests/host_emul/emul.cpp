@@ -1,0 +1,126 @@
+// emul.cpp — CPU emulation of the CUDA kernel's per-lane arithmetic (TEST INFRASTRUCTURE).
+//
+// Compiles the SAME headers the kernel uses (pmu_math.cuh, pmu_dft.cuh, pmu_host.cpp's
+// tables and plan) with g++ and walks the lane/slab/residue loops of pmu_kernel.cuh on
+// the host, so the restructured DFT and sweep arithmetic can be checked against the
+// oracle in the GPU-less dev container.  It is never linked into libpmu_estimator*.so
+// and is not a fallback: the product only runs the arithmetic on the GPU.
+#include <string.h>
+
+#include <vector>
+
+#include "../../synchropmu_b200/csrc/pmu_host.hpp"
+
+template <typename InT, int M, int KC>
+static void window_bins(const pmu::Plan& p, const std::vector<pmu_c>& U, const std::vector<pmu_c>& V,
+                        const InT* x, double* raw /* 2*KC */)
+{
+    double sum_r[KC], sum_i[KC];
+    for (int k = 0; k < KC; ++k) sum_r[k] = sum_i[k] = 0.0;
+    const int w_per_it = p.W / 32;
+    for (int lane = 0; lane < 32; ++lane) {
+        double ar[KC], ai[KC];
+        bool first = true;
+        for (int sl = 0; sl < p.nslab; ++sl) {
+            const int a_lo = sl * p.W;
+            const int w_s = (p.W < p.L - a_lo) ? p.W : p.L - a_lo;
+            const int n_it = (w_s + 31) / 32;
+            for (int ii = 0; ii < n_it; ++ii) {
+                const int a_loc = lane + 32 * ii;
+                const bool valid = a_loc < w_s;
+                double xv[M];
+                for (int b = 0; b < M; ++b) xv[b] = valid ? (double)x[(size_t)(a_lo + a_loc) + (size_t)p.L * b] : 0.0;
+                const pmu_c* u = U.data() + (size_t)(sl * w_per_it + ii) * KC;
+                if (first) { accumulate_residue<M, KC, true>(xv, u, ar, ai); first = false; }
+                else accumulate_residue<M, KC, false>(xv, u, ar, ai);
+            }
+        }
+        rotate_lane<KC>(V.data() + lane, 32, ar, ai);
+        for (int k = 0; k < KC; ++k) { sum_r[k] += ar[k]; sum_i[k] += ai[k]; }
+    }
+    for (int k = 0; k < KC; ++k) { raw[2 * k] = sum_r[k]; raw[2 * k + 1] = sum_i[k]; }
+}
+
+template <typename InT, int M>
+static void window_bins_kc(int KC, const pmu::Plan& p, const std::vector<pmu_c>& U, const std::vector<pmu_c>& V, const InT* x, double* raw)
+{
+    switch (KC) {
+        case 8: window_bins<InT, M, 8>(p, U, V, x, raw); break;
+        case 12: window_bins<InT, M, 12>(p, U, V, x, raw); break;
+        case 16: window_bins<InT, M, 16>(p, U, V, x, raw); break;
+        case 24: window_bins<InT, M, 24>(p, U, V, x, raw); break;
+    }
+}
+template <typename InT>
+static void window_bins_m(const pmu::Plan& p, const std::vector<pmu_c>& U, const std::vector<pmu_c>& V, const InT* x, double* raw)
+{
+    switch (p.M) {
+        case 16: window_bins_kc<InT, 16>(p.KC, p, U, V, x, raw); break;
+        case 8: window_bins_kc<InT, 8>(p.KC, p, U, V, x, raw); break;
+        case 4: window_bins_kc<InT, 4>(p.KC, p, U, V, x, raw); break;
+        case 1: window_bins_kc<InT, 1>(p.KC, p, U, V, x, raw); break;
+    }
+}
+
+extern "C" {
+
+// windows [T][S][N] (dtype), mid [T][S/C] (double), frames [T][S][4] (double),
+// flags [T][S], spectrum [T][S][K][2].  State starts fresh.  Returns 0 / -1.
+int emul_run(const pmub_config* cfg, int dtype, int n_channels, long n_streams, long n_frames, const void* windows,
+             const double* mid, double* frames, int* flags, double* spectrum, int* plan_out /* M, KC, nslab, W */)
+{
+    if (pmu::validate(*cfg)) return -1;
+    pmu::Plan p;
+    if (pmu::make_plan(*cfg, dtype, 232448, &p)) return -1;
+    pmu::Derived d = pmu::derive(*cfg, dtype);
+    std::vector<pmu_c> U, V, T;
+    pmu::build_tables(p, d.N, &U, &V, &T);
+    if (plan_out) { plan_out[0] = p.M; plan_out[1] = p.KC; plan_out[2] = p.nslab; plan_out[3] = p.W; }
+
+    PostParams pp;
+    memset(&pp, 0, sizeof pp);
+    pp.K = (int)cfg->n_bins; pp.P = (int)cfg->P; pp.Q = (int)cfg->Q; pp.iter_en = cfg->iter_eipdft ? 1 : 0;
+    pp.jlo = p.jlo; pp.jhi = p.jhi; pp.C = n_channels; pp.f0 = (int)cfg->f0;
+    pp.df = d.df; pp.S = d.S; pp.invS = d.invS; pp.eps = d.eps; pp.invN = 1.0 / (double)d.N;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    pp.c3q = (double)(-0.25L * cosl(pi / (long double)d.N));
+    pp.s3q = (double)(0.25L * sinl(pi / (long double)d.N));
+    pp.frame_rate = (double)cfg->frame_rate;
+    pp.thr0 = d.thr[0]; pp.thr1 = d.thr[1]; pp.thr2 = d.thr[2];
+    pp.lp0 = d.lp[0]; pp.lp1 = d.lp[1]; pp.lp2 = d.lp[2];
+    pp.trig = T.data();
+
+    const int K = pp.K;
+    std::vector<RocofState> st((size_t)n_streams);
+    for (auto& s : st) { s.f_old = (double)cfg->f0; s.dl0 = 0; s.dl1 = 0; s.st = 0; }
+    std::vector<double> raw((size_t)2 * p.KC + 2);
+    std::vector<pmu_c> X((size_t)K), W((size_t)K);
+    for (long t = 0; t < n_frames; ++t) {
+        for (long s = 0; s < n_streams; ++s) {
+            const size_t u = (size_t)t * n_streams + s;
+            if (dtype == PMUB_F64) window_bins_m<double>(p, U, V, (const double*)windows + u * d.N, raw.data());
+            else window_bins_m<float>(p, U, V, (const float*)windows + u * d.N, raw.data());
+            Col cx, cw;
+            cx.base = X.data(); cx.stride = 1;
+            cw.base = W.data(); cw.stride = 1;
+            for (int k = 0; k < K; ++k) {
+                pmu_c xw = hann_combine(raw.data(), k);
+                cx.put(k, xw.x, xw.y);
+                if (spectrum) { spectrum[(u * K + k) * 2] = xw.x; spectrum[(u * K + k) * 2 + 1] = xw.y; }
+            }
+            Tone tone;
+            int dbg = estimate_tone(pp, cx, cw, &tone);
+            double y = rocof_step(pp, tone.freq, &st[(size_t)s]);
+            double m = mid[(size_t)t * (n_streams / n_channels) + s / n_channels];
+            if (dtype == PMUB_F32) m = (double)(float)m;
+            fill_frame(pp, tone, y, m, frames + u * 4);
+            if (flags) flags[u] = dbg;
+        }
+    }
+    return 0;
+}
+
+int emul_parse_ini(const char* path, pmub_config* out) { return pmu::parse_ini(path, out); }
+int emul_validate(const pmub_config* c) { return pmu::validate(*c); }
+
+}  // extern "C"

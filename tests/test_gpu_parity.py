@@ -1,0 +1,330 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Everything here is marked ``gpu`` and calls libpmu_estimator*.so via ctypes.  The oracle
+(oracle/_ref = the unmodified reference when its build travelled with the snapshot, else
+oracle/pmu_oracle.c) is only the checker.  Tolerances are BASELINE.json's north_star
+(tests/parity.py): double |d amp|/amp <= 1e-9, |d ph| <= 1e-9 rad, |d f| <= 1e-7 Hz,
+|d ROCOF| <= 1e-4 Hz/s, peak bin exact; float checked against the float reference build.
+"""
+import ctypes as C
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from oracle_lib import CpuChecker
+from parity import assert_frames_close, golden_floats
+from stream_cases import STREAM_CASES, stream_case_windows
+from synchropmu_b200 import BatchEstimator, EstimatorConfig, PMUEstimator, api, configs, signals
+
+pytestmark = pytest.mark.gpu
+
+GOLD = Path(__file__).resolve().parent / "golden"
+SINGLE = json.loads((GOLD / "single_calls.json").read_text())
+NPZ = np.load(GOLD / "single_calls.npz")
+STREAMS = json.loads((GOLD / "streams.json").read_text())
+DT = {"f64": np.float64, "f32": np.float32}
+
+
+def checker(dtype, n_ch):
+    kind = "ref" if oracle_lib.have("ref", dtype, n_ch) else "port"
+    return CpuChecker(kind, dtype, n_ch)
+
+
+def three_phase_batch(cfg, n_inst, T, seed, interharmonic_frames=(), noise=1e-3):
+    prm = signals.three_phase_params(n_inst, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    N = configs.win_len(cfg)
+    win = np.zeros((T, n_inst, 6, N))
+    mid = np.zeros((T, n_inst))
+    for t in range(T):
+        harm = [(0.1, 75.0, 0.0)] if t in interharmonic_frames else [(0.03, 150.6, 0.3)]
+        x = signals.steady(cfg, t, prm["amp"], prm["freq"], prm["phase"], ramp=prm["ramp"], harmonics=harm)
+        x = x + noise * prm["amp"][:, None] * rng.standard_normal(x.shape)
+        win[t] = x.reshape(n_inst, 6, N)
+        mid[t] = signals.mid_fracsec(cfg, t)
+    return win, mid
+
+
+# ---------------------------------------------------------------------------------------
+# drop-in API (pmu_init / pmu_estimate / pmu_deinit) against the committed golden vectors
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", SINGLE, ids=[c["key"] for c in SINGLE])
+def test_dropin_single_call_matches_reference_golden(case):
+    dt = DT[case["dtype"]]
+    pmu = PMUEstimator(n_channels=case["C"], dtype=dt)
+    assert pmu.configure_from_class(EstimatorConfig.from_dict(case["cfg"])) == 0
+    assert pmu.win_len == case["win_len"]
+    assert abs(float(pmu.ctx.synch_params.norm_factor) - case["norm_factor"]) <= (0 if dt == np.float64 else 1e-3)
+    res = pmu.estimate(NPZ[case["key"] + "__win"], case["mid"])
+    assert res is not None
+    res = [res] if case["C"] == 1 else res
+    got = np.array([[r["amp"], r["ph"], r["freq"], r["rocof"]] for r in res])
+    want = golden_floats(case["frames"]).reshape(case["C"], 4)
+    assert_frames_close(got, want, case["dtype"], case["key"])
+    # ROCOF state mirrored into the caller's context like the reference keeps it there
+    if not np.isnan(want[:, 2]).any():
+        fo = np.array(list(pmu.ctx.rocof_params.freq_old))
+        assert np.allclose(fo, want[:, 2], rtol=0, atol=1e-7 if dt == np.float64 else 1e-3)
+    assert pmu.deinit() == 0
+
+
+@pytest.mark.parametrize("case", [c for c in SINGLE if c["C"] == 1], ids=[c["key"] for c in SINGLE if c["C"] == 1])
+def test_peak_bin_and_spectrum_match_reference_golden(case):
+    dt = DT[case["dtype"]]
+    with BatchEstimator(case["cfg"], 1, 1, dtype=dt) as est:
+        est.set_debug(True)
+        est.estimate(NPZ[case["key"] + "__win"].reshape(1, 1, -1), np.array([case["mid"]], dtype=dt))
+        km, _trig, spec = est.get_debug()
+    want_spec = golden_floats(case["spectrum_re"]) + 1j * golden_floats(case["spectrum_im"])
+    scale = max(float(np.max(np.abs(want_spec))), 1e-300)
+    tol = 1e-11 if case["dtype"] == "f64" else 2e-5
+    assert np.max(np.abs(spec[0, 0] - want_spec)) <= tol * scale
+    if not np.isnan(golden_floats(case["frames"])).any():
+        assert int(km[0, 0]) == case["km_last"]          # bit-exact peak index
+
+
+@pytest.mark.parametrize("run", STREAMS, ids=[f"{r['case']}__{r['dtype']}" for r in STREAMS])
+def test_batch_streams_match_reference_golden(run):
+    """Config-4 sweep (off-nominal, harmonics, interharmonics, AM/PM, ramps), consecutive frames."""
+    sc = next(s for s in STREAM_CASES if s["name"] == run["case"])
+    dt = DT[run["dtype"]]
+    win, mid = stream_case_windows(sc, dtype=dt)
+    T, S = mid.shape
+    want = golden_floats(run["frames"]).reshape(run["shape"])
+    got = np.zeros((T, S, 1, 4))
+    kms = np.zeros((T, S), dtype=np.int64)
+    with BatchEstimator(configs.NAMED[sc["cfg"]], S, 1, dtype=dt) as est:
+        est.set_debug(True)
+        for t in range(T):
+            got[t] = est.estimate(win[t], mid[t].astype(dt))
+            kms[t] = est.get_debug()[0][:, 0]
+    assert_frames_close(got, want, run["dtype"], run["case"])
+    if run["dtype"] == "f64":
+        assert kms.reshape(-1).tolist() == run["km"]
+
+
+# ---------------------------------------------------------------------------------------
+# live comparison with the oracle on seeded batches
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("cfgname", ["config.ini", "m_class_config.ini", "cfg5_600", "p_class_config.ini", "test_c_q22"])
+def test_batch_matches_oracle_three_phase(cfgname, dtype):
+    cfg = configs.NAMED[cfgname]
+    dt = DT[dtype]
+    n_inst, T = 40, 4
+    win, mid = three_phase_batch(cfg, n_inst, T, seed=101, interharmonic_frames=(2,))
+    win = win.astype(dt)
+    want, km_want, _ = checker(dt, 6).run(cfg, win, mid, n_threads=0)
+    got = np.zeros_like(want, dtype=np.float64)
+    km = np.zeros((T, n_inst, 6), dtype=np.int64)
+    trig_any = False
+    with BatchEstimator(cfg, n_inst, 6, dtype=dt) as est:
+        est.set_debug(True)
+        for t in range(T):
+            got[t] = est.estimate(win[t], mid[t].astype(dt))
+            k, trig, _ = est.get_debug()
+            km[t] = k
+            trig_any |= bool(trig.any())
+        assert est.launches == T
+    assert_frames_close(got, want, dtype, cfgname)
+    seen = km_want >= 0
+    assert np.array_equal(km[seen], km_want[seen])
+    if cfg["iter_eipdft"]:
+        assert trig_any          # frame 2 carries a 10 % interharmonic: the Q loop must have run
+
+
+def test_odd_window_length_and_wide_bins():
+    """Windows that are not a multiple of 4 (M = 1 direct path, per-element loads) and
+    n_bins = 18 (KC = 24), both legal per check_config_validity."""
+    for cfg in (dict(configs.DEFAULT_INI, fs=4750, n_cycles=3, n_bins=7),          # N = 285
+                dict(configs.DEFAULT_INI, fs=51200, n_cycles=8, n_bins=18, Q=5),    # N = 8192
+                dict(configs.DEFAULT_INI, fs=51200, n_cycles=16, n_bins=18, Q=2)):  # N = 16384, slabs
+        N = configs.win_len(cfg)
+        S, T = 9, 3
+        rng = np.random.default_rng(5)
+        f = 50 + rng.uniform(-2, 2, S)
+        win = np.zeros((T, S, 1, N))
+        mid = np.zeros((T, S))
+        for t in range(T):
+            win[t, :, 0, :] = signals.steady(cfg, t, 1 + rng.uniform(0, 1, S), f, rng.uniform(-3, 3, S),
+                                             harmonics=[(0.1, 75.0, 0.0)])
+            mid[t] = signals.mid_fracsec(cfg, t)
+        want, km_want, _ = checker(np.float64, 1).run(cfg, win, mid)
+        got = np.zeros_like(want)
+        with BatchEstimator(cfg, S, 1) as est:
+            est.set_debug(True)
+            for t in range(T):
+                got[t] = est.estimate(win[t], mid[t])
+                assert np.array_equal(est.get_debug()[0], km_want[t])
+        assert_frames_close(got, want, "f64", f"N={N}")
+
+
+def test_unsupported_configuration_fails_loudly():
+    cfg = dict(configs.DEFAULT_INI, n_cycles=30, n_bins=40)
+    with pytest.raises(RuntimeError):
+        BatchEstimator(cfg, 2, 1)
+
+
+# ---------------------------------------------------------------------------------------
+# load paths, pointer kinds, state
+# ---------------------------------------------------------------------------------------
+def test_device_and_host_pointers_and_unaligned_loads_agree():
+    torch = pytest.importorskip("torch")
+    cfg = configs.DEFAULT_INI
+    n_inst = 300
+    win, mid = three_phase_batch(cfg, n_inst, 1, seed=9)
+    with BatchEstimator(cfg, n_inst, 6) as a, BatchEstimator(cfg, n_inst, 6) as b, BatchEstimator(cfg, n_inst, 6) as c:
+        host = a.estimate(win[0], mid[0])                                   # chunked host path
+        dw = torch.from_numpy(win[0]).cuda()
+        dm = torch.from_numpy(mid[0]).cuda()
+        dev = b.estimate(dw, dm).cpu().numpy()                               # device pointers, TMA bulk loads
+        # same samples at an address that is only 8-byte aligned -> per-element cp.async loader
+        pad = torch.empty(win[0].size + 1, dtype=torch.float64, device="cuda")
+        pad[1:] = dw.reshape(-1)
+        una = c.estimate(pad[1:], dm).cpu().numpy()
+    assert np.array_equal(host, dev)
+    assert np.array_equal(dev, una)
+
+
+def test_rocof_state_checkpoint_resume_and_reset():
+    cfg = configs.DEFAULT_INI
+    n_inst, T = 12, 6
+    win, mid = three_phase_batch(cfg, n_inst, T, seed=21)
+    with BatchEstimator(cfg, n_inst, 6) as full, BatchEstimator(cfg, n_inst, 6) as resumed:
+        ref = [full.estimate(win[t], mid[t]) for t in range(T)]
+        for t in range(3):
+            full_state_run = resumed.estimate(win[t], mid[t])
+        snap = resumed.get_state()
+        resumed.reset()
+        fresh = resumed.get_state()
+        assert np.all(fresh["freq_old"] == cfg["f0"]) and not fresh["dl0"].any() and not fresh["state"].any()
+        resumed.set_state(snap)
+        for t in range(3, T):
+            out = resumed.estimate(win[t], mid[t])
+            assert np.array_equal(out, ref[t])
+
+
+def test_dropin_error_behaviour():
+    """0 / -1 convention of reference src/pmu_estimator.c:96-105, 176-180, 280-284."""
+    pmu = PMUEstimator()
+    x = np.zeros(2048)
+    assert pmu.lib.pmu_estimate(C.byref(pmu.ctx), x.ctypes.data, C.c_double(0.0), x.ctypes.data) == -1
+    assert pmu.deinit() == -1                                               # not initialised
+    bad = EstimatorConfig.from_dict(dict(configs.DEFAULT_INI, n_bins=5))
+    assert pmu.configure_from_class(bad) == -1
+    assert pmu.configure_from_ini(str(GOLD / "ini" / "syntax_error.ini")) == -1
+    assert pmu.configure_from_ini(str(GOLD.parent.parent / "config" / "config.ini")) == 0
+    assert pmu.configure_from_class(EstimatorConfig.from_dict(configs.DEFAULT_INI)) == -1   # already initialised
+    assert pmu.estimate(signals.steady(configs.DEFAULT_INI, 0, [2.0], [50.0], [1.0])[0], 0.0) is not None
+    assert pmu.deinit() == 0
+    assert pmu.deinit() == -1
+
+
+def test_reference_python_wrapper_layout_is_safe():
+    """The reference's ctypes mirror (python/pmu_estimator.py:27-72) is a 312-byte, wrongly
+    typed buffer; our library must work through it and never write past the real 296-byte
+    pmu_context."""
+    lib = C.CDLL(str(api.lib_path()))
+    buf = (C.c_ubyte * 512)()
+    for i in range(296, 512):
+        buf[i] = 0xA5
+
+    class Cfg(C.Structure):
+        _fields_ = [("n_cycles", C.c_uint), ("f0", C.c_uint), ("frame_rate", C.c_uint), ("fs", C.c_uint),
+                    ("n_bins", C.c_uint), ("P", C.c_uint), ("Q", C.c_uint), ("iter_eipdft", C.c_bool),
+                    ("interf_trig", C.c_double), ("rocof_thresh", C.c_double * 3),
+                    ("rocof_low_pass_coeffs", C.c_double * 3)]
+
+    d = configs.DEFAULT_INI
+    cfg = Cfg(d["n_cycles"], d["f0"], d["frame_rate"], d["fs"], d["n_bins"], d["P"], d["Q"], True,
+              d["interf_trig"], (C.c_double * 3)(*d["rocof_thresh"]), (C.c_double * 3)(*d["rocof_low_pass_coeffs"]))
+    lib.pmu_init.argtypes = [C.c_void_p, C.POINTER(Cfg), C.c_bool]
+    lib.pmu_estimate.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_double, C.c_void_p]
+    lib.pmu_deinit.argtypes = [C.c_void_p]
+    assert lib.pmu_init(buf, C.byref(cfg), False) == 0
+    x = signals.steady(d, 0, [2.0], [50.0], [1.0])[0]
+    frame = (C.c_double * 4)()
+    assert lib.pmu_estimate(buf, (C.c_double * len(x))(*x), C.c_double(0.0), frame) == 0
+    assert abs(frame[0] - 2.0) < 1e-9 and abs(frame[1] - 1.0) < 1e-9 and abs(frame[2] - 50.0) < 1e-7
+    assert lib.pmu_deinit(buf) == 0
+    assert all(buf[i] == 0xA5 for i in range(296, 512))
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties + a sampled oracle check
+# ---------------------------------------------------------------------------------------
+def test_config3_full_size_properties():
+    """4096 instances x 6 channels (config 3).  Properties: (a) permuting instances permutes the
+    frames bit-exactly (no cross-stream coupling, no dependence on CTA/lane placement);
+    (b) scaling a stream by 4 scales amp by 4 and leaves ph/freq/ROCOF unchanged to rounding;
+    (c) a random sample of streams matches the oracle."""
+    torch = pytest.importorskip("torch")
+    cfg = configs.DEFAULT_INI
+    n_inst, T = 4096, 3
+    prm = signals.three_phase_params(n_inst)
+    dev = torch.device("cuda")
+    pt = {k: torch.as_tensor(v, device=dev) for k, v in prm.items()}
+    perm = torch.randperm(n_inst, generator=torch.Generator().manual_seed(1)).to(dev)
+    rng = np.random.default_rng(77)
+    sample = np.sort(rng.choice(n_inst, 24, replace=False))
+    outs, outs_p, outs_s = [], [], []
+    sample_win = np.zeros((T, len(sample), 6, configs.win_len(cfg)))
+    mids = np.zeros((T, len(sample)))
+    with BatchEstimator(cfg, n_inst, 6) as e0, BatchEstimator(cfg, n_inst, 6) as e1, BatchEstimator(cfg, n_inst, 6) as e2:
+        for t in range(T):
+            x = signals.steady(cfg, t, pt["amp"], pt["freq"], pt["phase"], xp=torch, ramp=pt["ramp"],
+                               like=pt["amp"]).reshape(n_inst, 6, -1).contiguous()
+            m = torch.full((n_inst,), signals.mid_fracsec(cfg, t), dtype=torch.float64, device=dev)
+            outs.append(e0.estimate(x, m).cpu().numpy())
+            outs_p.append(e1.estimate(x[perm].contiguous(), m).cpu().numpy())
+            outs_s.append(e2.estimate((4.0 * x).contiguous(), m).cpu().numpy())
+            sample_win[t] = x[torch.as_tensor(sample, device=dev)].cpu().numpy()
+            mids[t] = signals.mid_fracsec(cfg, t)
+    o, p, s = np.stack(outs), np.stack(outs_p), np.stack(outs_s)
+    assert np.isfinite(o).all()
+    assert np.array_equal(p, o[:, perm.cpu().numpy()])
+    assert np.allclose(s[..., 0], 4.0 * o[..., 0], rtol=1e-12, atol=0)
+    assert np.max(np.abs(s[..., 1:3] - o[..., 1:3])) < 1e-10
+    assert np.max(np.abs(s[..., 3] - o[..., 3])) < 1e-8
+    want, _, _ = checker(np.float64, 6).run(cfg, sample_win, mids, n_threads=0)
+    assert_frames_close(o[:, sample], want, "f64", "config3 sample")
+    # both ROCOF states must occur in this workload (first frame raw, later frames filtered)
+    assert abs(o[0, :, :, 3]).max() > 3.0 and abs(o[-1, :, :, 3]).max() < 3.0
+
+
+def test_config5_sharded_slice_600_samples():
+    """Config 5 is 1M channels over 8 GPUs; one rank's share is ~131k channels of 600-sample
+    windows.  Run a rank-sized shard here, check a sample against the oracle and the shard
+    boundaries helper against the whole."""
+    torch = pytest.importorskip("torch")
+    cfg = configs.CFG5_600
+    total_inst = 174763
+    lo, hi = api.shard_instances(total_inst, 3, 8)
+    n_inst = hi - lo
+    assert sum(api.shard_instances(total_inst, r, 8)[1] - api.shard_instances(total_inst, r, 8)[0] for r in range(8)) == total_inst
+    prm = signals.three_phase_params(total_inst, seed=5)
+    sl = slice(lo * 6, hi * 6)
+    dev = torch.device("cuda")
+    pt = {k: torch.as_tensor(v[sl], device=dev) for k, v in prm.items()}
+    sample = np.sort(np.random.default_rng(3).choice(n_inst, 16, replace=False))
+    T = 2
+    sample_win = np.zeros((T, len(sample), 6, configs.win_len(cfg)))
+    mids = np.zeros((T, len(sample)))
+    got = []
+    with BatchEstimator(cfg, n_inst, 6) as est:
+        assert est.info.dft_radix == 8 and est.win_len == 600
+        for t in range(T):
+            x = signals.steady(cfg, t, pt["amp"], pt["freq"], pt["phase"], xp=torch, ramp=pt["ramp"],
+                               like=pt["amp"]).reshape(n_inst, 6, -1).contiguous()
+            m = torch.full((n_inst,), signals.mid_fracsec(cfg, t), dtype=torch.float64, device=dev)
+            out = est.estimate(x, m)
+            got.append(out[torch.as_tensor(sample, device=dev)].cpu().numpy())
+            sample_win[t] = x[torch.as_tensor(sample, device=dev)].cpu().numpy()
+            mids[t] = signals.mid_fracsec(cfg, t)
+            assert bool(torch.isfinite(out).all())
+    want, _, _ = checker(np.float64, 6).run(cfg, sample_win, mids, n_threads=0)
+    assert_frames_close(np.stack(got), want, "f64", "config5 sample")

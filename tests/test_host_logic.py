@@ -1,0 +1,188 @@
+"""CPU-only tests of the host side: the C ABI loads and exports every declared symbol, struct
+layouts match the reference's ABI, .ini parsing / validation behave like the reference
+(golden from its own iniparser + check_config_validity), the launch plan is sane, and the
+kernel's lane arithmetic — compiled for the CPU by tests/host_emul — matches the oracle."""
+import ctypes as C
+import json
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import emul_lib
+import oracle_lib
+from oracle_lib import CpuChecker
+from parity import assert_frames_close, golden_floats
+from stream_cases import STREAM_CASES, stream_case_windows
+from synchropmu_b200 import api, configs, signals
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    api.build_library()
+    oracle_lib.build_oracle()
+
+
+def _declared(header: str):
+    txt = (ROOT / "include" / header).read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pmub?_[a-z_]+)\s*\(", txt)))
+
+
+@pytest.mark.parametrize("variant", [(np.float64, 1), (np.float64, 6), (np.float32, 1), (np.float32, 6)])
+def test_library_loads_and_exports_every_declared_symbol(variant):
+    lib = C.CDLL(str(api.lib_path(*variant)))
+    names = _declared("pmu_estimator.h") + _declared("pmu_batch.h")
+    assert {"pmu_init", "pmu_estimate", "pmu_deinit", "pmu_dump_frame", "pmu_batch_init", "pmu_estimate_batch",
+            "pmu_batch_deinit", "pmub_create", "pmub_estimate", "pmub_estimate_async"} <= set(names)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_struct_layouts_match_reference_abi(tmp_path):
+    """sizeof/offsetof table of SURVEY.md appendix B (printed there from the real header)."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stddef.h>\n#include "pmu_estimator.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(pmu_context),offsetof(pmu_context,pmu_initialized),sizeof(estimator_config),sizeof(pmu_frame),'
+                   'offsetof(pmu_context,buff_params),offsetof(pmu_context,hann_params),offsetof(pmu_context,rocof_params));return 0;}')
+    want = {("double", 1): (296, 288, 88, 32, 88, 128, 208), ("double", 6): (456, 448, 88, 32),
+            ("float", 1): (192, 184, 60, 16), ("float", 6): (296, 288, 60, 16)}
+    for (ft, c), exp in want.items():
+        exe = tmp_path / f"abi_{ft}_{c}"
+        subprocess.run(["gcc", f"-I{ROOT / 'include'}", f"-DNUM_CHANLS={c}", f"-DPMU_FLOAT_P={ft}", str(src), "-o", str(exe)], check=True)
+        got = tuple(int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+        assert got[:len(exp)] == exp, (ft, c, got)
+
+
+@pytest.mark.skipif(not (Path("/root/reference/src/pmu_estimator.h").exists()), reason="reference tree not mounted")
+def test_struct_layouts_identical_to_reference_header(tmp_path):
+    """Byte-for-byte: every member offset of our header == the reference header's."""
+    members = ["synch_params.win_len", "synch_params.iter_eipdft_enabled", "synch_params.interf_trig", "synch_params.df",
+               "synch_params.norm_factor", "synch_params.phasor", "buff_params.Xf", "buff_params.hann_window",
+               "buff_params.signal_windows", "hann_params.C3", "hann_params.C5", "hann_params.C6",
+               "hann_params.inv_norm_factor", "rocof_params.freq_old", "rocof_params.thresholds",
+               "rocof_params.low_pass_coeff", "rocof_params.delay_line", "rocof_params.state", "pmu_initialized"]
+    body = "".join(f'printf("%zu ", offsetof(pmu_context, {m}));' for m in members)
+    cfgm = "".join(f'printf("%zu ", offsetof(estimator_config, {m}));' for m in
+                   ["n_cycles", "Q", "iter_eipdft", "interf_trig", "rocof_thresh", "rocof_low_pass_coeffs"])
+    src = tmp_path / "off.c"
+    src.write_text(f'#include <stddef.h>\n#include "pmu_estimator.h"\nint main(){{{body}{cfgm}'
+                   'printf("%zu %zu %zu\\n", sizeof(pmu_context), sizeof(estimator_config), sizeof(pmu_frame));return 0;}')
+    for c in (1, 6):
+        ours = tmp_path / f"ours{c}"
+        subprocess.run(["gcc", f"-I{ROOT / 'include'}", f"-DNUM_CHANLS={c}", "-DPMU_FLOAT_P=float", str(src), "-o", str(ours)], check=True)
+        ref = tmp_path / f"ref{c}"
+        subprocess.run(["gcc", "-I/root/reference/src", f"-DNUM_CHANLS={c}", str(src), "-o", str(ref)], check=True)   # reference default: float
+        a = subprocess.run([str(ours)], capture_output=True, text=True, check=True).stdout
+        b = subprocess.run([str(ref)], capture_output=True, text=True, check=True).stdout
+        assert a == b
+
+
+@pytest.mark.skipif(not Path("/root/reference/examples/simple_example2.c").exists(), reason="reference tree not mounted")
+def test_reference_c_callers_compile_and_link_unchanged(tmp_path):
+    """Source compatibility: the reference's own drivers build against OUR header and link OUR
+    library without edits (they are only run on the GPU box, via examples/ of this repo)."""
+    for src, flags in (("examples/simple_example2.c", []), ("examples/simple_example.c", []),
+                       ("test/test.c", ["-DPMU_FLOAT_P=float"]), ("test/test2.c", [])):
+        lib = "pmu_estimator_f32" if flags else "pmu_estimator"
+        exe = tmp_path / (Path(src).stem + ".out")
+        r = subprocess.run(["gcc", "-O1", *flags, f"-I{ROOT / 'include'}", f"/root/reference/{src}", "-o", str(exe),
+                            f"-L{api.LIB_DIR}", f"-l{lib}", "-lm", f"-Wl,-rpath,{api.LIB_DIR}"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_ini_parsing_matches_reference_golden():
+    gold = json.loads((GOLD / "ini_configs.json").read_text())
+    assert gold
+    for rel, g in gold.items():
+        cfg = api.parse_ini(str(ROOT / rel))
+        accepted = cfg is not None and api.validate(cfg)
+        assert accepted == g["accepted"], rel
+        if accepted:
+            assert configs.win_len(cfg) == g["win_len"] and cfg["n_bins"] == g["n_bins"]
+    for name in ("config.ini", "p_class_config.ini", "m_class_config.ini"):
+        assert api.parse_ini(str(ROOT / "config" / name)) == configs.NAMED[name]
+    assert api.parse_ini(str(ROOT / "config" / "does_not_exist.ini")) is None
+
+
+@pytest.mark.parametrize("bad", [
+    dict(f0=55), dict(n_cycles=0), dict(n_cycles=51), dict(fs=25601), dict(frame_rate=0), dict(n_bins=5),
+    dict(n_bins=1025), dict(P=0), dict(interf_trig=0.0), dict(interf_trig=1.5), dict(rocof_thresh=[0.0, 25.0, 0.035]),
+])
+def test_validation_rejects_what_the_reference_rejects(bad):
+    assert api.validate(configs.DEFAULT_INI)
+    assert not api.validate(dict(configs.DEFAULT_INI, **bad))
+    assert "ERROR" in api.last_error()
+
+
+def test_create_without_gpu_fails_loudly():
+    """No CPU fallback: on a box without a CUDA device creation must raise, never estimate."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        api.BatchEstimator(configs.DEFAULT_INI, 2, 1)
+
+
+# ---- the kernel's arithmetic on the CPU (tests/host_emul) vs the oracle ---------------------
+@pytest.mark.parametrize("sc", STREAM_CASES, ids=[s["name"] for s in STREAM_CASES])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_kernel_arithmetic_matches_oracle_on_sweep(sc, dtype):
+    dt = np.float64 if dtype == "f64" else np.float32
+    cfg = configs.NAMED[sc["cfg"]]
+    win, mid = stream_case_windows(sc, dtype=dt)
+    want, km, _ = CpuChecker("port", dt, 1).run(cfg, win, mid)
+    got, flags, _spec, _plan = emul_lib.run(cfg, win[:, :, 0, :], mid, dtype=dt)
+    assert_frames_close(got, want[:, :, 0, :], dtype, sc["name"])
+    assert np.array_equal(flags & 0xFFFF, km[:, :, 0])
+
+
+def test_kernel_arithmetic_golden_single_calls_and_spectrum():
+    meta = json.loads((GOLD / "single_calls.json").read_text())
+    npz = np.load(GOLD / "single_calls.npz")
+    for case in meta:
+        dt = np.float64 if case["dtype"] == "f64" else np.float32
+        w = npz[case["key"] + "__win"]
+        got, flags, spec, _ = emul_lib.run(case["cfg"], w[None, :, :], np.full((1, 1), case["mid"]), dtype=dt,
+                                           n_channels=case["C"])
+        want = golden_floats(case["frames"]).reshape(case["C"], 4)
+        assert_frames_close(got[0], want, case["dtype"], case["key"])
+        want_spec = golden_floats(case["spectrum_re"]) + 1j * golden_floats(case["spectrum_im"])
+        scale = max(float(np.max(np.abs(want_spec))), 1e-300)
+        assert np.max(np.abs(spec[0, -1] - want_spec)) <= (1e-11 if dt == np.float64 else 2e-5) * scale
+        if not np.isnan(want).any():
+            assert int(flags[0, -1] & 0xFFFF) == case["km_last"]
+
+
+@pytest.mark.parametrize("cfg,expect", [
+    (configs.DEFAULT_INI, dict(M=16, KC=12, nslab=1)),
+    (configs.M_CLASS_INI, dict(M=16, KC=12, nslab=2)),
+    (configs.CFG5_600, dict(M=8, KC=12, nslab=1)),
+    (configs.P_CLASS_INI, dict(M=16, KC=8, nslab=1)),
+    (dict(configs.DEFAULT_INI, fs=4750, n_cycles=3, n_bins=7), dict(M=1, KC=8, nslab=1)),
+    (dict(configs.DEFAULT_INI, fs=51200, n_cycles=16, n_bins=18), dict(M=16, KC=24, nslab=8)),
+    (dict(configs.DEFAULT_INI, fs=51200, n_cycles=8, n_bins=18), dict(M=16, KC=24, nslab=4)),
+    (dict(configs.DEFAULT_INI, f0=60, fs=4800, frame_rate=60, n_cycles=5, n_bins=9), dict(M=8, KC=12, nslab=1)),
+])
+def test_plan_and_arithmetic_for_other_window_lengths(cfg, expect):
+    N = configs.win_len(cfg)
+    S, T = 5, 3
+    rng = np.random.default_rng(N)
+    win = np.zeros((T, S, 1, N))
+    mid = np.zeros((T, S))
+    f = cfg["f0"] + rng.uniform(-2, 2, S)
+    for t in range(T):
+        win[t, :, 0, :] = signals.steady(cfg, t, 1 + rng.uniform(0, 1, S), f, rng.uniform(-3, 3, S),
+                                         harmonics=[(0.1, 1.5 * cfg["f0"], 0.0)])
+        mid[t] = signals.mid_fracsec(cfg, t)
+    want, km, _ = CpuChecker("port", np.float64, 1).run(cfg, win, mid)
+    got, flags, _spec, plan = emul_lib.run(cfg, win[:, :, 0, :], mid)
+    for k, v in expect.items():
+        assert plan[k] == v, (plan, expect)
+    assert_frames_close(got, want[:, :, 0, :], "f64", f"N={N}")
+    assert np.array_equal(flags & 0xFFFF, km[:, :, 0])
