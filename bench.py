@@ -234,7 +234,8 @@ def main():
         del x
     out = torch.empty((n_inst, n_ch, 4), dtype=tdt, device=dev)
     est = BatchEstimator(cfg, n_inst, n_ch, dtype=npdt, device=local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)   # a real (non-default) stream: the kernel and the timing
+    torch.cuda.set_stream(stream)            # events below are recorded on the same stream
     est.set_stream(stream.cuda_stream)
     n_est_step = n_inst * n_ch
 

@@ -49,7 +49,8 @@ struct pmub_batch {
     unsigned char* h_in;
     unsigned char* h_out;
     size_t h_in_bytes, h_out_bytes;
-    cudaStream_t stream[2];
+    cudaStream_t stream[2];     // copy/compute overlap of the chunked host path
+    cudaEvent_t ev_order;       // orders the two worker streams after the main stream
     cudaStream_t user_stream;
     bool has_user_stream;
     long long launches;
@@ -112,7 +113,10 @@ static bool is_device_ptr(const void* p)
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-static cudaStream_t main_stream(pmub_batch* b) { return b->has_user_stream ? b->user_stream : b->stream[0]; }
+// Without a caller-supplied stream the work goes to the LEGACY default stream, which orders
+// it after everything the caller already queued on blocking streams (e.g. the kernels that
+// produced device-resident inputs) - the same implicit ordering a synchronous C library has.
+static cudaStream_t main_stream(pmub_batch* b) { return b->has_user_stream ? b->user_stream : cudaStreamLegacy; }
 
 static int free_batch(pmub_batch* b)
 {
@@ -126,6 +130,7 @@ static int free_batch(pmub_batch* b)
     if (b->h_out) cudaFreeHost(b->h_out);
     for (int i = 0; i < 2; ++i)
         if (b->stream[i]) cudaStreamDestroy(b->stream[i]);
+    if (b->ev_order) cudaEventDestroy(b->ev_order);
     delete b;
     return 0;
 }
@@ -216,6 +221,7 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     CK(cudaMalloc(&b->d_mid, (size_t)n_instances * dtype));
     CK(cudaStreamCreateWithFlags(&b->stream[0], cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&b->stream[1], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&b->ev_order, cudaEventDisableTiming));
     // small batches (the single-instance pmu_estimate path) go through pinned staging
     const size_t in_bytes = n * b->d.N * (size_t)dtype + (size_t)n_instances * dtype;
     if (in_bytes <= (size_t)(4 << 20)) {
@@ -299,7 +305,7 @@ int pmub_sync(pmub_batch* b)
 {
     if (!b) return -1;
     CUDA_OK(cudaSetDevice(b->device));
-    if (b->has_user_stream) CUDA_OK(cudaStreamSynchronize(b->user_stream));
+    CUDA_OK(cudaStreamSynchronize(main_stream(b)));
     CUDA_OK(cudaStreamSynchronize(b->stream[0]));
     CUDA_OK(cudaStreamSynchronize(b->stream[1]));
     return 0;
@@ -357,7 +363,12 @@ int pmub_estimate(pmub_batch* b, const void* windows, const void* mid, void* fra
         if ((unsigned)n_chunks > b->n_inst) n_chunks = (int)b->n_inst;
     }
     if (!mid_dev) CUDA_OK(cudaMemcpyAsync(b->d_mid, mid, mid_bytes, cudaMemcpyHostToDevice, main_stream(b)));
-    if (!mid_dev && !b->has_user_stream) CUDA_OK(cudaStreamSynchronize(main_stream(b)));
+    if (!b->has_user_stream) {
+        // the two worker streams start after whatever is already queued on the main stream
+        CUDA_OK(cudaEventRecord(b->ev_order, main_stream(b)));
+        CUDA_OK(cudaStreamWaitEvent(b->stream[0], b->ev_order, 0));
+        CUDA_OK(cudaStreamWaitEvent(b->stream[1], b->ev_order, 0));
+    }
     for (int c = 0; c < n_chunks; ++c) {
         cudaStream_t s = b->has_user_stream ? b->user_stream : b->stream[c & 1];
         const long long i0 = (long long)b->n_inst * c / n_chunks, i1 = (long long)b->n_inst * (c + 1) / n_chunks;

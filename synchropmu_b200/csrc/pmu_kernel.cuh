@@ -67,6 +67,7 @@ struct KernelArgs {
 struct CtrlBlock {
     unsigned long long full[PMU_MAX_STAGES];
     unsigned long long empty[PMU_MAX_STAGES];
+    int stage_seq[PMU_MAX_STAGES];  // how many times each stage has been released by a consumer
     int ticket;
     int batch_cnt[PMU_MAX_RAW];
     int raw_owner[PMU_MAX_RAW];
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         for (int s = 0; s < a.n_stage; ++s) {
             mbar_init(&ctrl->full[s], full_count);
             mbar_init(&ctrl->empty[s], 1u);
+            ctrl->stage_seq[s] = 0;
         }
         ctrl->ticket = 0;
         for (int i = 0; i < PMU_MAX_RAW; ++i) {
@@ -369,8 +371,13 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         for (int sl = 0; sl < a.nslab; ++sl) {
             const int idx = t * a.nslab + sl;
             const int st = idx % a.n_stage;
-            const uint32_t par = (uint32_t)((idx / a.n_stage) & 1);
-            mbar_wait(&ctrl->full[st], par);
+            const int use = idx / a.n_stage;
+            // Tickets are claimed out of order w.r.t. the ring: a parity wait is only unambiguous
+            // once the stage's previous occupant (slab idx - n_stage) has been released.
+            if (lane == 0)
+                while (ld_volatile_s32(&ctrl->stage_seq[st]) != use) __nanosleep(32);
+            __syncwarp();
+            mbar_wait(&ctrl->full[st], (uint32_t)(use & 1));
             const InT* xs = reinterpret_cast<const InT*>(stages + (size_t)st * a.stage_bytes);
             const int a_lo = sl * a.W;
             const int w_s = min(a.W, a.L - a_lo);
@@ -394,7 +401,10 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ctrl->empty[st]);
+            if (lane == 0) {
+                *reinterpret_cast<volatile int*>(&ctrl->stage_seq[st]) = use + 1;
+                mbar_arrive(&ctrl->empty[st]);
+            }
         }
         rotate_lane<KC>(sV + lane, PMU_WARP, ar, ai);
 

@@ -175,7 +175,7 @@ def test_unsupported_configuration_fails_loudly():
 def test_device_and_host_pointers_and_unaligned_loads_agree():
     torch = pytest.importorskip("torch")
     cfg = configs.DEFAULT_INI
-    n_inst = 300
+    n_inst = 700          # 69 MB of samples: the host path is split into 3 overlapped chunks
     win, mid = three_phase_batch(cfg, n_inst, 1, seed=9)
     with BatchEstimator(cfg, n_inst, 6) as a, BatchEstimator(cfg, n_inst, 6) as b, BatchEstimator(cfg, n_inst, 6) as c:
         host = a.estimate(win[0], mid[0])                                   # chunked host path
@@ -292,8 +292,8 @@ def test_config3_full_size_properties():
     assert np.max(np.abs(s[..., 3] - o[..., 3])) < 1e-8
     want, _, _ = checker(np.float64, 6).run(cfg, sample_win, mids, n_threads=0)
     assert_frames_close(o[:, sample], want, "f64", "config3 sample")
-    # both ROCOF states must occur in this workload (first frame raw, later frames filtered)
-    assert abs(o[0, :, :, 3]).max() > 3.0 and abs(o[-1, :, :, 3]).max() < 3.0
+    # first frame: freq_old = f0 makes |ROCOF| large (raw state); afterwards it follows the +-1 Hz/s ramps
+    assert abs(o[0, :, :, 3]).max() > 3.0 and np.median(abs(o[-1, :, :, 3])) < 1.5
 
 
 def test_config5_sharded_slice_600_samples():
