@@ -50,12 +50,14 @@ WORKLOADS = {
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--frames", type=int, default=4, help="distinct consecutive frames resident in HBM")
+    ap.add_argument("--frames-per-step", type=int, default=8,
+                    help="consecutive frames of every stream handed to one pmub_estimate_frames call (= one step)")
+    ap.add_argument("--sets", type=int, default=2, help="distinct input sets (each frames-per-step frames) cycled in HBM")
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -185,8 +187,9 @@ def main():
     bpe = configs.bytes_per_estimate(cfg, itemsize, n_ch)
     config = dict(workload=f"{args.workload}: {wl['desc']}", n_instances_per_gpu=n_inst, n_channels=n_ch,
                   win_len=N, n_bins=cfg["n_bins"], P=cfg["P"], Q=cfg["Q"], iter_eipdft=cfg["iter_eipdft"],
-                  frames_resident=args.frames, parallelism=f"instances sharded over {world} GPU(s), no collective",
-                  l2_policy="inputs larger than L2 (frames cycled, %.0f MB each)" % (n_inst * n_ch * N * itemsize / 1e6),
+                  frames_per_step=args.frames_per_step, frames_resident=args.frames_per_step * args.sets, parallelism=f"instances sharded over {world} GPU(s), no collective",
+                  l2_policy="inputs larger than L2 (%.0f MB per frame, %d distinct frames cycled)" % (
+                      n_inst * n_ch * N * itemsize / 1e6, args.frames_per_step * args.sets),
                   interharmonic=bool(args.interharmonic))
 
     # ---------------- reference arm: the CPU implementation on the host cores ----------------
@@ -225,22 +228,27 @@ def main():
     sl = slice(rank * n_inst * n_ch, (rank + 1) * n_inst * n_ch)
     pt = {k: torch.as_tensor(v[sl], device=dev) for k, v in prm.items()}
     harm = [(0.1, 75.0, 0.0)] if args.interharmonic else []
-    frames_in, mids = [], []
-    for t in range(args.frames):
+    F = args.frames_per_step
+    n_frames_res = F * args.sets
+    win_all = torch.empty((n_frames_res, n_inst, n_ch, N), dtype=tdt, device=dev)
+    mid_all = torch.empty((n_frames_res, n_inst), dtype=tdt, device=dev)
+    for t in range(n_frames_res):
         x = signals.steady(cfg, t, pt["amp"], pt["freq"], pt["phase"], xp=torch, ramp=pt["ramp"], harmonics=harm,
                            like=pt["amp"])
-        frames_in.append(x.to(tdt).reshape(n_inst, n_ch, N).contiguous())
-        mids.append(torch.full((n_inst,), signals.mid_fracsec(cfg, t), dtype=tdt, device=dev))
+        win_all[t] = x.to(tdt).reshape(n_inst, n_ch, N)
+        mid_all[t] = signals.mid_fracsec(cfg, t)
         del x
-    out = torch.empty((n_inst, n_ch, 4), dtype=tdt, device=dev)
+    out = torch.empty((F, n_inst, n_ch, 4), dtype=tdt, device=dev)
     est = BatchEstimator(cfg, n_inst, n_ch, dtype=npdt, device=local_rank)
     stream = torch.cuda.Stream(device=dev)   # a real (non-default) stream: the kernel and the timing
+    torch.cuda.synchronize()
     torch.cuda.set_stream(stream)            # events below are recorded on the same stream
     est.set_stream(stream.cuda_stream)
-    n_est_step = n_inst * n_ch
+    n_est_step = n_inst * n_ch * F
 
     def step(i):
-        est.estimate_async(frames_in[i % args.frames], mids[i % args.frames], out)
+        s0 = (i % args.sets) * F
+        est.estimate_frames_async(F, win_all[s0:s0 + F], mid_all[s0:s0 + F], out)
 
     for i in range(max(3, args.warmup)):
         step(i)
@@ -287,25 +295,44 @@ def main():
     # optional gather of the frames to rank 0 over NCCL/NVLink (off the hot path, timed separately)
     gather_ms = None
     if dist is not None:
-        bufs = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+        last = out[F - 1].contiguous()
+        bufs = [torch.empty_like(last) for _ in range(world)] if rank == 0 else None
         torch.cuda.synchronize()
         dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        dist.gather(out, bufs, dst=0)
+        dist.gather(last, bufs, dst=0)
         g1.record()
         torch.cuda.synchronize()
         gather_ms = g0.elapsed_time(g1)
 
+    # ---------------- the same kernel launched one frame at a time (pmub_estimate_async) ----------
+    single = None
+    if F > 1:
+        out1 = out[0]
+        n1 = max(20, min(args.steps * F, 400))
+        for i in range(5):
+            est.estimate_async(win_all[i % n_frames_res], mid_all[i % n_frames_res], out1)
+        s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0e.record(stream)
+        for i in range(n1):
+            est.estimate_async(win_all[i % n_frames_res], mid_all[i % n_frames_res], out1)
+        s1e.record(stream)
+        torch.cuda.synchronize()
+        ms1 = s0e.elapsed_time(s1e) / n1
+        single = dict(value=world * n_inst * n_ch / (ms1 * 1e-3), unit=UNIT, ms_per_launch=ms1,
+                      note="one frame (%d estimates) per kernel launch" % (n_inst * n_ch))
+
     # ---------------- e2e: pinned host buffers through the synchronous C-ABI call ----------------
     e2e = None
     if not args.no_e2e:
+        torch.cuda.set_stream(torch.cuda.default_stream(dev))
         est.set_stream(None)
         est.reset()
         host_in = [torch.empty((n_inst, n_ch, N), dtype=tdt).pin_memory() for _ in range(2)]
         for i in range(2):
-            host_in[i].copy_(frames_in[i % args.frames])
-        host_mid = [mids[i % args.frames].cpu().pin_memory() for i in range(2)]
+            host_in[i].copy_(win_all[i % n_frames_res])
+        host_mid = [mid_all[i % n_frames_res].cpu().pin_memory() for i in range(2)]
         host_out = torch.empty((n_inst, n_ch, 4), dtype=tdt).pin_memory()
         hin = [h.numpy() for h in host_in]
         hmid = [h.numpy() for h in host_mid]
@@ -324,10 +351,11 @@ def main():
             tm = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             dt = float(tm.item())
-        e2e = dict(value=world * n_est_step * args.e2e_steps / dt, unit=UNIT,
+        e2e = dict(value=world * n_inst * n_ch * args.e2e_steps / dt, unit=UNIT,
                    h2d_bytes_per_step=int(n_inst * n_ch * N * itemsize + n_inst * itemsize),
                    d2h_bytes_per_step=int(n_inst * n_ch * 4 * itemsize), steps=args.e2e_steps,
-                   ms_per_step=dt / args.e2e_steps * 1e3, host_memory="pinned")
+                   ms_per_step=dt / args.e2e_steps * 1e3, host_memory="pinned",
+                   note="one frame per synchronous pmub_estimate call, H2D of the windows and D2H of the frames inside")
 
     if rank != 0:
         if dist is not None:
@@ -352,7 +380,7 @@ def main():
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                 ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype,
                 data="synthetic", config=config, roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, clocks=clocks,
-                gpu_launches=int(launches), outputs_finite=finite, impl="ours")
+                gpu_launches=int(launches), outputs_finite=finite, impl="ours", single_frame_launch=single)
     if gather_ms is not None:
         line["frame_gather_ms"] = gather_ms
     print(json.dumps(line))

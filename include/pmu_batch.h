@@ -100,6 +100,18 @@ int pmub_estimate(pmub_batch *b, const void *windows, const void *mid_fracsec, v
 /* Device pointers only; enqueues on the batch's stream and returns immediately. */
 int pmub_estimate_async(pmub_batch *b, const void *d_windows, const void *d_mid_fracsec,
                         void *d_frames);
+/* Several consecutive frames of the same streams in one call (e.g. a replay, or a streaming front
+ * end that hands over a block of frames): exactly equivalent to calling pmub_estimate n_frames
+ * times, frame f reading
+ *   windows     float_p [n_frames][n_instances][n_channels][win_len]
+ *   mid_fracsec float_p [n_frames][n_instances]
+ * and writing frames float_p [n_frames][n_instances][n_channels][4]; the ROCOF state of every
+ * stream is carried from frame to frame inside the kernel, so the launch ramp-up and the tail are
+ * paid once per call instead of once per frame. */
+int pmub_estimate_frames(pmub_batch *b, int n_frames, const void *windows, const void *mid_fracsec,
+                         void *frames);
+int pmub_estimate_frames_async(pmub_batch *b, int n_frames, const void *d_windows,
+                               const void *d_mid_fracsec, void *d_frames);
 int pmub_sync(pmub_batch *b);
 /* Run on the caller's CUDA stream (cudaStream_t passed as void*); NULL = own stream. */
 int pmub_set_stream(pmub_batch *b, void *cuda_stream);

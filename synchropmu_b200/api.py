@@ -107,6 +107,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.pmub_get_info.argtypes = [vp, C.POINTER(BatchInfo)]
     lib.pmub_estimate.argtypes = [vp, vp, vp, vp]
     lib.pmub_estimate_async.argtypes = [vp, vp, vp, vp]
+    lib.pmub_estimate_frames.argtypes = [vp, ip, vp, vp, vp]
+    lib.pmub_estimate_frames_async.argtypes = [vp, ip, vp, vp, vp]
     lib.pmub_sync.argtypes = [vp]
     lib.pmub_set_stream.argtypes = [vp, vp]
     lib.pmub_launch_count.argtypes = [vp]
@@ -117,7 +119,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.pmub_set_debug.argtypes = [vp, ip]
     lib.pmub_get_debug.argtypes = [vp, vp, vp]
     for fn in ("pmub_validate", "pmub_parse_ini", "pmub_create", "pmub_create_ini", "pmub_destroy",
-               "pmub_get_info", "pmub_estimate", "pmub_estimate_async", "pmub_sync", "pmub_set_stream",
+               "pmub_get_info", "pmub_estimate", "pmub_estimate_async", "pmub_estimate_frames",
+               "pmub_estimate_frames_async", "pmub_sync", "pmub_set_stream",
                "pmub_reset", "pmub_get_state", "pmub_set_state", "pmub_set_debug", "pmub_get_debug"):
         getattr(lib, fn).restype = ip
     if path is None:
@@ -229,6 +232,36 @@ class BatchEstimator:
                 out = np.empty((n, c, 4), dtype=self.dtype)
         self._check(self.lib.pmub_estimate(self._h, _ptr(windows), _ptr(mid_fracsec), _ptr(out)), "pmub_estimate")
         return out
+
+    def estimate_frames(self, windows, mid_fracsec, out=None):
+        """``n_frames`` consecutive frames in one call: windows ``[F, n_instances, n_channels, win_len]``,
+        mid_fracsec ``[F, n_instances]`` -> frames ``[F, n_instances, n_channels, 4]``.  Same results as
+        F calls of :meth:`estimate`; the kernel carries the ROCOF state from frame to frame."""
+        n, c = self.n_instances, self.n_channels
+        is_torch = hasattr(windows, "data_ptr")
+        if is_torch:
+            import torch
+
+            tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+            F = int(windows.shape[0])
+            assert windows.dtype == tdt and windows.is_contiguous() and windows.numel() == F * n * c * self.win_len
+            assert mid_fracsec.dtype == tdt and mid_fracsec.is_contiguous() and mid_fracsec.numel() == F * n
+            if out is None:
+                out = torch.empty((F, n, c, 4), dtype=tdt, device=windows.device)
+        else:
+            windows = np.ascontiguousarray(windows, dtype=self.dtype)
+            mid_fracsec = np.ascontiguousarray(mid_fracsec, dtype=self.dtype)
+            F = int(windows.shape[0])
+            assert windows.size == F * n * c * self.win_len and mid_fracsec.size == F * n
+            if out is None:
+                out = np.empty((F, n, c, 4), dtype=self.dtype)
+        self._check(self.lib.pmub_estimate_frames(self._h, F, _ptr(windows), _ptr(mid_fracsec), _ptr(out)),
+                    "pmub_estimate_frames")
+        return out
+
+    def estimate_frames_async(self, n_frames: int, d_windows, d_mid_fracsec, d_out) -> None:
+        self._check(self.lib.pmub_estimate_frames_async(self._h, int(n_frames), _ptr(d_windows), _ptr(d_mid_fracsec),
+                                                        _ptr(d_out)), "pmub_estimate_frames_async")
 
     def estimate_async(self, d_windows, d_mid_fracsec, d_out) -> None:
         """Device tensors only; enqueue on the batch stream and return."""

@@ -39,9 +39,13 @@ struct pmub_batch {
     pmu_c *dU, *dV, *dT;
     double *st_fold, *st_dl0, *st_dl1;
     unsigned char* st_state;
-    unsigned char* d_windows;   // staging for host inputs (lazy)
+    unsigned char* d_windows;   // staging for host inputs (lazy, grows with the frame count)
+    size_t d_windows_cap;
     unsigned char* d_mid;
+    size_t d_mid_cap;
     unsigned char* d_out;       // frames [n][4] float_p, then export [n][4] double
+    unsigned char* d_frames;    // staging for multi-frame host outputs (lazy)
+    size_t d_frames_cap;
     int* d_dbg;
     double* d_spec;
     bool debug, mirror;
@@ -71,11 +75,12 @@ static int grid_for(const pmub_batch* b, long long n)
     return (int)g;
 }
 
-// Launch the kernel over windows [w0, w1) of the batch (w0 on an instance boundary).
-static int launch_range(pmub_batch* b, long long w0, long long w1, const void* d_windows_base,
+// Launch the kernel over streams [w0, w1) of the batch (w0 on an instance boundary), for
+// n_frames consecutive frames laid out frame-major with the full batch as frame pitch.
+static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames, const void* d_windows_base,
                         const void* d_mid_base, void* d_frames_base, double* d_export_base, cudaStream_t s)
 {
-    if (w1 <= w0) return 0;
+    if (w1 <= w0 || n_frames < 1) return 0;
     KernelArgs a = b->args;
     const size_t sz = (size_t)b->dtype;
     a.windows = (const unsigned char*)d_windows_base + (size_t)w0 * b->d.N * sz;
@@ -86,6 +91,9 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, const void* d
     a.st_dl1 = b->st_dl1 + w0;
     a.st_state = b->st_state + w0;
     a.n_windows = w1 - w0;
+    a.n_frames = n_frames;
+    a.frame_stride = b->n_windows;
+    a.mid_frame_stride = b->n_inst;
     a.dbg = b->debug ? b->d_dbg + w0 : nullptr;
     a.spec_out = b->debug ? b->d_spec + (size_t)w0 * b->cfg.n_bins * 2 : nullptr;
     a.state_export = d_export_base ? d_export_base + (size_t)w0 * 4 : nullptr;
@@ -100,6 +108,50 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, const void* d
                                     : pmu_launch_f32(b->plan.M, b->plan.KC, a, grid, block, b->plan.smem_bytes, s);
     if (rc == 0) b->launches++;
     return rc;
+}
+
+// How many consecutive frames one launch over `n` streams may carry: the in-kernel frame
+// dependency tracks groups of 32 streams per CTA in a fixed-size table, and debug recording
+// keeps one frame of observations.
+static int frames_per_launch(const pmub_batch* b, long long n, int n_frames)
+{
+    if (n_frames <= 1 || b->debug) return 1;
+    const int grid = grid_for(b, n);
+    const long long n_local = (n + grid - 1) / grid;
+    if ((n_local + PMU_WARP - 1) / PMU_WARP > PMU_MAX_GROUPS) return 1;
+    if (n_local * (long long)n_frames * b->plan.nslab > (1ll << 30)) return 1;
+    return n_frames;
+}
+
+// launch_range for any frame count: splits into per-frame launches when one launch cannot carry them
+static int launch_frames(pmub_batch* b, long long w0, long long w1, int n_frames, const void* dW, const void* dM,
+                         void* dF, double* d_export, cudaStream_t s)
+{
+    const int fpl = frames_per_launch(b, w1 - w0, n_frames);
+    const size_t sz = (size_t)b->dtype;
+    for (int f = 0; f < n_frames; f += fpl) {
+        const int nf = (n_frames - f < fpl) ? n_frames - f : fpl;
+        if (launch_range(b, w0, w1, nf, (const unsigned char*)dW + (size_t)f * b->n_windows * b->d.N * sz,
+                         (const unsigned char*)dM + (size_t)f * b->n_inst * sz, (unsigned char*)dF + (size_t)f * b->n_windows * 4 * sz,
+                         d_export, s))
+            return -1;
+    }
+    return 0;
+}
+
+static int ensure_cap(unsigned char** p, size_t* cap, size_t need)
+{
+    if (*cap >= need) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) {
+        set_error(std::string("[pmu_estimate] CUDA ERROR: ") + cudaGetErrorString(e) + " allocating staging memory");
+        return -1;
+    }
+    *cap = need;
+    return 0;
 }
 
 static bool is_device_ptr(const void* p)
@@ -124,7 +176,7 @@ static int free_batch(pmub_batch* b)
     cudaSetDevice(b->device);
     cudaFree(b->dU); cudaFree(b->dV); cudaFree(b->dT);
     cudaFree(b->st_fold); cudaFree(b->st_dl0); cudaFree(b->st_dl1); cudaFree(b->st_state);
-    cudaFree(b->d_windows); cudaFree(b->d_mid); cudaFree(b->d_out);
+    cudaFree(b->d_windows); cudaFree(b->d_mid); cudaFree(b->d_out); cudaFree(b->d_frames);
     cudaFree(b->d_dbg); cudaFree(b->d_spec);
     if (b->h_in) cudaFreeHost(b->h_in);
     if (b->h_out) cudaFreeHost(b->h_out);
@@ -219,6 +271,7 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     CK(cudaMalloc(&b->st_state, n));
     CK(cudaMalloc(&b->d_out, n * 4 * (size_t)dtype + n * 4 * sizeof(double)));
     CK(cudaMalloc(&b->d_mid, (size_t)n_instances * dtype));
+    b->d_mid_cap = (size_t)n_instances * dtype;
     CK(cudaStreamCreateWithFlags(&b->stream[0], cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&b->stream[1], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&b->ev_order, cudaEventDisableTiming));
@@ -230,6 +283,7 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
         CK(cudaMallocHost(&b->h_in, b->h_in_bytes));
         CK(cudaMallocHost(&b->h_out, b->h_out_bytes));
         CK(cudaMalloc(&b->d_windows, n * b->d.N * (size_t)dtype));
+        b->d_windows_cap = n * b->d.N * (size_t)dtype;
     }
 #undef CK
 
@@ -311,37 +365,42 @@ int pmub_sync(pmub_batch* b)
     return 0;
 }
 
-int pmub_estimate_async(pmub_batch* b, const void* d_windows, const void* d_mid, void* d_frames)
+int pmub_estimate_frames_async(pmub_batch* b, int n_frames, const void* d_windows, const void* d_mid, void* d_frames)
 {
-    if (!b || !d_windows || !d_mid || !d_frames) { set_error("[pmu_estimate] ERROR: NULL argument"); return -1; }
+    if (!b || !d_windows || !d_mid || !d_frames || n_frames < 1) { set_error("[pmu_estimate] ERROR: bad argument"); return -1; }
     CUDA_OK(cudaSetDevice(b->device));
-    return launch_range(b, 0, b->n_windows, d_windows, d_mid, d_frames, nullptr, main_stream(b));
+    return launch_frames(b, 0, b->n_windows, n_frames, d_windows, d_mid, d_frames, nullptr, main_stream(b));
 }
 
-int pmub_estimate(pmub_batch* b, const void* windows, const void* mid, void* frames)
+int pmub_estimate_async(pmub_batch* b, const void* d_windows, const void* d_mid, void* d_frames)
 {
-    if (!b || !windows || !mid || !frames) { set_error("[pmu_estimate] ERROR: NULL argument"); return -1; }
+    return pmub_estimate_frames_async(b, 1, d_windows, d_mid, d_frames);
+}
+
+int pmub_estimate_frames(pmub_batch* b, int n_frames, const void* windows, const void* mid, void* frames)
+{
+    if (!b || !windows || !mid || !frames || n_frames < 1) { set_error("[pmu_estimate] ERROR: bad argument"); return -1; }
     CUDA_OK(cudaSetDevice(b->device));
     const size_t sz = (size_t)b->dtype;
     const size_t n = (size_t)b->n_windows;
-    const size_t win_bytes = n * b->d.N * sz, mid_bytes = (size_t)b->n_inst * sz, fr_bytes = n * 4 * sz;
+    const size_t win_bytes = n * b->d.N * sz, mid_bytes = (size_t)b->n_inst * sz, fr_bytes = n * 4 * sz;  // per frame
     const bool win_dev = is_device_ptr(windows), mid_dev = is_device_ptr(mid), fr_dev = is_device_ptr(frames);
     double* d_export = reinterpret_cast<double*>(b->d_out + fr_bytes);
 
     if (win_dev && mid_dev && fr_dev && !b->mirror) {
-        if (launch_range(b, 0, b->n_windows, windows, mid, frames, nullptr, main_stream(b))) return -1;
+        if (launch_frames(b, 0, b->n_windows, n_frames, windows, mid, frames, nullptr, main_stream(b))) return -1;
         CUDA_OK(cudaStreamSynchronize(main_stream(b)));
         return 0;
     }
 
-    // ---- small batch, host buffers: one pinned round trip (the pmu_estimate path) ----
-    if (b->h_in && !win_dev && !mid_dev && !fr_dev) {
+    // ---- small batch, one frame, host buffers: one pinned round trip (the pmu_estimate path) ----
+    if (b->h_in && n_frames == 1 && !win_dev && !mid_dev && !fr_dev) {
         cudaStream_t s = main_stream(b);
         memcpy(b->h_in, windows, win_bytes);
         memcpy(b->h_in + win_bytes, mid, mid_bytes);
         CUDA_OK(cudaMemcpyAsync(b->d_windows, b->h_in, win_bytes, cudaMemcpyHostToDevice, s));
         CUDA_OK(cudaMemcpyAsync(b->d_mid, b->h_in + win_bytes, mid_bytes, cudaMemcpyHostToDevice, s));
-        if (launch_range(b, 0, b->n_windows, b->d_windows, b->d_mid, b->d_out, b->mirror ? d_export : nullptr, s)) return -1;
+        if (launch_range(b, 0, b->n_windows, 1, b->d_windows, b->d_mid, b->d_out, b->mirror ? d_export : nullptr, s)) return -1;
         const size_t back = b->mirror ? b->h_out_bytes : fr_bytes;
         CUDA_OK(cudaMemcpyAsync(b->h_out, b->d_out, back, cudaMemcpyDeviceToHost, s));
         CUDA_OK(cudaStreamSynchronize(s));
@@ -350,19 +409,21 @@ int pmub_estimate(pmub_batch* b, const void* windows, const void* mid, void* fra
     }
 
     // ---- general path: chunk by instance, copies overlapped with kernels on two streams ----
-    if (!win_dev && !b->d_windows) CUDA_OK(cudaMalloc(&b->d_windows, win_bytes));
+    if (!win_dev && ensure_cap(&b->d_windows, &b->d_windows_cap, win_bytes * n_frames)) return -1;
+    if (!mid_dev && ensure_cap(&b->d_mid, &b->d_mid_cap, mid_bytes * n_frames)) return -1;
+    if (!fr_dev && n_frames > 1 && ensure_cap(&b->d_frames, &b->d_frames_cap, fr_bytes * n_frames)) return -1;
     const unsigned char* dW = win_dev ? (const unsigned char*)windows : b->d_windows;
     const unsigned char* dM = mid_dev ? (const unsigned char*)mid : b->d_mid;
-    unsigned char* dF = fr_dev ? (unsigned char*)frames : b->d_out;
+    unsigned char* dF = fr_dev ? (unsigned char*)frames : (n_frames > 1 ? b->d_frames : b->d_out);
     int n_chunks = 1;
     if (!win_dev) {
         const size_t target = 32u << 20;  // ~32 MiB of samples per chunk
-        n_chunks = (int)((win_bytes + target - 1) / target);
+        n_chunks = (int)((win_bytes * n_frames + target - 1) / target);
         if (n_chunks < 1) n_chunks = 1;
         if (n_chunks > 64) n_chunks = 64;
         if ((unsigned)n_chunks > b->n_inst) n_chunks = (int)b->n_inst;
     }
-    if (!mid_dev) CUDA_OK(cudaMemcpyAsync(b->d_mid, mid, mid_bytes, cudaMemcpyHostToDevice, main_stream(b)));
+    if (!mid_dev) CUDA_OK(cudaMemcpyAsync(b->d_mid, mid, mid_bytes * n_frames, cudaMemcpyHostToDevice, main_stream(b)));
     if (!b->has_user_stream) {
         // the two worker streams start after whatever is already queued on the main stream
         CUDA_OK(cudaEventRecord(b->ev_order, main_stream(b)));
@@ -373,15 +434,21 @@ int pmub_estimate(pmub_batch* b, const void* windows, const void* mid, void* fra
         cudaStream_t s = b->has_user_stream ? b->user_stream : b->stream[c & 1];
         const long long i0 = (long long)b->n_inst * c / n_chunks, i1 = (long long)b->n_inst * (c + 1) / n_chunks;
         const long long w0 = i0 * b->C, w1 = i1 * b->C;
-        if (!win_dev)
-            CUDA_OK(cudaMemcpyAsync(b->d_windows + (size_t)w0 * b->d.N * sz, (const unsigned char*)windows + (size_t)w0 * b->d.N * sz,
-                                    (size_t)(w1 - w0) * b->d.N * sz, cudaMemcpyHostToDevice, s));
-        if (launch_range(b, w0, w1, dW, dM, dF, b->mirror ? d_export : nullptr, s)) return -1;
+        if (!win_dev)   // rows = frames, row pitch = one full frame of the batch
+            CUDA_OK(cudaMemcpy2DAsync(b->d_windows + (size_t)w0 * b->d.N * sz, win_bytes,
+                                      (const unsigned char*)windows + (size_t)w0 * b->d.N * sz, win_bytes,
+                                      (size_t)(w1 - w0) * b->d.N * sz, (size_t)n_frames, cudaMemcpyHostToDevice, s));
+        if (launch_frames(b, w0, w1, n_frames, dW, dM, dF, b->mirror ? d_export : nullptr, s)) return -1;
         if (!fr_dev)
-            CUDA_OK(cudaMemcpyAsync((unsigned char*)frames + (size_t)w0 * 4 * sz, dF + (size_t)w0 * 4 * sz, (size_t)(w1 - w0) * 4 * sz,
-                                    cudaMemcpyDeviceToHost, s));
+            CUDA_OK(cudaMemcpy2DAsync((unsigned char*)frames + (size_t)w0 * 4 * sz, fr_bytes, dF + (size_t)w0 * 4 * sz, fr_bytes,
+                                      (size_t)(w1 - w0) * 4 * sz, (size_t)n_frames, cudaMemcpyDeviceToHost, s));
     }
     return pmub_sync(b);
+}
+
+int pmub_estimate(pmub_batch* b, const void* windows, const void* mid, void* frames)
+{
+    return pmub_estimate_frames(b, 1, windows, mid, frames);
 }
 
 int pmub_get_state(pmub_batch* b, double* freq_old, double* dl0, double* dl1, unsigned char* state)

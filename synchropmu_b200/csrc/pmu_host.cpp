@@ -264,21 +264,33 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
         if (N % m == 0 && (N / m >= 32 || m == 1)) { p.M = m; break; }
     p.L = N / p.M;
 
-    const int stage_target = env_int("PMU_STAGE_BYTES", 16384);
-    if (N * s <= stage_target) {
-        p.W = p.L;
-        p.nslab = 1;
-        p.stage_bytes = align_up(N * s, 128);
+    if (p.M == 16) {
+        // fixed row pitch: slabs are at most PMU_PITCH16 residues wide, rows PMU_PITCH16 elements apart
+        p.pitch = PMU_PITCH16;
+        p.W = p.L < PMU_PITCH16 ? p.L : PMU_PITCH16;
+        p.nslab = (p.L + p.W - 1) / p.W;
+        p.stage_bytes = align_up(p.M * p.pitch * s, 128);
     } else {
-        int w = stage_target / (p.M * s) / 32 * 32;
-        if (w < 32) w = 32;
-        if (w > p.L) w = align_up(p.L, 32);
-        p.W = w;
-        p.nslab = (p.L + w - 1) / w;
-        p.stage_bytes = align_up(p.M * w * s, 128);
-        if (p.nslab == 1) p.W = p.L, p.stage_bytes = align_up(N * s, 128);
+        const int stage_target = env_int("PMU_STAGE_BYTES", 16384);
+        if (N * s <= stage_target) {
+            p.W = p.L;
+            p.nslab = 1;
+        } else {
+            int w = stage_target / (p.M * s) / 32 * 32;
+            if (w < 32) w = 32;
+            if (w >= p.L) w = p.L;
+            p.W = w;
+            p.nslab = (p.L + w - 1) / w;
+        }
+        p.pitch = p.W;
+        p.stage_bytes = align_up(p.M * p.W * s, 128);
     }
-    p.aligned16 = ((N * s) % 16 == 0) && (p.nslab == 1 || ((p.L * s) % 16 == 0 && (p.W * s) % 16 == 0));
+    // TMA bulk copies: whole window when its rows are already contiguous at the stage pitch,
+    // otherwise one copy per row; both need 16-byte granularity
+    const bool whole = (p.nslab == 1 && p.pitch == p.L);
+    p.aligned16 = whole ? ((N * s) % 16 == 0)
+                        : ((N * s) % 16 == 0 && (p.L * s) % 16 == 0 && (p.W * s) % 16 == 0 &&
+                           ((p.L - (p.nslab - 1) * p.W) * s) % 16 == 0 && (p.pitch * s) % 16 == 0);
 
     p.n_cons = env_int("PMU_CONSUMER_WARPS", PMU_MAX_CONSUMERS);
     if (p.n_cons < 1) p.n_cons = 1;

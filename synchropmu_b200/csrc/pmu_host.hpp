@@ -36,6 +36,7 @@ Derived derive(const pmub_config& c, int dtype);
 struct Plan {
     int M, KC;          // codelet size, bins per lane
     int L, W, nslab;    // residues, slab width, slabs per window
+    int pitch;          // stage row pitch in elements (PMU_PITCH16 for the 16-point codelet, else W)
     int Kp;             // n_bins + 1
     int n_stage, stage_bytes;
     int n_cons, n_raw, raw_stride, n_post;

@@ -10,6 +10,9 @@
 // a batch of <= 32 consecutive windows becomes its POST-PROCESSOR: lane = window, Hann in
 // the frequency domain, IpDFT / e-IpDFT / interference iterations (pmu_math.cuh), ROCOF
 // state read-modify-write in HBM, frame store.  No block-wide barrier after start-up.
+// A launch may carry several consecutive frames of the same streams: the ring then streams
+// (frame, stream) items frame-major, and a batch of frame f waits for the same streams' batch of
+// frame f-1 before touching the ROCOF state, so only one ramp-up and one tail are paid per launch.
 //
 // Replaces reference src/pmu_estimator.c:170-271 (pmu_estimate) for a whole batch.
 #pragma once
@@ -26,8 +29,10 @@
 #endif
 #define PMU_MAX_CONSUMERS (PMU_BLOCK_THREADS / PMU_WARP - 1)
 #define PMU_MAX_STAGES 16
+#define PMU_PITCH16 128  // stage row pitch (elements) of the 16-point-codelet kernels
 #define PMU_MAX_RAW 8
 #define PMU_MAX_POST 8
+#define PMU_MAX_GROUPS 256  // groups of <= 32 streams per CTA when a launch carries several frames
 
 enum { PMU_LOAD_BULK = 0, PMU_LOAD_ELEM = 1 };
 
@@ -57,11 +62,16 @@ struct KernelArgs {
     double* st_dl0;
     double* st_dl1;
     unsigned char* st_state;
-    long long n_windows;
-    // optional debug / mirror outputs (may be null)
-    int* dbg;                    // [n_windows]  km | flags
-    double* spec_out;            // [n_windows][K][2] Hann-windowed bins
-    double* state_export;        // [n_windows][4]  f_old, dl0, dl1, state after the update
+    long long n_windows;         // windows (streams) handled by this launch
+    // consecutive frames processed by this launch, in order, per stream (ROCOF state carried)
+    int n_frames;
+    long long frame_stride;      // streams per frame in the caller's arrays (>= n_windows: a launch
+                                 // may cover a sub-range of the batch), in windows
+    long long mid_frame_stride;  // instances per frame in `mid`
+    // optional debug / mirror outputs (may be null); frame-major like `frames`
+    int* dbg;                    // [n_frames][frame_stride]  km | flags
+    double* spec_out;            // [n_frames][frame_stride][K][2] Hann-windowed bins
+    double* state_export;        // [frame_stride][4]  f_old, dl0, dl1, state after the last frame
 };
 
 struct CtrlBlock {
@@ -72,6 +82,7 @@ struct CtrlBlock {
     int batch_cnt[PMU_MAX_RAW];
     int raw_owner[PMU_MAX_RAW];
     int post_lock[PMU_MAX_POST];
+    int grp_done[PMU_MAX_GROUPS];   // per group of <= 32 streams: frames fully post-processed
 };
 
 #if defined(__CUDACC__)
@@ -181,24 +192,21 @@ struct BatchMap {
 };
 
 // ---- post-processing of one batch (lane = window) --------------------------------------
+// Batch = <= 32 consecutive streams of this CTA at frame f.  w_first = index (within this
+// launch) of the batch's first stream.
 template <typename InT>
-__device__ __noinline__ void post_batch(const KernelArgs& a, const PostParams& pp, unsigned char* smem, int raw_buf,
-                                        int post_slot, long long w_first, int bsz, int batch_id, int lane)
+__device__ __noinline__ void post_batch(const KernelArgs& a, const PostParams& pp, int raw_buf, int post_slot,
+                                        long long w_first, int frame, int bsz, int batch_id, int lane)
 {
+    extern __shared__ __align__(128) unsigned char smem[];
     CtrlBlock* ctrl = reinterpret_cast<CtrlBlock*>(smem + a.off_ctrl);
     const int K = pp.K;
-    pmu_c* scratch;
-    if (a.scratch_global)
-        scratch = a.scratch + ((size_t)blockIdx.x * a.n_post + post_slot) * (size_t)(2 * K * PMU_WARP);
-    else
-        scratch = reinterpret_cast<pmu_c*>(smem + a.off_post) + (size_t)post_slot * (2 * K * PMU_WARP);
-    Col X, Wk;
-    X.base = scratch + lane;
-    X.stride = PMU_WARP;
-    Wk.base = scratch + K * PMU_WARP + lane;
-    Wk.stride = PMU_WARP;
+    pmu_c* scratch = reinterpret_cast<pmu_c*>(smem + a.off_post) + (size_t)post_slot * (2 * K * PMU_WARP);
+    const Col X = Col::make(scratch + lane, PMU_WARP);
+    const Col Wk = Col::make(scratch + K * PMU_WARP + lane, PMU_WARP);
     const bool active = lane < bsz;
-    const long long w = w_first + lane;
+    const long long w = w_first + lane;                         // stream index within the launch
+    const long long wf = (long long)frame * a.frame_stride + w; // row in the frame-major arrays
 
     if (active) {
         const double* row = reinterpret_cast<const double*>(smem + a.off_raw) +
@@ -207,8 +215,8 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, const PostParams& p
             pmu_c xw = hann_combine(row, k);
             X.put(k, xw.x, xw.y);
             if (a.spec_out) {
-                a.spec_out[((size_t)w * K + k) * 2] = xw.x;
-                a.spec_out[((size_t)w * K + k) * 2 + 1] = xw.y;
+                a.spec_out[((size_t)wf * K + k) * 2] = xw.x;
+                a.spec_out[((size_t)wf * K + k) * 2 + 1] = xw.y;
             }
         }
     }
@@ -224,19 +232,20 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, const PostParams& p
         Tone t;
         int dbg = estimate_tone(pp, X, Wk, &t);
         RocofState rs;
-        rs.f_old = a.st_fold[w];
-        rs.dl0 = a.st_dl0[w];
-        rs.dl1 = a.st_dl1[w];
-        rs.st = a.st_state[w];
+        // the previous frame's state may have been written by another warp of this CTA
+        rs.f_old = __ldcg(&a.st_fold[w]);
+        rs.dl0 = __ldcg(&a.st_dl0[w]);
+        rs.dl1 = __ldcg(&a.st_dl1[w]);
+        rs.st = __ldcg(&a.st_state[w]);
         double y = rocof_step(pp, t.freq, &rs);
         a.st_fold[w] = rs.f_old;
         a.st_dl0[w] = rs.dl0;
         a.st_dl1[w] = rs.dl1;
         a.st_state[w] = (unsigned char)rs.st;
-        double mid = (double)reinterpret_cast<const InT*>(a.mid)[w / pp.C];
+        double mid = (double)reinterpret_cast<const InT*>(a.mid)[(long long)frame * a.mid_frame_stride + w / pp.C];
         double fr[4];
         fill_frame(pp, t, y, mid, fr);
-        InT* out = reinterpret_cast<InT*>(a.frames) + (size_t)w * 4;
+        InT* out = reinterpret_cast<InT*>(a.frames) + (size_t)wf * 4;
         if constexpr (sizeof(InT) == 8) {
             double2* o2 = reinterpret_cast<double2*>(out);
             o2[0] = make_double2(fr[0], fr[1]);
@@ -244,8 +253,8 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, const PostParams& p
         } else {
             *reinterpret_cast<float4*>(out) = make_float4((float)fr[0], (float)fr[1], (float)fr[2], (float)fr[3]);
         }
-        if (a.dbg) a.dbg[w] = dbg;
-        if (a.state_export) {
+        if (a.dbg) a.dbg[wf] = dbg;
+        if (a.state_export && frame == a.n_frames - 1) {
             double2* e2 = reinterpret_cast<double2*>(a.state_export + (size_t)w * 4);
             e2[0] = make_double2(rs.f_old, rs.dl0);
             e2[1] = make_double2(rs.dl1, (double)rs.st);
@@ -258,8 +267,29 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, const PostParams& p
     }
 }
 
+// Load the M samples of one residue from a stage (row pitch in elements).  FULL: every lane of
+// the group is a valid residue, no masking.
+template <typename InT, int M, bool FULL>
+__device__ __forceinline__ void load_residue(const InT* xs, int pitch, int a_loc, int w_s, double* x)
+{
+    if constexpr (FULL) {
+#pragma unroll
+        for (int b = 0; b < M; ++b) x[b] = (double)xs[b * pitch + a_loc];
+    } else {
+        const bool valid = a_loc < w_s;
+        const int a_c = valid ? a_loc : 0;
+#pragma unroll
+        for (int b = 0; b < M; ++b) {
+            double v = (double)xs[b * pitch + a_c];
+            x[b] = valid ? v : 0.0;
+        }
+    }
+}
+
 // ---- the kernel ----------------------------------------------------------------------
-template <typename InT, int M, int KC>
+// PITCH > 0: stage rows are PITCH elements apart (compile-time: the sample loads need no address
+// arithmetic); PITCH == 0: row pitch = a.W at run time.
+template <typename InT, int M, int KC, int PITCH>
 __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const __grid_constant__ KernelArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -274,7 +304,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     const int lane = tid % PMU_WARP;
     const int nthreads = blockDim.x;
 
-    // contiguous, balanced range of windows for this CTA
+    // contiguous, balanced range of streams for this CTA
     const long long w_begin = (a.n_windows * (long long)blockIdx.x) / gridDim.x;
     const long long w_end = (a.n_windows * (long long)(blockIdx.x + 1)) / gridDim.x;
     const int n_local = (int)(w_end - w_begin);
@@ -295,6 +325,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         for (int i = 0; i < PMU_MAX_POST; ++i) ctrl->post_lock[i] = 0;
         mbar_fence_init();
     }
+    for (int i = tid; i < PMU_MAX_GROUPS; i += nthreads) ctrl->grp_done[i] = 0;
     for (int i = tid; i < a.n_u; i += nthreads) sU[i] = a.U[i];
     for (int i = tid; i < KC * PMU_WARP; i += nthreads) sV[i] = a.V[i];
     for (int i = tid; i < a.post.jlo + a.post.jhi + 1; i += nthreads) sT[i] = a.trig[i];
@@ -302,8 +333,9 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     if (n_local <= 0) return;
 
     const size_t win_bytes = (size_t)a.N * sizeof(InT);
-    const unsigned char* gwin = reinterpret_cast<const unsigned char*>(a.windows) + (size_t)w_begin * win_bytes;
-    const int total_slabs = n_local * a.nslab;
+    const int n_items = n_local * a.n_frames;   // (frame, stream) pairs, frame-major
+    const int total_slabs = n_items * a.nslab;
+    const int pitch = PITCH > 0 ? PITCH : a.W;
 
     if (warp == 0) {
         // ================= PRODUCER =================
@@ -313,10 +345,12 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                     const int st = i % a.n_stage;
                     const uint32_t par = (uint32_t)((i / a.n_stage) & 1);
                     mbar_wait(&ctrl->empty[st], par ^ 1u);
-                    const int t = i / a.nslab, sl = i - t * a.nslab;
+                    const int item = i / a.nslab, sl = i - item * a.nslab;
+                    const int f = item / n_local, t = item - f * n_local;
                     unsigned char* dst = stages + (size_t)st * a.stage_bytes;
-                    const unsigned char* src = gwin + (size_t)t * win_bytes;
-                    if (a.nslab == 1) {
+                    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.windows) +
+                                               ((size_t)f * a.frame_stride + (size_t)(w_begin + t)) * win_bytes;
+                    if (a.nslab == 1 && pitch == a.L) {
                         mbar_expect_tx(&ctrl->full[st], (uint32_t)win_bytes);
                         bulk_g2s(dst, src, (uint32_t)win_bytes, &ctrl->full[st]);
                     } else {
@@ -325,7 +359,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                         const uint32_t row_bytes = (uint32_t)(w_s * sizeof(InT));
                         mbar_expect_tx(&ctrl->full[st], row_bytes * M);
                         for (int b = 0; b < M; ++b)
-                            bulk_g2s(dst + (size_t)b * a.W * sizeof(InT),
+                            bulk_g2s(dst + (size_t)b * pitch * sizeof(InT),
                                      src + ((size_t)a_lo + (size_t)a.L * b) * sizeof(InT), row_bytes, &ctrl->full[st]);
                     }
                 }
@@ -335,14 +369,16 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 const int st = i % a.n_stage;
                 const uint32_t par = (uint32_t)((i / a.n_stage) & 1);
                 mbar_wait(&ctrl->empty[st], par ^ 1u);
-                const int t = i / a.nslab, sl = i - t * a.nslab;
+                const int item = i / a.nslab, sl = i - item * a.nslab;
+                const int f = item / n_local, t = item - f * n_local;
                 InT* dst = reinterpret_cast<InT*>(stages + (size_t)st * a.stage_bytes);
-                const InT* src = reinterpret_cast<const InT*>(gwin + (size_t)t * win_bytes);
+                const InT* src = reinterpret_cast<const InT*>(reinterpret_cast<const unsigned char*>(a.windows) +
+                                                              ((size_t)f * a.frame_stride + (size_t)(w_begin + t)) * win_bytes);
                 const int a_lo = sl * a.W;
                 const int w_s = min(a.W, a.L - a_lo);
                 for (int b = 0; b < M; ++b)
                     for (int e = lane; e < w_s; e += PMU_WARP)
-                        cp_async_elem<(int)sizeof(InT)>(dst + (size_t)b * a.W + e, src + (size_t)a_lo + (size_t)a.L * b + e);
+                        cp_async_elem<(int)sizeof(InT)>(dst + (size_t)b * pitch + e, src + (size_t)a_lo + (size_t)a.L * b + e);
                 cp_async_mbar_arrive(&ctrl->full[st]);
             }
         }
@@ -358,18 +394,19 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     const int w_per_it = a.W / PMU_WARP;  // full-slab residue groups (W % 32 == 0 when nslab > 1)
 
     for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(&ctrl->ticket, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n_local) break;
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&ctrl->ticket, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int f = item / n_local, t = item - f * n_local;
 
-        // ---- pruned rectangular DFT of window t ----
+        // ---- pruned rectangular DFT of stream t, frame f ----
         double acc[2 * KC];  // ar = acc[0..KC), ai = acc[KC..2KC)
         double* ar = acc;
         double* ai = acc + KC;
         bool first = true;
         for (int sl = 0; sl < a.nslab; ++sl) {
-            const int idx = t * a.nslab + sl;
+            const int idx = item * a.nslab + sl;
             const int st = idx % a.n_stage;
             const int use = idx / a.n_stage;
             // Tickets are claimed out of order w.r.t. the ring: a parity wait is only unambiguous
@@ -382,16 +419,16 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             const int a_lo = sl * a.W;
             const int w_s = min(a.W, a.L - a_lo);
             const int n_it = (w_s + PMU_WARP - 1) / PMU_WARP;
+#ifdef PMU_EXP_ALWAYS_MASK
+            const bool all_full = false;
+#else
+            const bool all_full = (w_s % PMU_WARP) == 0;
+#endif
             for (int ii = 0; ii < n_it; ++ii) {
                 const int a_loc = lane + PMU_WARP * ii;
-                const bool valid = a_loc < w_s;
-                const int a_c = valid ? a_loc : 0;
                 double x[M];
-#pragma unroll
-                for (int b = 0; b < M; ++b) {
-                    double v = (double)xs[b * a.W + a_c];
-                    x[b] = valid ? v : 0.0;
-                }
+                if (all_full) load_residue<InT, M, true>(xs, pitch, a_loc, w_s, x);
+                else load_residue<InT, M, false>(xs, pitch, a_loc, w_s, x);
                 const pmu_c* u = sU + (size_t)(sl * w_per_it + ii) * KC;
                 if (first) {
                     accumulate_residue<M, KC, true>(x, u, ar, ai);
@@ -422,9 +459,10 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         // ---- deposit into the batch's raw buffer ----
         int g, slot, bsz, first_t;
         bm.locate(t, &g, &slot, &bsz, &first_t);
-        const int rb = g % a.n_raw;
+        const int gb = f * bm.nb + g;              // batch id over the whole launch, in ticket order
+        const int rb = gb % a.n_raw;
         if (lane == 0) {
-            while (ld_volatile_s32(&ctrl->raw_owner[rb]) != g) __nanosleep(64);
+            while (ld_volatile_s32(&ctrl->raw_owner[rb]) != gb) __nanosleep(64);
         }
         __syncwarp();
         __threadfence_block();
@@ -441,10 +479,13 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         }
         done = __shfl_sync(0xffffffffu, done, 0);
         if (done == bsz) {
-            // ---- this warp post-processes batch g ----
+            // ---- this warp post-processes batch (f, g) ----
             __threadfence_block();
             int ps = 0;
             if (lane == 0) {
+                // frame f of these streams needs the ROCOF state left by frame f-1
+                if (a.n_frames > 1)
+                    while (ld_volatile_s32(&ctrl->grp_done[g]) != f) __nanosleep(64);
                 for (;;) {
                     bool got = false;
                     for (int s = 0; s < a.n_post; ++s)
@@ -454,7 +495,12 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 }
             }
             ps = __shfl_sync(0xffffffffu, ps, 0);
-            post_batch<InT>(a, pp, smem, rb, ps, w_begin + first_t, bsz, g, lane);
+            __threadfence_block();
+            post_batch<InT>(a, pp, rb, ps, w_begin + first_t, f, bsz, gb, lane);
+            if (a.n_frames > 1 && lane == 0) {
+                __threadfence_block();
+                *reinterpret_cast<volatile int*>(&ctrl->grp_done[g]) = f + 1;
+            }
         }
     }
 }

@@ -11,18 +11,18 @@
 
 namespace {
 
-template <typename T, int M, int KC>
+template <typename T, int M, int KC, int PITCH>
 int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
 {
     static int configured[64];  // per device: dynamic smem already opted in for this instantiation
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess && (dev < 0 || dev >= 64 || configured[dev] != smem)) {
-        e = cudaFuncSetAttribute(pmu_fused_kernel<T, M, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(pmu_fused_kernel<T, M, KC, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev] = smem;
     }
     if (e == cudaSuccess) {
-        pmu_fused_kernel<T, M, KC><<<grid, block, smem, s>>>(a);
+        pmu_fused_kernel<T, M, KC, PITCH><<<grid, block, smem, s>>>(a);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) {
@@ -32,14 +32,21 @@ int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t
     return 0;
 }
 
+// The 16-point codelet always runs on stages with a fixed row pitch of PMU_PITCH16 elements
+// (the plan never makes its slabs wider), so its sample loads carry immediate offsets.
 template <typename T, int M>
 int launch_kc(int KC, const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
 {
+#ifdef PMU_EXP_NOPITCH
+    constexpr int PITCH = 0;
+#else
+    constexpr int PITCH = (M == 16) ? PMU_PITCH16 : 0;
+#endif
     switch (KC) {
-        case 8: return launch_inst<T, M, 8>(a, grid, block, smem, s);
-        case 12: return launch_inst<T, M, 12>(a, grid, block, smem, s);
-        case 16: return launch_inst<T, M, 16>(a, grid, block, smem, s);
-        case 24: return launch_inst<T, M, 24>(a, grid, block, smem, s);
+        case 8: return launch_inst<T, M, 8, PITCH>(a, grid, block, smem, s);
+        case 12: return launch_inst<T, M, 12, PITCH>(a, grid, block, smem, s);
+        case 16: return launch_inst<T, M, 16, PITCH>(a, grid, block, smem, s);
+        case 24: return launch_inst<T, M, 24, PITCH>(a, grid, block, smem, s);
     }
     pmu::set_error("[pmu_estimate] ERROR: unsupported bin-count specialisation");
     return -1;

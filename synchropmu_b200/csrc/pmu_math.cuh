@@ -83,8 +83,22 @@ struct PostParams {
     const pmu_c* trig;    // trig[j + jlo] = (cos(j pi/N), sin(j pi/N))
 };
 
+// Table read: on the device the table sits in shared memory (the assumption lets the compiler
+// emit LDS instead of a generic LD).
+PMU_HD pmu_c pmu_trig(const PostParams& p, int idx)
+{
+#if defined(__CUDA_ARCH__)
+    __builtin_assume(__isShared(p.trig));
+#endif
+    return p.trig[idx];
+}
+
+// A tone estimate.  The phase is carried as the unit phasor (cr, ci) = exp(i ph): the
+// compensation / synthesis steps only ever need exp(+-i ph) (src/pmu_estimator.c:567-568, :646),
+// so no atan2 / sincos round trip is needed between passes; the angle itself is taken once,
+// when the frame is written (:265).
 struct Tone {
-    double amp, ph, freq;
+    double amp, cr, ci, freq;
 };
 
 // One sweep of wf(k, f, z) over the bins for a fixed tone (f, z).
@@ -116,14 +130,14 @@ struct Sweep {
     // 1 / sin(pi (r + j)/N)
     PMU_HD double inv_den(const PostParams& p, int j) const
     {
-        pmu_c t = p.trig[j + p.jlo];
+        pmu_c t = pmu_trig(p, j + p.jlo);
         return 1.0 / (sr * t.x + cr * t.y);
     }
 
     // value at bin k given I[m-1], I[m], I[m+1]
     PMU_HD void eval(const PostParams& p, int k, double im1, double i0, double ip1, double* wr, double* wi) const
     {
-        pmu_c e = p.trig[(k - kstar) + p.jlo];
+        pmu_c e = pmu_trig(p, (k - kstar) + p.jlo);
         double br = p.c3q * (im1 + ip1) + 0.5 * i0;
         double bi = p.s3q * (im1 - ip1);
         double tr = e.x * br - e.y * bi;
@@ -154,6 +168,8 @@ struct Peak {
 
 // ipDFT tail (src/pmu_estimator.c:594-623) from the tracked peak.  Returns 1 when
 // |delta| <= 1e-11 (the reference's literal 10e-12, :603).
+//   reference: amp = |Y| |(d^2-1) pi d / sin(pi d)|,  ph = arg(Y) - pi d
+//   here     : exp(i ph) = (Y/|Y|) exp(-i pi d), sin(pi d) from the same sincospi.
 PMU_HD int ipdft_finish(const PostParams& p, const Peak& pk, Tone* t)
 {
     double mk = sqrt(pk.best);
@@ -161,25 +177,45 @@ PMU_HD int ipdft_finish(const PostParams& p, const Peak& pk, Tone* t)
     double mr = (pk.km == p.K - 1) ? ml : sqrt(pk.right);       // kr = km-1 at the last bin (:719)
     double d = 2 * (mr - ml) / (ml + mr + 2 * mk);              // :598
     t->freq = (pk.km + d) * p.df;                               // :601
-    double arg = atan2(pk.yi, pk.yr);
+    double inv = 1.0 / mk;
+    double ur = pk.yr * inv, ui = pk.yi * inv;                  // exp(i arg Y)
     if (fabs(d) <= 10e-12) {                                    // :603-613
         t->amp = mk;
-        t->ph = arg;
+        t->cr = ur;
+        t->ci = ui;
         return 1;
     }
-    double pd = PMU_PI * d;
-    t->amp = mk * fabs((d * d - 1) * pd / sin(pd));             // :616
-    t->ph = arg - pd;                                           // :617
+    double sd, cd;
+    pmu_sincospi(d, &sd, &cd);
+    t->amp = mk * fabs((d * d - 1) * (PMU_PI * d) / sd);        // :616
+    t->cr = ur * cd + ui * sd;                                  // :617  exp(i(arg Y - pi d))
+    t->ci = ui * cd - ur * sd;
     return 0;
 }
 
-// Column view of a [K][32] complex array in shared memory (lane = window).
+// Column view of a [K][32] complex array (lane = window); shared memory on the device.
 struct Col {
-    pmu_c* base;  // already offset by the lane
+    pmu_c* base;  // bin 0 of this lane's column
     int stride;   // elements between consecutive bins
-    PMU_HD pmu_c get(int j) const { return base[j * stride]; }
+    PMU_HD static Col make(pmu_c* ptr, int stride_elems)
+    {
+        Col c;
+        c.base = ptr;
+        c.stride = stride_elems;
+        return c;
+    }
+    PMU_HD pmu_c get(int j) const
+    {
+#if defined(__CUDA_ARCH__)
+        __builtin_assume(__isShared(base));  // plain (schedulable) LDS instead of a generic LD
+#endif
+        return base[j * stride];
+    }
     PMU_HD void put(int j, double re, double im) const
     {
+#if defined(__CUDA_ARCH__)
+        __builtin_assume(__isShared(base));
+#endif
         pmu_c v; v.x = re; v.y = im;
         base[j * stride] = v;
     }
@@ -193,9 +229,7 @@ PMU_HD int ipdft_pass(const PostParams& p, const Col& Y, const Tone& prev, Tone*
     Sweep sw;
     double im1 = 0, i0 = 0, ip1 = 0;
     if (COMP) {
-        double s, c;
-        pmu_sincos(prev.ph, &s, &c);
-        sw.init(p, -prev.freq, prev.amp * c, -prev.amp * s);
+        sw.init(p, -prev.freq, prev.amp * prev.cr, -prev.amp * prev.ci);  // amp e^{-i ph}, :646
         im1 = sw.inv_den(p, -sw.kstar - 1);
         i0 = sw.inv_den(p, -sw.kstar);
     }
@@ -239,11 +273,9 @@ PMU_HD void e_ipdft(const PostParams& p, const Col& Y, Tone* t, int* km_first)
 template <bool ENERGY>
 PMU_HD void residual(const PostParams& p, const Col& X, const Tone& t, const Col& W, double* Ed, double* E)
 {
-    double s, c;
-    pmu_sincos(t.ph, &s, &c);
     Sweep sp, sn;
-    sp.init(p, t.freq, t.amp * c, t.amp * s);    // phsr_0 = amp e^{+i ph}
-    sn.init(p, -t.freq, t.amp * c, -t.amp * s);  // phsr_1 = amp e^{-i ph}
+    sp.init(p, t.freq, t.amp * t.cr, t.amp * t.ci);    // phsr_0 = amp e^{+i ph}
+    sn.init(p, -t.freq, t.amp * t.cr, -t.amp * t.ci);  // phsr_1 = amp e^{-i ph}
     double pm1 = sp.inv_den(p, -sp.kstar - 1), p0 = sp.inv_den(p, -sp.kstar);
     double nm1 = sn.inv_den(p, -sn.kstar - 1), n0 = sn.inv_den(p, -sn.kstar);
     double ed = 0, e = 0;
@@ -277,7 +309,7 @@ PMU_HD void residual(const PostParams& p, const Col& X, const Tone& t, const Col
 PMU_HD int estimate_tone(const PostParams& p, const Col& X, const Col& W, Tone* out)
 {
     Tone f;
-    f.amp = 0; f.ph = 0; f.freq = 0;
+    f.amp = 0; f.cr = 1; f.ci = 0; f.freq = 0;
     int km = 0;
     e_ipdft(p, X, &f, &km);                                  // :205
     int dbg = km & PMU_DBG_KM_MASK;
@@ -286,7 +318,7 @@ PMU_HD int estimate_tone(const PostParams& p, const Col& X, const Col& W, Tone* 
     if (p.iter_en && Ed > p.eps * E) {                       // :227-229 (NaN compares false)
         dbg |= PMU_DBG_TRIGGERED;
         Tone it;
-        it.amp = 0; it.ph = 0; it.freq = 0;
+        it.amp = 0; it.cr = 1; it.ci = 0; it.freq = 0;
         for (int i = 0; i < p.Q; ++i) {                      // :675
             e_ipdft(p, W, &it, nullptr);                     // :679   interference tone from Xi
             residual<false>(p, X, it, W, nullptr, nullptr);  // :680-684  W = Xf = X - pure(it)
@@ -328,7 +360,7 @@ PMU_HD double wrap_angle_pi(double rad)
 PMU_HD void fill_frame(const PostParams& p, const Tone& t, double rocof, double mid_fracsec, double out[4])
 {
     out[0] = 2 * t.amp / p.S;
-    out[1] = wrap_angle_pi(t.ph - 2 * PMU_PI * p.f0 * mid_fracsec);
+    out[1] = wrap_angle_pi(atan2(t.ci, t.cr) - 2 * PMU_PI * p.f0 * mid_fracsec);
     out[2] = t.freq;
     out[3] = rocof;
 }

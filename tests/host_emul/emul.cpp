@@ -100,9 +100,7 @@ int emul_run(const pmub_config* cfg, int dtype, int n_channels, long n_streams, 
             const size_t u = (size_t)t * n_streams + s;
             if (dtype == PMUB_F64) window_bins_m<double>(p, U, V, (const double*)windows + u * d.N, raw.data());
             else window_bins_m<float>(p, U, V, (const float*)windows + u * d.N, raw.data());
-            Col cx, cw;
-            cx.base = X.data(); cx.stride = 1;
-            cw.base = W.data(); cw.stride = 1;
+            const Col cx = Col::make(X.data(), 1), cw = Col::make(W.data(), 1);
             for (int k = 0; k < K; ++k) {
                 pmu_c xw = hann_combine(raw.data(), k);
                 cx.put(k, xw.x, xw.y);

@@ -328,3 +328,30 @@ def test_config5_sharded_slice_600_samples():
             assert bool(torch.isfinite(out).all())
     want, _, _ = checker(np.float64, 6).run(cfg, sample_win, mids, n_threads=0)
     assert_frames_close(np.stack(got), want, "f64", "config5 sample")
+
+
+# ---------------------------------------------------------------------------------------
+# several consecutive frames in one launch == the same frames one call at a time
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfgname,n_inst", [("config.ini", 7), ("config.ini", 900), ("m_class_config.ini", 150),
+                                           ("cfg5_600", 333)])
+def test_multi_frame_launch_equals_sequential_calls(cfgname, n_inst):
+    torch = pytest.importorskip("torch")
+    cfg = configs.NAMED[cfgname]
+    T = 5
+    win, mid = three_phase_batch(cfg, n_inst, T, seed=31, interharmonic_frames=(3,))
+    with BatchEstimator(cfg, n_inst, 6) as seq, BatchEstimator(cfg, n_inst, 6) as multi_host, \
+            BatchEstimator(cfg, n_inst, 6) as multi_dev:
+        ref = np.stack([seq.estimate(win[t], mid[t]) for t in range(T)])
+        got_host = multi_host.estimate_frames(win, mid)                       # host buffers, chunked 2-D copies
+        dw, dm = torch.from_numpy(win).cuda(), torch.from_numpy(mid).cuda()
+        got_dev = multi_dev.estimate_frames(dw, dm).cpu().numpy()             # device buffers, one launch
+        assert multi_dev.launches == 1
+        st_a, st_b = seq.get_state(), multi_dev.get_state()
+    assert np.array_equal(got_dev, ref)
+    assert np.array_equal(got_host, ref)
+    for k in st_a:
+        assert np.array_equal(st_a[k], st_b[k])
+    # and against the oracle, so that the frame-to-frame ROCOF hand-over inside the kernel is pinned
+    want, _, _ = checker(np.float64, 6).run(cfg, win[:, :40], mid[:, :40], n_threads=0)
+    assert_frames_close(got_dev[:, :want.shape[1]], want, "f64", cfgname)

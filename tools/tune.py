@@ -18,32 +18,43 @@ sys.path.insert(0, str(ROOT))
 from synchropmu_b200 import api, configs, signals  # noqa: E402
 
 
-def time_case(cfg, n_inst, n_ch, lib, steps=200, frames=3, dtype=np.float64, harm=()):
+def time_case(cfg, n_inst, n_ch, lib, steps=200, frames=3, dtype=np.float64, harm=(), fpl=1):
     dev = torch.device("cuda")
     tdt = torch.float64 if dtype == np.float64 else torch.float32
     prm = signals.three_phase_params(n_inst)
     pt = {k: torch.as_tensor(v, device=dev) for k, v in prm.items()}
     N = configs.win_len(cfg)
     xs, ms = [], []
+    frames = max(frames, fpl)
     for t in range(frames):
         x = signals.steady(cfg, t, pt["amp"], pt["freq"], pt["phase"], xp=torch, ramp=pt["ramp"], harmonics=list(harm), like=pt["amp"])
         xs.append(x.to(tdt).reshape(n_inst, n_ch, N).contiguous())
         ms.append(torch.full((n_inst,), signals.mid_fracsec(cfg, t), dtype=tdt, device=dev))
-    out = torch.empty((n_inst, n_ch, 4), dtype=tdt, device=dev)
+    out = torch.empty((max(1, fpl), n_inst, n_ch, 4), dtype=tdt, device=dev)
+    if fpl > 1:
+        xs = [torch.stack(xs[:fpl]).contiguous()]
+        ms = [torch.stack(ms[:fpl]).contiguous()]
+        frames = 1
+        steps = max(10, steps // fpl)
     est = api.BatchEstimator(cfg, n_inst, n_ch, dtype=dtype, lib=lib)
     s = torch.cuda.Stream()
     torch.cuda.synchronize()
     with torch.cuda.stream(s):
         est.set_stream(s.cuda_stream)
-        for i in range(10):
-            est.estimate_async(xs[i % frames], ms[i % frames], out)
+        def go(i):
+            if fpl > 1:
+                est.estimate_frames_async(fpl, xs[0], ms[0], out)
+            else:
+                est.estimate_async(xs[i % frames], ms[i % frames], out)
+        for i in range(5):
+            go(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(s)
         for i in range(steps):
-            est.estimate_async(xs[i % frames], ms[i % frames], out)
+            go(i)
         e1.record(s)
     torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / steps * 1e3
+    us = e0.elapsed_time(e1) / steps * 1e3 / max(1, fpl)
     info = est.info
     est.close()
     del xs, ms, out
@@ -92,6 +103,8 @@ def main():
                           streaming_gbs=round(bpe / (b * 1e3), 1))), flush=True)
     if a.quick:
         return
+    for fpl in (2, 4, 8, 16):
+        run(f"frames_per_launch={fpl}", 4096, fpl=fpl)
     run("light_post(P=1,iter=0)", 4096, cfg_=dict(cfg, P=1, iter_eipdft=0))
     run("triggered(10% 75Hz)", 4096, harm=[(0.1, 75.0, 0.0)])
     for st in (3, 5, 7):
