@@ -304,12 +304,14 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     pp.thr0 = d.thr[0]; pp.thr1 = d.thr[1]; pp.thr2 = d.thr[2];
     pp.lp0 = d.lp[0]; pp.lp1 = d.lp[1]; pp.lp2 = d.lp[2];
     pp.trig = b->dT;
+    pp.trig_off = (unsigned)b->plan.off_trig;
     a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
     a.n_stage = b->plan.n_stage; a.stage_bytes = b->plan.stage_bytes; a.n_cons = b->plan.n_cons;
     a.n_raw = b->plan.n_raw; a.raw_stride = b->plan.raw_stride; a.n_post = b->plan.n_post;
     a.n_u = b->plan.n_u; a.scratch_global = 0;
     a.off_ctrl = b->plan.off_ctrl; a.off_U = b->plan.off_U; a.off_V = b->plan.off_V; a.off_trig = b->plan.off_trig;
-    a.off_raw = b->plan.off_raw; a.off_post = b->plan.off_post; a.off_stage = b->plan.off_stage;
+    a.off_raw = b->plan.off_raw; a.off_post = b->plan.off_post; a.off_red = b->plan.off_red; a.off_stage = b->plan.off_stage;
+    a.red_stride = b->plan.red_stride;
     a.U = b->dU; a.V = b->dV; a.trig = b->dT; a.scratch = nullptr;
 
     if (pmub_reset(b)) { free_batch(b); return -1; }

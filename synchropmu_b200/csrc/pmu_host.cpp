@@ -292,40 +292,61 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
                         : ((N * s) % 16 == 0 && (p.L * s) % 16 == 0 && (p.W * s) % 16 == 0 &&
                            ((p.L - (p.nslab - 1) * p.W) * s) % 16 == 0 && (p.pitch * s) % 16 == 0);
 
-    p.n_cons = env_int("PMU_CONSUMER_WARPS", PMU_MAX_CONSUMERS);
-    if (p.n_cons < 1) p.n_cons = 1;
-    if (p.n_cons > PMU_MAX_CONSUMERS) p.n_cons = PMU_MAX_CONSUMERS;
-    p.n_raw = env_int("PMU_RAW_BUFFERS", 4);
-    if (p.n_raw < 2) p.n_raw = 2;
-    if (p.n_raw > PMU_MAX_RAW) p.n_raw = PMU_MAX_RAW;
-    p.n_post = env_int("PMU_POST_SLOTS", 4);
-    if (p.n_post < 1) p.n_post = 1;
-    if (p.n_post > PMU_MAX_POST) p.n_post = PMU_MAX_POST;
-    p.raw_stride = 2 * p.Kp + 1;  // odd number of doubles: lane-per-window reads stay conflict-free
     const int n_groups = (p.nslab == 1) ? (p.L + 31) / 32 : (p.nslab - 1) * (p.W / 32) + ((p.L - (p.nslab - 1) * p.W) + 31) / 32;
     p.n_u = n_groups * p.KC;
     p.jlo = K + 2;
     p.jhi = 2 * K + 1;
+    p.raw_stride = 2 * p.Kp + 1;  // odd number of doubles: lane-per-window reads stay conflict-free
+    // per-lane row of the reduction scratch: >= 2*Kp doubles, an odd number of 16-byte units so that the
+    // 128-bit stores of a quarter warp hit distinct banks
+    p.red_stride = (p.Kp % 2 == 0) ? 2 * p.Kp + 2 : 2 * p.Kp + 4;
 
-    int off = 0;
-    p.off_ctrl = off; off += align_up((int)sizeof(CtrlBlock), 128);
-    p.off_U = off;    off += align_up(p.n_u * 16, 128);
-    p.off_V = off;    off += align_up(p.KC * 32 * 16, 128);
-    p.off_trig = off; off += align_up((p.jlo + p.jhi + 1) * 16, 128);
-    p.off_raw = off;  off += align_up(p.n_raw * 32 * p.raw_stride * 8, 128);
-    p.off_post = off; off += align_up(p.n_post * 2 * K * 32 * 16, 128);
-    p.off_stage = off;
-    const int avail = max_smem - off;
-    int ns = avail / p.stage_bytes;
-    const int ns_cap = env_int("PMU_STAGES", PMU_MAX_STAGES);
-    if (ns > ns_cap) ns = ns_cap;
-    if (ns > PMU_MAX_STAGES) ns = PMU_MAX_STAGES;
-    if (ns < 2) {
+    int want_cons = env_int("PMU_CONSUMER_WARPS", PMU_MAX_CONSUMERS);
+    if (want_cons < 1) want_cons = 1;
+    if (want_cons > PMU_MAX_CONSUMERS) want_cons = PMU_MAX_CONSUMERS;
+    int want_raw = env_int("PMU_RAW_BUFFERS", 4);
+    if (want_raw < 2) want_raw = 2;
+    if (want_raw > PMU_MAX_RAW) want_raw = PMU_MAX_RAW;
+    int want_post = env_int("PMU_POST_SLOTS", 4);
+    if (want_post < 1) want_post = 1;
+    if (want_post > PMU_MAX_POST) want_post = PMU_MAX_POST;
+    int ns_cap = env_int("PMU_STAGES", PMU_MAX_STAGES);
+    if (ns_cap > PMU_MAX_STAGES) ns_cap = PMU_MAX_STAGES;
+
+    // Shared-memory budget: prefer the full complement of scratch; when bins/windows are large,
+    // give up scratch slots (then consumer warps) until at least `min_stages` ring stages fit.
+    auto layout = [&](int n_cons, int n_raw, int n_post) {
+        p.n_cons = n_cons; p.n_raw = n_raw; p.n_post = n_post;
+        int off = 0;
+        p.off_ctrl = off; off += align_up((int)sizeof(CtrlBlock), 128);
+        p.off_U = off;    off += align_up(p.n_u * 16, 128);
+        p.off_V = off;    off += align_up(p.KC * 32 * 16, 128);
+        p.off_trig = off; off += align_up((p.jlo + p.jhi + 1) * 16, 128);
+        p.off_raw = off;  off += align_up(p.n_raw * 32 * p.raw_stride * 8, 128);
+        p.off_post = off; off += align_up(p.n_post * 2 * K * 32 * 16, 128);
+        p.off_red = off;  off += align_up(p.n_cons * 32 * p.red_stride * 8, 128);
+        p.off_stage = off;
+        int ns = (max_smem - off) / p.stage_bytes;
+        if (ns > ns_cap) ns = ns_cap;
+        p.n_stage = ns;
+        p.smem_bytes = off + (ns > 0 ? ns : 0) * p.stage_bytes;
+        return ns;
+    };
+    const int tries[][3] = {{want_cons, want_raw, want_post}, {want_cons, 3, 3}, {want_cons, 2, 2}, {want_cons, 2, 1},
+                            {5, 2, 2}, {5, 2, 1}, {3, 2, 1}, {2, 2, 1}, {1, 2, 1}};
+    bool ok = false;
+    for (int pass = 0; pass < 2 && !ok; ++pass) {
+        const int min_stages = pass == 0 ? 4 : 2;
+        for (const auto& t : tries) {
+            const int nc = t[0] < want_cons ? t[0] : want_cons, nr = t[1] < want_raw ? t[1] : want_raw,
+                      np = t[2] < want_post ? t[2] : want_post;
+            if (layout(nc, nr < 2 ? 2 : nr, np < 1 ? 1 : np) >= min_stages) { ok = true; break; }
+        }
+    }
+    if (!ok) {
         set_error("[pmu_init] ERROR: configuration does not fit the shared-memory budget of the CUDA estimator (window too long or too many bins)");
         return -1;
     }
-    p.n_stage = ns;
-    p.smem_bytes = off + ns * p.stage_bytes;
     *out = p;
     return 0;
 }

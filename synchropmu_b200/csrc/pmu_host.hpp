@@ -42,7 +42,8 @@ struct Plan {
     int n_cons, n_raw, raw_stride, n_post;
     int n_u;
     int jlo, jhi;
-    int off_ctrl, off_U, off_V, off_trig, off_raw, off_post, off_stage;
+    int off_ctrl, off_U, off_V, off_trig, off_raw, off_post, off_red, off_stage;
+    int red_stride;     // doubles per lane row of the per-warp reduction scratch
     int smem_bytes;
     bool aligned16;     // window pitch and row pitch allow TMA bulk copies
 };

@@ -48,7 +48,8 @@ struct KernelArgs {
     int n_u;                     // entries of U (complex)
     int scratch_global;          // 1: X/W scratch lives in global memory (large n_bins)
     // shared-memory layout (byte offsets from the dynamic smem base)
-    int off_ctrl, off_U, off_V, off_trig, off_raw, off_post, off_stage;
+    int off_ctrl, off_U, off_V, off_trig, off_raw, off_post, off_red, off_stage;
+    int red_stride;              // doubles per lane row of the per-warp reduction scratch (even)
     // tables (global memory; copied to smem by the kernel)
     const pmu_c* U;              // [ceil(L/32)][KC]   W_N^{32 i k}
     const pmu_c* V;              // [KC][32]           W_N^{lane k}
@@ -113,10 +114,10 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity)
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware, do not spin
             : "memory");
     } while (!done);
 }
@@ -195,10 +196,11 @@ struct BatchMap {
 // Batch = <= 32 consecutive streams of this CTA at frame f.  w_first = index (within this
 // launch) of the batch's first stream.
 template <typename InT>
-__device__ __noinline__ void post_batch(const KernelArgs& a, const PostParams& pp, int raw_buf, int post_slot,
-                                        long long w_first, int frame, int bsz, int batch_id, int lane)
+__device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, int post_slot, long long w_first, int frame,
+                                        int bsz, int batch_id, int lane)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* smem = pmu_smem;
+    const PostParams& pp = a.post;   // stays in the kernel-parameter constant bank
     CtrlBlock* ctrl = reinterpret_cast<CtrlBlock*>(smem + a.off_ctrl);
     const int K = pp.K;
     pmu_c* scratch = reinterpret_cast<pmu_c*>(smem + a.off_post) + (size_t)post_slot * (2 * K * PMU_WARP);
@@ -292,7 +294,7 @@ __device__ __forceinline__ void load_residue(const InT* xs, int pitch, int a_loc
 template <typename InT, int M, int KC, int PITCH>
 __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const __grid_constant__ KernelArgs a)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* smem = pmu_smem;
     CtrlBlock* ctrl = reinterpret_cast<CtrlBlock*>(smem + a.off_ctrl);
     pmu_c* sU = reinterpret_cast<pmu_c*>(smem + a.off_U);
     pmu_c* sV = reinterpret_cast<pmu_c*>(smem + a.off_V);
@@ -387,8 +389,6 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     if (warp > a.n_cons) return;
 
     // ================= CONSUMERS =================
-    PostParams pp = a.post;
-    pp.trig = sT;
     BatchMap bm;
     bm.init(n_local);
     const int w_per_it = a.W / PMU_WARP;  // full-slab residue groups (W % 32 == 0 when nslab > 1)
@@ -445,18 +445,16 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         }
         rotate_lane<KC>(sV + lane, PMU_WARP, ar, ai);
 
-        // ---- sum the 32 lane partials; lane ends up owning component(s) `base` ----
-        double v[2 * KC];
+        // ---- sum the 32 lane partials through shared memory: every lane drops its KC complex
+        //      partials into its row of the warp's scratch (128-bit stores, conflict-free row
+        //      stride), then lane c adds up column c of the 32 rows and deposits the total ----
+        double* red = reinterpret_cast<double*>(smem + a.off_red) + (size_t)(warp - 1) * PMU_WARP * a.red_stride;
+        {
+            double2* my = reinterpret_cast<double2*>(red + (size_t)lane * a.red_stride);
 #pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            v[2 * k] = ar[k];
-            v[2 * k + 1] = ai[k];
+            for (int k = 0; k < KC; ++k)
+                if (k < a.Kp) my[k] = make_double2(ar[k], ai[k]);
         }
-        int base = 0, lim = 2 * KC;
-        ReduceScatter<2 * KC, 16>::run(v, lane, base, lim);
-        constexpr int NF = ReduceFinal<2 * KC>::value;
-
-        // ---- deposit into the batch's raw buffer ----
         int g, slot, bsz, first_t;
         bm.locate(t, &g, &slot, &bsz, &first_t);
         const int gb = f * bm.nb + g;              // batch id over the whole launch, in ticket order
@@ -467,10 +465,18 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         __syncwarp();
         __threadfence_block();
         double* row = reinterpret_cast<double*>(smem + a.off_raw) + ((size_t)rb * PMU_WARP + slot) * a.raw_stride;
-        const int lim2 = min(lim, 2 * a.Kp);
+        for (int c = lane; c < 2 * a.Kp; c += PMU_WARP) {
+            const double* col = red + c;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-        for (int j = 0; j < NF; ++j)
-            if (base + j < lim2) row[base + j] = v[j];
+            for (int l = 0; l < PMU_WARP; l += 4) {
+                s0 += col[(l + 0) * a.red_stride];
+                s1 += col[(l + 1) * a.red_stride];
+                s2 += col[(l + 2) * a.red_stride];
+                s3 += col[(l + 3) * a.red_stride];
+            }
+            row[c] = (s0 + s1) + (s2 + s3);
+        }
         __syncwarp();
         int done = 0;
         if (lane == 0) {
@@ -496,7 +502,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             }
             ps = __shfl_sync(0xffffffffu, ps, 0);
             __threadfence_block();
-            post_batch<InT>(a, pp, rb, ps, w_begin + first_t, f, bsz, gb, lane);
+            post_batch<InT>(a, rb, ps, w_begin + first_t, f, bsz, gb, lane);
             if (a.n_frames > 1 && lane == 0) {
                 __threadfence_block();
                 *reinterpret_cast<volatile int*>(&ctrl->grp_done[g]) = f + 1;

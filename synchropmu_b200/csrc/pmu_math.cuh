@@ -80,17 +80,25 @@ struct PostParams {
     double frame_rate;
     double thr0, thr1, thr2;  // ROCOF thresholds
     double lp0, lp1, lp2;     // ROCOF low-pass coefficients
-    const pmu_c* trig;    // trig[j + jlo] = (cos(j pi/N), sin(j pi/N))
+    const pmu_c* trig;    // trig[j + jlo] = (cos(j pi/N), sin(j pi/N)) (host emulation; global copy on device)
+    unsigned trig_off;    // device: byte offset of the table's shared-memory copy from the dynamic smem base
 };
+
+#if defined(__CUDACC__)
+// The kernel's dynamic shared memory.  Tables and per-lane columns are addressed as 32-bit offsets
+// from this base, so the compiler emits LDS/STS with 32-bit address arithmetic.
+extern __shared__ __align__(128) unsigned char pmu_smem[];
+#endif
 
 // Table read: on the device the table sits in shared memory (the assumption lets the compiler
 // emit LDS instead of a generic LD).
 PMU_HD pmu_c pmu_trig(const PostParams& p, int idx)
 {
 #if defined(__CUDA_ARCH__)
-    __builtin_assume(__isShared(p.trig));
-#endif
+    return *reinterpret_cast<const pmu_c*>(pmu_smem + p.trig_off + (unsigned)idx * 16u);
+#else
     return p.trig[idx];
+#endif
 }
 
 // A tone estimate.  The phase is carried as the unit phasor (cr, ci) = exp(i ph): the
@@ -195,30 +203,42 @@ PMU_HD int ipdft_finish(const PostParams& p, const Peak& pk, Tone* t)
 
 // Column view of a [K][32] complex array (lane = window); shared memory on the device.
 struct Col {
-    pmu_c* base;  // bin 0 of this lane's column
-    int stride;   // elements between consecutive bins
-    PMU_HD static Col make(pmu_c* ptr, int stride_elems)
+#if defined(__CUDA_ARCH__)
+    unsigned off;     // byte offset (from the dynamic smem base) of bin 0 of this lane's column
+    unsigned stride;  // bytes between consecutive bins
+    __device__ __forceinline__ static Col make(pmu_c* ptr, int stride_elems)
+    {
+        Col c;
+        c.off = (unsigned)(reinterpret_cast<unsigned char*>(ptr) - pmu_smem);
+        c.stride = (unsigned)stride_elems * 16u;
+        return c;
+    }
+    __device__ __forceinline__ pmu_c get(int j) const
+    {
+        return *reinterpret_cast<const pmu_c*>(pmu_smem + off + (unsigned)j * stride);
+    }
+    __device__ __forceinline__ void put(int j, double re, double im) const
+    {
+        pmu_c v; v.x = re; v.y = im;
+        *reinterpret_cast<pmu_c*>(pmu_smem + off + (unsigned)j * stride) = v;
+    }
+#else
+    pmu_c* base;
+    int stride;
+    static Col make(pmu_c* ptr, int stride_elems)
     {
         Col c;
         c.base = ptr;
         c.stride = stride_elems;
         return c;
     }
-    PMU_HD pmu_c get(int j) const
+    pmu_c get(int j) const { return base[j * stride]; }
+    void put(int j, double re, double im) const
     {
-#if defined(__CUDA_ARCH__)
-        __builtin_assume(__isShared(base));  // plain (schedulable) LDS instead of a generic LD
-#endif
-        return base[j * stride];
-    }
-    PMU_HD void put(int j, double re, double im) const
-    {
-#if defined(__CUDA_ARCH__)
-        __builtin_assume(__isShared(base));
-#endif
         pmu_c v; v.x = re; v.y = im;
         base[j * stride] = v;
     }
+#endif
 };
 
 // One ipDFT over Y[j] (COMP=false) or over Y[j] - wf(j, -f, amp e^{-i ph}) (COMP=true,
