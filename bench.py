@@ -6,10 +6,11 @@
 
 Workload (BASELINE.json config 3, the one the metric is quoted on): per GPU 4096 independent
 estimator instances x 6 channels, config/config.ini parameters (2048-sample window, 11 bins,
-P=3, Q=3, iterations enabled), consecutive frames with ROCOF state carried in HBM.  One step =
-one frame for every stream = 24576 estimates = one kernel launch.  Several distinct consecutive
-frames (>= 1.6 GB) are resident in HBM and cycled, so every step reads inputs far larger than
-the 126 MB L2.  Weak scaling: every rank owns its own 4096 instances, no collective on the hot
+P=3, Q=3, iterations enabled), streaming consecutive windows with ROCOF state carried in HBM.
+One step = one pmub_estimate_frames call = `--frames-per-step` (8) consecutive frames of every
+stream = 196608 estimates = one kernel launch; `single_frame_launch` in the output is the same
+kernel launched one frame (24576 estimates) at a time.  16 distinct consecutive frames (6.4 GB)
+are resident in HBM and cycled, so every step reads inputs far larger than the 126 MB L2.  Weak scaling: every rank owns its own 4096 instances, no collective on the hot
 path; the optional NCCL gather of frames to rank 0 is timed separately.
 
 Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM;

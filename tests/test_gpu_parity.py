@@ -355,3 +355,34 @@ def test_multi_frame_launch_equals_sequential_calls(cfgname, n_inst):
     # and against the oracle, so that the frame-to-frame ROCOF hand-over inside the kernel is pinned
     want, _, _ = checker(np.float64, 6).run(cfg, win[:, :40], mid[:, :40], n_threads=0)
     assert_frames_close(got_dev[:, :want.shape[1]], want, "f64", cfgname)
+
+
+# ---------------------------------------------------------------------------------------
+# C callers: compile against include/ and run against the in-tree libraries
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("src,defs,lib", [
+    ("dropin_single.c", [], "pmu_estimator"),
+    ("dropin_single.c", ["-DNUM_CHANLS=6"], "pmu_estimator_c6"),
+    ("dropin_single.c", ["-DPMU_FLOAT_P=float"], "pmu_estimator_f32"),
+    ("batch_from_ini.c", ["-DNUM_CHANLS=6"], "pmu_estimator_c6"),
+])
+def test_c_examples_build_and_run(tmp_path, src, defs, lib):
+    import re
+    import subprocess
+
+    root = GOLD.parent.parent
+    exe = tmp_path / "a.out"
+    subprocess.run(["gcc", "-O1", *defs, f"-I{root / 'include'}", str(root / "examples" / src), "-o", str(exe),
+                    f"-L{api.LIB_DIR}", f"-l{lib}", "-lm", f"-Wl,-rpath,{api.LIB_DIR}"], check=True)
+    r = subprocess.run([str(exe), str(root / "config" / "config.ini")], capture_output=True, text=True, cwd=root, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    if src == "dropin_single.c":
+        # same text format as the reference's pmu_dump_frame (src/pmu_estimator.c:315)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("[Synchrophasor]")]
+        assert len(lines) == (6 if "-DNUM_CHANLS=6" in defs else 1)
+        m = re.match(r"\[Synchrophasor\] amplitude: ([-\d.]+), phase: ([-\d.]+), frequency: ([-\d.]+), rocof: ([-\d.]+)", lines[0])
+        amp, ph, freq, rocof = map(float, m.groups())
+        assert abs(amp - 2.0) < 1e-5 and abs(ph - 1.0) < 1e-5 and abs(freq - 50.0) < 1e-4 and abs(rocof) < 1e-3
+        assert "already initialized" in r.stderr and "not initialized" in r.stderr
+    else:
+        assert "instance  0 ch0: amp 325.27" in r.stdout and "freq 49.5000000" in r.stdout
