@@ -358,6 +358,39 @@ def main():
                    ms_per_step=dt / args.e2e_steps * 1e3, host_memory="pinned",
                    note="one frame per synchronous pmub_estimate call, H2D of the windows and D2H of the frames inside")
 
+    # ---------------- e2e through the streaming front end: only the hop new samples cross PCIe ----
+    e2e_stream = None
+    if not args.no_e2e:
+        hop = configs.hop(cfg)
+        est.stream_begin(hop=hop, max_frames_per_push=1, history=win_all[0][:, :, :N - hop].contiguous())
+        h_new = [torch.empty((1, n_inst, n_ch, hop), dtype=tdt).pin_memory() for _ in range(2)]
+        for i in range(2):
+            h_new[i][0].copy_(win_all[(i + 1) % n_frames_res][:, :, N - hop:])
+        h_out = torch.empty((1, n_inst, n_ch, 4), dtype=tdt).pin_memory()
+        hn = [h.numpy() for h in h_new]
+        ho = h_out.numpy()
+        for i in range(2):
+            est.stream_push(hn[i % 2], None, out=ho)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        n_push = args.e2e_steps * 4
+        for i in range(n_push):
+            est.stream_push(hn[i % 2], None, out=ho)
+            _ = float(ho[0, 0, 0, 2])
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            tm = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dt = float(tm.item())
+        e2e_stream = dict(value=world * n_inst * n_ch * n_push / dt, unit=UNIT,
+                          h2d_bytes_per_step=int(n_inst * n_ch * hop * itemsize),
+                          d2h_bytes_per_step=int(n_inst * n_ch * 4 * itemsize), steps=n_push,
+                          ms_per_step=dt / n_push * 1e3, host_memory="pinned",
+                          note="pmub_stream_push: sample rings resident in HBM, one frame per call, only the "
+                               "%d new samples per stream are copied in" % hop)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -381,7 +414,8 @@ def main():
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                 ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype,
                 data="synthetic", config=config, roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, clocks=clocks,
-                gpu_launches=int(launches), outputs_finite=finite, impl="ours", single_frame_launch=single)
+                gpu_launches=int(launches), outputs_finite=finite, impl="ours", single_frame_launch=single,
+                e2e_stream=e2e_stream)
     if gather_ms is not None:
         line["frame_gather_ms"] = gather_ms
     print(json.dumps(line))

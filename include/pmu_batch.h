@@ -112,6 +112,26 @@ int pmub_estimate_frames(pmub_batch *b, int n_frames, const void *windows, const
                          void *frames);
 int pmub_estimate_frames_async(pmub_batch *b, int n_frames, const void *d_windows,
                                const void *d_mid_fracsec, void *d_frames);
+/* ---- streaming front end ---------------------------------------------------------
+ * In the reference the caller cuts every window out of its sample stream (test/test.c:49-62)
+ * and hands over win_len samples per frame although consecutive windows overlap by
+ * win_len - hop samples.  Here the library keeps each stream's recent samples in a ring buffer
+ * in HBM: after pmub_stream_begin, every pushed block of `hop` new samples per stream yields one
+ * frame (the window = the last win_len samples), so only the new samples cross PCIe.
+ *   hop                 samples between frames; 0 = fs / frame_rate
+ *   max_frames_per_push upper bound for n_frames of pmub_stream_push
+ *   history             float_p [n_instances][n_channels][win_len - hop] samples preceding the
+ *                       first push (host or device), NULL = zeros
+ *   first_sample_index  absolute index of history[0] counted from the top of a second; used for
+ *                       mid_fracsec when pmub_stream_push is given mid_fracsec == NULL
+ * pmub_stream_push: new_samples float_p [n_frames][n_instances][n_channels][hop],
+ *   mid_fracsec float_p [n_frames][n_instances] or NULL (= centre of each window modulo one second,
+ *   computed on the device), frames float_p [n_frames][n_instances][n_channels][4].
+ * Results are identical to pmub_estimate on the explicitly extracted windows. */
+int pmub_stream_begin(pmub_batch *b, unsigned hop, unsigned max_frames_per_push, const void *history,
+                      unsigned long long first_sample_index);
+int pmub_stream_push(pmub_batch *b, int n_frames, const void *new_samples, const void *mid_fracsec,
+                     void *frames);
 int pmub_sync(pmub_batch *b);
 /* Run on the caller's CUDA stream (cudaStream_t passed as void*); NULL = own stream. */
 int pmub_set_stream(pmub_batch *b, void *cuda_stream);

@@ -109,6 +109,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.pmub_estimate_async.argtypes = [vp, vp, vp, vp]
     lib.pmub_estimate_frames.argtypes = [vp, ip, vp, vp, vp]
     lib.pmub_estimate_frames_async.argtypes = [vp, ip, vp, vp, vp]
+    lib.pmub_stream_begin.argtypes = [vp, C.c_uint, C.c_uint, vp, C.c_ulonglong]
+    lib.pmub_stream_push.argtypes = [vp, ip, vp, vp, vp]
     lib.pmub_sync.argtypes = [vp]
     lib.pmub_set_stream.argtypes = [vp, vp]
     lib.pmub_launch_count.argtypes = [vp]
@@ -120,7 +122,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.pmub_get_debug.argtypes = [vp, vp, vp]
     for fn in ("pmub_validate", "pmub_parse_ini", "pmub_create", "pmub_create_ini", "pmub_destroy",
                "pmub_get_info", "pmub_estimate", "pmub_estimate_async", "pmub_estimate_frames",
-               "pmub_estimate_frames_async", "pmub_sync", "pmub_set_stream",
+               "pmub_estimate_frames_async", "pmub_stream_begin", "pmub_stream_push", "pmub_sync", "pmub_set_stream",
                "pmub_reset", "pmub_get_state", "pmub_set_state", "pmub_set_debug", "pmub_get_debug"):
         getattr(lib, fn).restype = ip
     if path is None:
@@ -257,6 +259,43 @@ class BatchEstimator:
                 out = np.empty((F, n, c, 4), dtype=self.dtype)
         self._check(self.lib.pmub_estimate_frames(self._h, F, _ptr(windows), _ptr(mid_fracsec), _ptr(out)),
                     "pmub_estimate_frames")
+        return out
+
+    # -- streaming front end --------------------------------------------------
+    def stream_begin(self, hop: int = 0, max_frames_per_push: int = 8, history=None, first_sample_index: int = 0) -> int:
+        """Keep every stream's recent samples in an HBM ring; ``history`` = the ``win_len - hop``
+        samples ``[n_instances, n_channels, win_len - hop]`` that precede the first push (None = zeros).
+        Returns the hop in samples."""
+        if history is not None and not hasattr(history, "data_ptr"):
+            history = np.ascontiguousarray(history, dtype=self.dtype)
+        self._check(self.lib.pmub_stream_begin(self._h, int(hop), int(max_frames_per_push),
+                                               _ptr(history) if history is not None else None,
+                                               int(first_sample_index)), "pmub_stream_begin")
+        self.hop = int(hop) if hop else None
+        return self.hop
+
+    def stream_push(self, new_samples, mid_fracsec=None, out=None):
+        """``new_samples [F, n_instances, n_channels, hop]`` -> frames ``[F, n_instances, n_channels, 4]``;
+        ``mid_fracsec [F, n_instances]`` or None (computed on the device from the sample counter)."""
+        n, c = self.n_instances, self.n_channels
+        is_torch = hasattr(new_samples, "data_ptr")
+        F = int(new_samples.shape[0])
+        if is_torch:
+            import torch
+
+            tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+            assert new_samples.dtype == tdt and new_samples.is_contiguous()
+            if out is None:
+                out = torch.empty((F, n, c, 4), dtype=tdt, device=new_samples.device)
+        else:
+            new_samples = np.ascontiguousarray(new_samples, dtype=self.dtype)
+            if mid_fracsec is not None:
+                mid_fracsec = np.ascontiguousarray(mid_fracsec, dtype=self.dtype)
+            if out is None:
+                out = np.empty((F, n, c, 4), dtype=self.dtype)
+        self._check(self.lib.pmub_stream_push(self._h, F, _ptr(new_samples),
+                                              _ptr(mid_fracsec) if mid_fracsec is not None else None, _ptr(out)),
+                    "pmub_stream_push")
         return out
 
     def estimate_frames_async(self, n_frames: int, d_windows, d_mid_fracsec, d_out) -> None:

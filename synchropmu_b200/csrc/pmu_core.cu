@@ -46,6 +46,13 @@ struct pmub_batch {
     unsigned char* d_out;       // frames [n][4] float_p, then export [n][4] double
     unsigned char* d_frames;    // staging for multi-frame host outputs (lazy)
     size_t d_frames_cap;
+    // streaming front end (pmub_stream_*): per-stream sample rings resident in HBM
+    unsigned char* d_ring;      // float_p [n_windows][ring_cap]
+    long long ring_cap;         // samples per stream ring (multiple of hop, >= win_len + (max_frames-1)*hop)
+    long long ring_wpos;        // next write position
+    int hop, stream_max_frames;
+    unsigned long long stream_origin, stream_pushed;  // absolute index of sample 0; samples pushed so far
+    unsigned char* d_push;      // staging for device-side mid / host mid of a push (lazy)
     int* d_dbg;
     double* d_spec;
     bool debug, mirror;
@@ -77,14 +84,30 @@ static int grid_for(const pmub_batch* b, long long n)
 
 // Launch the kernel over streams [w0, w1) of the batch (w0 on an instance boundary), for
 // n_frames consecutive frames laid out frame-major with the full batch as frame pitch.
+// Where a launch reads its windows from when it is fed by the streaming front end.
+struct RingSrc {
+    long long start;            // ring position of frame 0's first sample
+    unsigned long long t0;      // absolute sample index (mod fs) of that sample
+};
+
 static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames, const void* d_windows_base,
-                        const void* d_mid_base, void* d_frames_base, double* d_export_base, cudaStream_t s)
+                        const void* d_mid_base, void* d_frames_base, double* d_export_base, cudaStream_t s,
+                        const RingSrc* ring = nullptr)
 {
     if (w1 <= w0 || n_frames < 1) return 0;
     KernelArgs a = b->args;
     const size_t sz = (size_t)b->dtype;
-    a.windows = (const unsigned char*)d_windows_base + (size_t)w0 * b->d.N * sz;
-    a.mid = (const unsigned char*)d_mid_base + (size_t)(w0 / b->C) * sz;
+    if (ring) {
+        a.windows = b->d_ring + (size_t)w0 * (size_t)b->ring_cap * sz;
+        a.ring_cap = b->ring_cap;
+        a.ring_start = ring->start;
+        a.hop = b->hop;
+        a.fs = (int)b->cfg.fs;
+        a.t0_samples = ring->t0;
+    } else {
+        a.windows = (const unsigned char*)d_windows_base + (size_t)w0 * b->d.N * sz;
+    }
+    a.mid = d_mid_base ? (const unsigned char*)d_mid_base + (size_t)(w0 / b->C) * sz : nullptr;
     a.frames = (unsigned char*)d_frames_base + (size_t)w0 * 4 * sz;
     a.st_fold = b->st_fold + w0;
     a.st_dl0 = b->st_dl0 + w0;
@@ -98,7 +121,8 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     a.spec_out = b->debug ? b->d_spec + (size_t)w0 * b->cfg.n_bins * 2 : nullptr;
     a.state_export = d_export_base ? d_export_base + (size_t)w0 * 4 : nullptr;
     // TMA bulk copies need 16-byte aligned sources; otherwise per-element cp.async
-    const bool ok16 = b->plan.aligned16 && (((uintptr_t)a.windows) % 16 == 0);
+    bool ok16 = b->plan.aligned16 && (((uintptr_t)a.windows) % 16 == 0);
+    if (ring) ok16 = ok16 && ((size_t)b->ring_cap * sz) % 16 == 0 && ((size_t)b->hop * sz) % 16 == 0;
     a.load_mode = ok16 ? PMU_LOAD_BULK : PMU_LOAD_ELEM;
     static const int force_elem = getenv("PMU_FORCE_ELEM_LOAD") ? atoi(getenv("PMU_FORCE_ELEM_LOAD")) : 0;
     if (force_elem) a.load_mode = PMU_LOAD_ELEM;
@@ -125,15 +149,20 @@ static int frames_per_launch(const pmub_batch* b, long long n, int n_frames)
 
 // launch_range for any frame count: splits into per-frame launches when one launch cannot carry them
 static int launch_frames(pmub_batch* b, long long w0, long long w1, int n_frames, const void* dW, const void* dM,
-                         void* dF, double* d_export, cudaStream_t s)
+                         void* dF, double* d_export, cudaStream_t s, const RingSrc* ring = nullptr)
 {
     const int fpl = frames_per_launch(b, w1 - w0, n_frames);
     const size_t sz = (size_t)b->dtype;
     for (int f = 0; f < n_frames; f += fpl) {
         const int nf = (n_frames - f < fpl) ? n_frames - f : fpl;
-        if (launch_range(b, w0, w1, nf, (const unsigned char*)dW + (size_t)f * b->n_windows * b->d.N * sz,
-                         (const unsigned char*)dM + (size_t)f * b->n_inst * sz, (unsigned char*)dF + (size_t)f * b->n_windows * 4 * sz,
-                         d_export, s))
+        RingSrc r2;
+        if (ring) {
+            r2.start = (ring->start + (long long)f * b->hop) % b->ring_cap;
+            r2.t0 = (ring->t0 + (unsigned long long)f * (unsigned)b->hop) % b->cfg.fs;
+        }
+        if (launch_range(b, w0, w1, nf, ring ? nullptr : (const unsigned char*)dW + (size_t)f * b->n_windows * b->d.N * sz,
+                         dM ? (const unsigned char*)dM + (size_t)f * b->n_inst * sz : nullptr,
+                         (unsigned char*)dF + (size_t)f * b->n_windows * 4 * sz, d_export, s, ring ? &r2 : nullptr))
             return -1;
     }
     return 0;
@@ -176,7 +205,7 @@ static int free_batch(pmub_batch* b)
     cudaSetDevice(b->device);
     cudaFree(b->dU); cudaFree(b->dV); cudaFree(b->dT);
     cudaFree(b->st_fold); cudaFree(b->st_dl0); cudaFree(b->st_dl1); cudaFree(b->st_state);
-    cudaFree(b->d_windows); cudaFree(b->d_mid); cudaFree(b->d_out); cudaFree(b->d_frames);
+    cudaFree(b->d_windows); cudaFree(b->d_mid); cudaFree(b->d_out); cudaFree(b->d_frames); cudaFree(b->d_ring);
     cudaFree(b->d_dbg); cudaFree(b->d_spec);
     if (b->h_in) cudaFreeHost(b->h_in);
     if (b->h_out) cudaFreeHost(b->h_out);
@@ -451,6 +480,92 @@ int pmub_estimate_frames(pmub_batch* b, int n_frames, const void* windows, const
 int pmub_estimate(pmub_batch* b, const void* windows, const void* mid, void* frames)
 {
     return pmub_estimate_frames(b, 1, windows, mid, frames);
+}
+
+// ---- streaming front end -----------------------------------------------------------------------
+int pmub_stream_begin(pmub_batch* b, unsigned hop, unsigned max_frames_per_push, const void* history,
+                      unsigned long long first_sample_index)
+{
+    if (!b) { set_error("[pmu_stream] ERROR: NULL batch"); return -1; }
+    CUDA_OK(cudaSetDevice(b->device));
+    if (hop == 0) hop = b->cfg.fs / b->cfg.frame_rate;   // one frame every 1/frame_rate seconds
+    if (hop == 0 || hop > b->d.N) { set_error("[pmu_stream] ERROR: hop must be in 1..win_len"); return -1; }
+    if (max_frames_per_push < 1) max_frames_per_push = 1;
+    if (pmub_sync(b)) return -1;
+    const size_t sz = (size_t)b->dtype;
+    const long long N = b->d.N;
+    long long cap = N + (long long)(max_frames_per_push - 1) * hop;
+    cap = (cap + hop - 1) / hop * hop;                  // whole hops: a pushed block never wraps
+    if (b->d_ring) { cudaFree(b->d_ring); b->d_ring = nullptr; }
+    CUDA_OK(cudaMalloc(&b->d_ring, (size_t)b->n_windows * (size_t)cap * sz));
+    CUDA_OK(cudaMemset(b->d_ring, 0, (size_t)b->n_windows * (size_t)cap * sz));
+    b->ring_cap = cap;
+    b->hop = (int)hop;
+    b->stream_max_frames = (int)max_frames_per_push;
+    const long long hist = N - hop;                     // samples needed before the first push completes a window
+    if (history && hist > 0)
+        CUDA_OK(cudaMemcpy2D(b->d_ring, (size_t)cap * sz, history, (size_t)hist * sz, (size_t)hist * sz, (size_t)b->n_windows,
+                             cudaMemcpyDefault));
+    b->ring_wpos = hist % cap;
+    b->stream_origin = first_sample_index;
+    b->stream_pushed = (unsigned long long)hist;
+    return 0;
+}
+
+int pmub_stream_push(pmub_batch* b, int n_frames, const void* new_samples, const void* mid, void* frames)
+{
+    if (!b || !b->d_ring) { set_error("[pmu_stream] ERROR: call pmub_stream_begin first"); return -1; }
+    if (!new_samples || !frames || n_frames < 1 || n_frames > b->stream_max_frames) {
+        set_error("[pmu_stream] ERROR: bad argument (n_frames must be 1..max_frames_per_push)");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(b->device));
+    const size_t sz = (size_t)b->dtype;
+    const size_t n = (size_t)b->n_windows;
+    const long long cap = b->ring_cap, hop = b->hop, N = b->d.N;
+    const size_t mid_bytes = (size_t)b->n_inst * sz, fr_bytes = n * 4 * sz;   // per frame
+    const bool in_dev = is_device_ptr(new_samples), mid_dev = mid ? is_device_ptr(mid) : true, fr_dev = is_device_ptr(frames);
+    if (mid && !mid_dev && ensure_cap(&b->d_mid, &b->d_mid_cap, mid_bytes * n_frames)) return -1;
+    if (!fr_dev && ensure_cap(&b->d_frames, &b->d_frames_cap, fr_bytes * n_frames)) return -1;
+    const unsigned char* dM = mid ? (mid_dev ? (const unsigned char*)mid : b->d_mid) : nullptr;
+    unsigned char* dF = fr_dev ? (unsigned char*)frames : b->d_frames;
+    RingSrc ring;
+    ring.start = ((b->ring_wpos + hop - N) % cap + cap) % cap;
+    ring.t0 = (b->stream_origin + b->stream_pushed + (unsigned long long)hop - (unsigned long long)N) % b->cfg.fs;
+
+    int n_chunks = 1;
+    if (!in_dev) {
+        const size_t target = 32u << 20;
+        n_chunks = (int)((n * (size_t)hop * sz * n_frames + target - 1) / target);
+        if (n_chunks < 1) n_chunks = 1;
+        if (n_chunks > 64) n_chunks = 64;
+        if ((unsigned)n_chunks > b->n_inst) n_chunks = (int)b->n_inst;
+    }
+    if (mid && !mid_dev) CUDA_OK(cudaMemcpyAsync(b->d_mid, mid, mid_bytes * n_frames, cudaMemcpyHostToDevice, main_stream(b)));
+    if (!b->has_user_stream) {
+        CUDA_OK(cudaEventRecord(b->ev_order, main_stream(b)));
+        CUDA_OK(cudaStreamWaitEvent(b->stream[0], b->ev_order, 0));
+        CUDA_OK(cudaStreamWaitEvent(b->stream[1], b->ev_order, 0));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        cudaStream_t s = b->has_user_stream ? b->user_stream : b->stream[c & 1];
+        const long long i0 = (long long)b->n_inst * c / n_chunks, i1 = (long long)b->n_inst * (c + 1) / n_chunks;
+        const long long w0 = i0 * b->C, w1 = i1 * b->C;
+        // ingest: frame f's hop samples of every stream go to ring position (wpos + f*hop) mod cap
+        for (int f = 0; f < n_frames; ++f) {
+            const long long p = (b->ring_wpos + (long long)f * hop) % cap;
+            CUDA_OK(cudaMemcpy2DAsync(b->d_ring + ((size_t)w0 * (size_t)cap + (size_t)p) * sz, (size_t)cap * sz,
+                                      (const unsigned char*)new_samples + ((size_t)f * n + (size_t)w0) * (size_t)hop * sz, (size_t)hop * sz,
+                                      (size_t)hop * sz, (size_t)(w1 - w0), cudaMemcpyDefault, s));
+        }
+        if (launch_frames(b, w0, w1, n_frames, nullptr, dM, dF, nullptr, s, &ring)) return -1;
+        if (!fr_dev)
+            CUDA_OK(cudaMemcpy2DAsync((unsigned char*)frames + (size_t)w0 * 4 * sz, fr_bytes, dF + (size_t)w0 * 4 * sz, fr_bytes,
+                                      (size_t)(w1 - w0) * 4 * sz, (size_t)n_frames, cudaMemcpyDeviceToHost, s));
+    }
+    b->ring_wpos = (b->ring_wpos + (long long)n_frames * hop) % cap;
+    b->stream_pushed += (unsigned long long)n_frames * (unsigned long long)hop;
+    return pmub_sync(b);
 }
 
 int pmub_get_state(pmub_batch* b, double* freq_old, double* dl0, double* dl1, unsigned char* state)

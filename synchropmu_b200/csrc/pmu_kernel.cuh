@@ -69,6 +69,15 @@ struct KernelArgs {
     long long frame_stride;      // streams per frame in the caller's arrays (>= n_windows: a launch
                                  // may cover a sub-range of the batch), in windows
     long long mid_frame_stride;  // instances per frame in `mid`
+    // streaming front end: when ring_cap > 0 `windows` is a per-stream ring buffer
+    // InT [n_streams][ring_cap]; frame f of a stream is the win_len samples starting at
+    // (ring_start + f * hop) mod ring_cap (one wrap at most), and mid_fracsec may be derived
+    // from the running sample counter instead of being read (mid == nullptr)
+    long long ring_cap;
+    long long ring_start;
+    int hop;
+    int fs;
+    unsigned long long t0_samples;   // absolute index (mod fs) of the first sample of frame 0's window
     // optional debug / mirror outputs (may be null); frame-major like `frames`
     int* dbg;                    // [n_frames][frame_stride]  km | flags
     double* spec_out;            // [n_frames][frame_stride][K][2] Hann-windowed bins
@@ -127,6 +136,26 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Copy `len` elements starting `off` elements into a window that begins at ring position `start`
+// of a ring of `cap` elements (cap == 0: plain linear window at `base`): one bulk copy, or two when
+// the segment crosses the end of the ring.  Sizes/addresses stay 16-byte granular because the wrap
+// point is a whole number of hops into the window (checked on the host).
+template <typename InT>
+__device__ __forceinline__ void bulk_segment(unsigned char* dst, const InT* base, long long start, long long cap,
+                                             int off, int len, void* bar)
+{
+    if (cap == 0) {
+        bulk_g2s(dst, base + off, (uint32_t)(len * sizeof(InT)), bar);
+        return;
+    }
+    long long p = start + off;
+    if (p >= cap) p -= cap;
+    const long long room = cap - p;
+    const int n1 = room < (long long)len ? (int)room : len;
+    bulk_g2s(dst, base + p, (uint32_t)(n1 * sizeof(InT)), bar);
+    if (n1 < len) bulk_g2s(dst + (size_t)n1 * sizeof(InT), base, (uint32_t)((len - n1) * sizeof(InT)), bar);
+}
+
 template <int BYTES>
 __device__ __forceinline__ void cp_async_elem(void* dst, const void* src)
 {
@@ -244,7 +273,14 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, int po
         a.st_dl0[w] = rs.dl0;
         a.st_dl1[w] = rs.dl1;
         a.st_state[w] = (unsigned char)rs.st;
-        double mid = (double)reinterpret_cast<const InT*>(a.mid)[(long long)frame * a.mid_frame_stride + w / pp.C];
+        double mid;
+        if (a.mid) {
+            mid = (double)reinterpret_cast<const InT*>(a.mid)[(long long)frame * a.mid_frame_stride + w / pp.C];
+        } else {
+            // centre of the window, modulo one second, from the running sample counter
+            const unsigned long long c = (a.t0_samples + (unsigned long long)frame * (unsigned)a.hop + (unsigned)(a.N / 2)) % (unsigned)a.fs;
+            mid = (double)(InT)((double)c / (double)a.fs);
+        }
         double fr[4];
         fill_frame(pp, t, y, mid, fr);
         InT* out = reinterpret_cast<InT*>(a.frames) + (size_t)wf * 4;
@@ -350,19 +386,24 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                     const int item = i / a.nslab, sl = i - item * a.nslab;
                     const int f = item / n_local, t = item - f * n_local;
                     unsigned char* dst = stages + (size_t)st * a.stage_bytes;
-                    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.windows) +
-                                               ((size_t)f * a.frame_stride + (size_t)(w_begin + t)) * win_bytes;
+                    const InT* src;
+                    long long start = 0;
+                    if (a.ring_cap == 0) {
+                        src = reinterpret_cast<const InT*>(a.windows) + ((size_t)f * a.frame_stride + (size_t)(w_begin + t)) * a.N;
+                    } else {
+                        src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + t) * a.ring_cap;
+                        start = (a.ring_start + (long long)f * a.hop) % a.ring_cap;
+                    }
                     if (a.nslab == 1 && pitch == a.L) {
                         mbar_expect_tx(&ctrl->full[st], (uint32_t)win_bytes);
-                        bulk_g2s(dst, src, (uint32_t)win_bytes, &ctrl->full[st]);
+                        bulk_segment<InT>(dst, src, start, a.ring_cap, 0, a.N, &ctrl->full[st]);
                     } else {
                         const int a_lo = sl * a.W;
                         const int w_s = min(a.W, a.L - a_lo);
-                        const uint32_t row_bytes = (uint32_t)(w_s * sizeof(InT));
-                        mbar_expect_tx(&ctrl->full[st], row_bytes * M);
+                        mbar_expect_tx(&ctrl->full[st], (uint32_t)(w_s * sizeof(InT)) * M);
                         for (int b = 0; b < M; ++b)
-                            bulk_g2s(dst + (size_t)b * pitch * sizeof(InT),
-                                     src + ((size_t)a_lo + (size_t)a.L * b) * sizeof(InT), row_bytes, &ctrl->full[st]);
+                            bulk_segment<InT>(dst + (size_t)b * pitch * sizeof(InT), src, start, a.ring_cap, a_lo + a.L * b, w_s,
+                                              &ctrl->full[st]);
                     }
                 }
             }
@@ -374,13 +415,22 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 const int item = i / a.nslab, sl = i - item * a.nslab;
                 const int f = item / n_local, t = item - f * n_local;
                 InT* dst = reinterpret_cast<InT*>(stages + (size_t)st * a.stage_bytes);
-                const InT* src = reinterpret_cast<const InT*>(reinterpret_cast<const unsigned char*>(a.windows) +
-                                                              ((size_t)f * a.frame_stride + (size_t)(w_begin + t)) * win_bytes);
+                const InT* src;
+                long long start = 0;
+                if (a.ring_cap == 0) {
+                    src = reinterpret_cast<const InT*>(a.windows) + ((size_t)f * a.frame_stride + (size_t)(w_begin + t)) * a.N;
+                } else {
+                    src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + t) * a.ring_cap;
+                    start = (a.ring_start + (long long)f * a.hop) % a.ring_cap;
+                }
                 const int a_lo = sl * a.W;
                 const int w_s = min(a.W, a.L - a_lo);
                 for (int b = 0; b < M; ++b)
-                    for (int e = lane; e < w_s; e += PMU_WARP)
-                        cp_async_elem<(int)sizeof(InT)>(dst + (size_t)b * pitch + e, src + (size_t)a_lo + (size_t)a.L * b + e);
+                    for (int e = lane; e < w_s; e += PMU_WARP) {
+                        long long p = start + a_lo + (long long)a.L * b + e;
+                        if (a.ring_cap != 0 && p >= a.ring_cap) p -= a.ring_cap;
+                        cp_async_elem<(int)sizeof(InT)>(dst + (size_t)b * pitch + e, src + p);
+                    }
                 cp_async_mbar_arrive(&ctrl->full[st]);
             }
         }

@@ -386,3 +386,52 @@ def test_c_examples_build_and_run(tmp_path, src, defs, lib):
         assert "already initialized" in r.stderr and "not initialized" in r.stderr
     else:
         assert "instance  0 ch0: amp 325.27" in r.stdout and "freq 49.5000000" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------
+# streaming front end: pushing hop new samples == estimating the explicitly extracted windows
+# ---------------------------------------------------------------------------------------
+def _long_streams(cfg, n_streams, total, seed):
+    rng = np.random.default_rng(seed)
+    t = np.arange(total) / cfg["fs"]
+    f = cfg["f0"] + rng.uniform(-1.5, 1.5, (n_streams, 1))
+    a = rng.uniform(0.5, 300.0, (n_streams, 1))
+    ph = rng.uniform(-3, 3, (n_streams, 1))
+    ramp = rng.uniform(-1, 1, (n_streams, 1))
+    x = a * np.cos(2 * math.pi * f * t + math.pi * ramp * t * t + ph) + 0.1 * a * np.cos(2 * math.pi * 1.5 * cfg["f0"] * t + ph)
+    return x + 1e-3 * a * rng.standard_normal(x.shape)
+
+
+@pytest.mark.parametrize("cfg,dtype,F,given_mid", [
+    (configs.DEFAULT_INI, "f64", 1, True),
+    (configs.DEFAULT_INI, "f64", 3, False),
+    (configs.M_CLASS_INI, "f64", 2, False),
+    (configs.CFG5_600, "f64", 4, True),
+    (configs.DEFAULT_INI, "f32", 2, False),
+    (dict(configs.DEFAULT_INI, fs=4750, n_cycles=3, n_bins=7), "f64", 2, False),   # odd hop: per-element loader
+], ids=["default_F1", "default_F3", "mclass_F2", "cfg5_F4", "float_F2", "oddhop_F2"])
+def test_stream_push_equals_explicit_windows(cfg, dtype, F, given_mid):
+    dt = DT[dtype]
+    n_inst, C_ = 23, 6
+    N, hop = configs.win_len(cfg), configs.hop(cfg)
+    pushes = 5
+    T = pushes * F                       # more frames than the ring holds: exercises the wrap-around
+    x = _long_streams(cfg, n_inst * C_, N + T * hop, seed=N + F).astype(dt)
+    with BatchEstimator(cfg, n_inst, C_, dtype=dt) as explicit, BatchEstimator(cfg, n_inst, C_, dtype=dt) as stream:
+        want = np.zeros((T, n_inst, C_, 4), dtype=dt)
+        mids = np.zeros((T, n_inst), dtype=dt)
+        for t in range(T):
+            mids[t] = signals.mid_fracsec(cfg, t)
+            want[t] = explicit.estimate(x[:, t * hop:t * hop + N].reshape(n_inst, C_, N), mids[t])
+        stream.stream_begin(hop=0, max_frames_per_push=F, history=x[:, :N - hop].reshape(n_inst, C_, N - hop))
+        got = np.zeros_like(want)
+        for p in range(pushes):
+            blk = np.stack([x[:, N - hop + t * hop:N + t * hop].reshape(n_inst, C_, hop) for t in range(p * F, (p + 1) * F)])
+            got[p * F:(p + 1) * F] = stream.stream_push(blk, mids[p * F:(p + 1) * F] if given_mid else None)
+    if given_mid:
+        assert np.array_equal(got, want)
+    else:
+        # amp / freq / ROCOF do not depend on mid_fracsec; the phase correction uses a mid that may
+        # differ by an ulp from the caller-side formula
+        assert np.array_equal(got[..., [0, 2, 3]], want[..., [0, 2, 3]])
+        assert np.max(np.abs(got[..., 1].astype(np.float64) - want[..., 1])) < (1e-11 if dtype == "f64" else 1e-5)
