@@ -340,7 +340,6 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     a.n_u = b->plan.n_u; a.scratch_global = 0;
     a.off_ctrl = b->plan.off_ctrl; a.off_U = b->plan.off_U; a.off_V = b->plan.off_V; a.off_trig = b->plan.off_trig;
     a.off_raw = b->plan.off_raw; a.off_post = b->plan.off_post; a.off_red = b->plan.off_red; a.off_stage = b->plan.off_stage;
-    a.red_stride = b->plan.red_stride;
     a.U = b->dU; a.V = b->dV; a.trig = b->dT; a.scratch = nullptr;
 
     if (pmub_reset(b)) { free_batch(b); return -1; }

@@ -299,14 +299,13 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
     p.raw_stride = 2 * p.Kp + 1;  // odd number of doubles: lane-per-window reads stay conflict-free
     // per-lane row of the reduction scratch: >= 2*Kp doubles, an odd number of 16-byte units so that the
     // 128-bit stores of a quarter warp hit distinct banks
-    p.red_stride = (p.Kp % 2 == 0) ? 2 * p.Kp + 2 : 2 * p.Kp + 4;
+    p.red_stride = 2 * p.KC + 2;  // compile-time in the kernel (immediate LDS offsets)
 
     int want_cons = env_int("PMU_CONSUMER_WARPS", PMU_MAX_CONSUMERS);
     if (want_cons < 1) want_cons = 1;
     if (want_cons > PMU_MAX_CONSUMERS) want_cons = PMU_MAX_CONSUMERS;
-    int want_raw = env_int("PMU_RAW_BUFFERS", 4);
-    if (want_raw < 2) want_raw = 2;
-    if (want_raw > PMU_MAX_RAW) want_raw = PMU_MAX_RAW;
+    int want_raw = env_int("PMU_RAW_BUFFERS", 4);   // powers of two only (the kernel masks)
+    want_raw = want_raw >= 8 ? 8 : (want_raw >= 4 ? 4 : 2);
     int want_post = env_int("PMU_POST_SLOTS", 4);
     if (want_post < 1) want_post = 1;
     if (want_post > PMU_MAX_POST) want_post = PMU_MAX_POST;
@@ -332,7 +331,7 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
         p.smem_bytes = off + (ns > 0 ? ns : 0) * p.stage_bytes;
         return ns;
     };
-    const int tries[][3] = {{want_cons, want_raw, want_post}, {want_cons, 3, 3}, {want_cons, 2, 2}, {want_cons, 2, 1},
+    const int tries[][3] = {{want_cons, want_raw, want_post}, {want_cons, 2, 3}, {want_cons, 2, 2}, {want_cons, 2, 1},
                             {5, 2, 2}, {5, 2, 1}, {3, 2, 1}, {2, 2, 1}, {1, 2, 1}};
     bool ok = false;
     for (int pass = 0; pass < 2 && !ok; ++pass) {

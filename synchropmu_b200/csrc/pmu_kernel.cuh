@@ -49,7 +49,6 @@ struct KernelArgs {
     int scratch_global;          // 1: X/W scratch lives in global memory (large n_bins)
     // shared-memory layout (byte offsets from the dynamic smem base)
     int off_ctrl, off_U, off_V, off_trig, off_raw, off_post, off_red, off_stage;
-    int red_stride;              // doubles per lane row of the per-warp reduction scratch (even)
     // tables (global memory; copied to smem by the kernel)
     const pmu_c* U;              // [ceil(L/32)][KC]   W_N^{32 i k}
     const pmu_c* V;              // [KC][32]           W_N^{lane k}
@@ -198,25 +197,47 @@ struct ReduceFinal {  // values left per lane after the five exchange steps
                          value = (s4 + 1) / 2;
 };
 
+// ---- division by a run-time constant without the ~25-instruction integer-divide sequence ----
+// q = umulhi(x, floor((2^32-1)/d)) is the true quotient or one less (x < 2^31): one correction.
+struct FastDiv {
+    unsigned d, m;
+    __device__ __forceinline__ void init(unsigned dd)
+    {
+        d = dd;
+        m = 0xFFFFFFFFu / dd;
+    }
+    __device__ __forceinline__ unsigned div(unsigned x, unsigned* rem) const
+    {
+        unsigned q = __umulhi(x, m);
+        unsigned r = x - q * d;
+        if (r >= d) { ++q; r -= d; }
+        *rem = r;
+        return q;
+    }
+};
+
 // ---- window -> (batch, slot) mapping inside one CTA: balanced batches of <= 32 -----------
 struct BatchMap {
     int nb, q, rem;  // batches, base size, number of batches with q+1 windows
+    FastDiv by_q, by_q1;
     __device__ __forceinline__ void init(int n)
     {
         nb = (n + PMU_WARP - 1) / PMU_WARP;
         if (nb < 1) nb = 1;
         q = n / nb;
         rem = n - q * nb;
+        by_q.init((unsigned)q);
+        by_q1.init((unsigned)(q + 1));
     }
     __device__ __forceinline__ void locate(int t, int* g, int* slot, int* size, int* first) const
     {
         int big = rem * (q + 1);
+        unsigned r;
         if (t < big) {
-            *g = t / (q + 1); *slot = t - *g * (q + 1); *size = q + 1; *first = *g * (q + 1);
+            *g = (int)by_q1.div((unsigned)t, &r); *slot = (int)r; *size = q + 1; *first = *g * (q + 1);
         } else {
-            int u = t - big;
-            int gg = u / q;
-            *g = rem + gg; *slot = u - gg * q; *size = q; *first = big + gg * q;
+            int gg = (int)by_q.div((unsigned)(t - big), &r);
+            *g = rem + gg; *slot = (int)r; *size = q; *first = big + gg * q;
         }
     }
 };
@@ -379,12 +400,10 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         // ================= PRODUCER =================
         if (a.load_mode == PMU_LOAD_BULK) {
             if (lane == 0) {
+                int st = 0, sl = 0, t = 0, f = 0;      // running (stage, slab, stream, frame) of slab i
+                uint32_t par = 0;
                 for (int i = 0; i < total_slabs; ++i) {
-                    const int st = i % a.n_stage;
-                    const uint32_t par = (uint32_t)((i / a.n_stage) & 1);
                     mbar_wait(&ctrl->empty[st], par ^ 1u);
-                    const int item = i / a.nslab, sl = i - item * a.nslab;
-                    const int f = item / n_local, t = item - f * n_local;
                     unsigned char* dst = stages + (size_t)st * a.stage_bytes;
                     const InT* src;
                     long long start = 0;
@@ -405,15 +424,18 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                             bulk_segment<InT>(dst + (size_t)b * pitch * sizeof(InT), src, start, a.ring_cap, a_lo + a.L * b, w_s,
                                               &ctrl->full[st]);
                     }
+                    if (++st == a.n_stage) { st = 0; par ^= 1u; }
+                    if (++sl == a.nslab) {
+                        sl = 0;
+                        if (++t == n_local) { t = 0; ++f; }
+                    }
                 }
             }
         } else {
+            int st = 0, sl = 0, t = 0, f = 0;
+            uint32_t par = 0;
             for (int i = 0; i < total_slabs; ++i) {
-                const int st = i % a.n_stage;
-                const uint32_t par = (uint32_t)((i / a.n_stage) & 1);
                 mbar_wait(&ctrl->empty[st], par ^ 1u);
-                const int item = i / a.nslab, sl = i - item * a.nslab;
-                const int f = item / n_local, t = item - f * n_local;
                 InT* dst = reinterpret_cast<InT*>(stages + (size_t)st * a.stage_bytes);
                 const InT* src;
                 long long start = 0;
@@ -432,6 +454,11 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                         cp_async_elem<(int)sizeof(InT)>(dst + (size_t)b * pitch + e, src + p);
                     }
                 cp_async_mbar_arrive(&ctrl->full[st]);
+                if (++st == a.n_stage) { st = 0; par ^= 1u; }
+                if (++sl == a.nslab) {
+                    sl = 0;
+                    if (++t == n_local) { t = 0; ++f; }
+                }
             }
         }
         return;
@@ -441,14 +468,23 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     // ================= CONSUMERS =================
     BatchMap bm;
     bm.init(n_local);
+    FastDiv by_nlocal, by_nstage;
+    by_nlocal.init((unsigned)n_local);
+    by_nstage.init((unsigned)a.n_stage);
     const int w_per_it = a.W / PMU_WARP;  // full-slab residue groups (W % 32 == 0 when nslab > 1)
+    const int raw_mask = a.n_raw - 1;     // n_raw is a power of two
 
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(&ctrl->ticket, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        const int f = item / n_local, t = item - f * n_local;
+        int f = 0, t = item;
+        if (a.n_frames > 1) {
+            unsigned r;
+            f = (int)by_nlocal.div((unsigned)item, &r);
+            t = (int)r;
+        }
 
         // ---- pruned rectangular DFT of stream t, frame f ----
         double acc[2 * KC];  // ar = acc[0..KC), ai = acc[KC..2KC)
@@ -457,8 +493,9 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         bool first = true;
         for (int sl = 0; sl < a.nslab; ++sl) {
             const int idx = item * a.nslab + sl;
-            const int st = idx % a.n_stage;
-            const int use = idx / a.n_stage;
+            unsigned st_u;
+            const int use = (int)by_nstage.div((unsigned)idx, &st_u);
+            const int st = (int)st_u;
             // Tickets are claimed out of order w.r.t. the ring: a parity wait is only unambiguous
             // once the stage's previous occupant (slab idx - n_stage) has been released.
             if (lane == 0)
@@ -498,9 +535,10 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         // ---- sum the 32 lane partials through shared memory: every lane drops its KC complex
         //      partials into its row of the warp's scratch (128-bit stores, conflict-free row
         //      stride), then lane c adds up column c of the 32 rows and deposits the total ----
-        double* red = reinterpret_cast<double*>(smem + a.off_red) + (size_t)(warp - 1) * PMU_WARP * a.red_stride;
+        constexpr int RS = 2 * KC + 2;  // row stride in doubles: an odd number of 16-byte units
+        double* red = reinterpret_cast<double*>(smem + a.off_red) + (size_t)(warp - 1) * PMU_WARP * RS;
         {
-            double2* my = reinterpret_cast<double2*>(red + (size_t)lane * a.red_stride);
+            double2* my = reinterpret_cast<double2*>(red + (size_t)lane * RS);
 #pragma unroll
             for (int k = 0; k < KC; ++k)
                 if (k < a.Kp) my[k] = make_double2(ar[k], ai[k]);
@@ -508,7 +546,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         int g, slot, bsz, first_t;
         bm.locate(t, &g, &slot, &bsz, &first_t);
         const int gb = f * bm.nb + g;              // batch id over the whole launch, in ticket order
-        const int rb = gb % a.n_raw;
+        const int rb = gb & raw_mask;
         if (lane == 0) {
             while (ld_volatile_s32(&ctrl->raw_owner[rb]) != gb) __nanosleep(64);
         }
@@ -520,10 +558,10 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
             for (int l = 0; l < PMU_WARP; l += 4) {
-                s0 += col[(l + 0) * a.red_stride];
-                s1 += col[(l + 1) * a.red_stride];
-                s2 += col[(l + 2) * a.red_stride];
-                s3 += col[(l + 3) * a.red_stride];
+                s0 += col[(l + 0) * RS];
+                s1 += col[(l + 1) * RS];
+                s2 += col[(l + 2) * RS];
+                s3 += col[(l + 3) * RS];
             }
             row[c] = (s0 + s1) + (s2 + s3);
         }
