@@ -53,6 +53,31 @@ PMU_HD constexpr double cos16(int k)
 }
 PMU_HD constexpr double sin16(int k) { return cos16(k - 4); }
 
+// On the device the three non-trivial twiddle values are read from the constant bank: an FP64
+// instruction takes a c[bank][offset] operand for free, whereas a 64-bit literal has to be
+// materialised with two (uniform) moves every time the compiler rematerialises it.
+#if defined(__CUDACC__)
+static __constant__ double pmu_tw16[3] = {0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173};
+#endif
+template <int K16>
+PMU_HD double cosv16()
+{
+    constexpr int k = K16 & 15;
+#if defined(__CUDA_ARCH__)
+    if constexpr (k == 1 || k == 15) return pmu_tw16[0];
+    else if constexpr (k == 2 || k == 14) return pmu_tw16[1];
+    else if constexpr (k == 3 || k == 13) return pmu_tw16[2];
+    else if constexpr (k == 5 || k == 11) return -pmu_tw16[2];
+    else if constexpr (k == 6 || k == 10) return -pmu_tw16[1];
+    else if constexpr (k == 7 || k == 9) return -pmu_tw16[0];
+    else return cos16(k);
+#else
+    return cos16(k);
+#endif
+}
+template <int K16>
+PMU_HD double sinv16() { return cosv16<K16 - 4>(); }
+
 // (tr, ti) = W_M^K * (orr, oi),  W_M = exp(-2 pi i / M), M | 16; trivial twiddles cost nothing.
 template <int K, int M>
 PMU_HD void tw_mul(double orr, double oi, double* tr, double* ti)
@@ -63,7 +88,7 @@ PMU_HD void tw_mul(double orr, double oi, double* tr, double* ti)
     else if constexpr (k16 == 8) { *tr = -orr; *ti = -oi; }       // -1
     else if constexpr (k16 == 12) { *tr = -oi; *ti = orr; }       // +i
     else {
-        constexpr double wr = cos16(k16), wi = -sin16(k16);
+        const double wr = cosv16<k16>(), wi = -sinv16<k16>();
         *tr = wr * orr - wi * oi;
         *ti = wr * oi + wi * orr;
     }
@@ -105,7 +130,7 @@ struct RFFT {
                     else if constexpr (k16 == 8) { re[k] = Er - Or; im[k] = 0.0; }
                     else if constexpr (k16 == 4) { re[k] = Er; im[k] = -Or; }
                     else {
-                        constexpr double wr = cos16(k16), wi = -sin16(k16);
+                        const double wr = cosv16<k16>(), wi = -sinv16<k16>();
                         re[k] = Er + wr * Or; im[k] = wi * Or;
                     }
                 } else {
