@@ -145,6 +145,24 @@ int pmub_get_state(pmub_batch *b, double *freq_old, double *dl0, double *dl1, un
 int pmub_set_state(pmub_batch *b, const double *freq_old, const double *dl0, const double *dl1,
                    const unsigned char *state);
 
+/* ---- consumers of the frame stream (not in the reference) ------
+ * Both take frames float_p [n_instances][n_channels][4] in host or device memory.
+ *
+ * pmub_sequence_components: channels are grouped in threes (a, b, c); out is
+ *   float_p [n_instances][n_channels/3][3][2] = (amp, ph) of the positive, negative and
+ *   zero sequence phasors.
+ * pmub_c37118_pack: one IEEE C37.118.2-2011 data frame per instance, big-endian:
+ *   SYNC 0xAA01 | FRAMESIZE | IDCODE (idcode0 + instance) | SOC | FRACSEC | STAT |
+ *   n_channels x {magnitude, angle[rad]} as IEEE float32 | FREQ [Hz] | DFREQ [Hz/s] | CHK
+ *   (CRC-CCITT, 0xFFFF seed), pmub_c37118_frame_bytes(n_channels) = 26 + 8 n_channels bytes each.
+ *   FREQ/DFREQ come from channel 0 of the instance. */
+int pmub_sequence_components(int dtype, const void *frames, void *out, unsigned n_instances,
+                             unsigned n_channels);
+int pmub_c37118_frame_bytes(unsigned n_channels);
+int pmub_c37118_pack(int dtype, const void *frames, void *out, unsigned n_instances,
+                     unsigned n_channels, unsigned idcode0, unsigned soc, unsigned fracsec,
+                     unsigned stat);
+
 /* ---- parity / debug observability ------------------------------------------------ */
 /* After pmub_set_debug(b, 1) every estimate also records, per (instance, channel):
  *   flags    int    : bits 0-15 = peak bin km of the first ipDFT, bit 16 = interference

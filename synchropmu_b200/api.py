@@ -120,6 +120,11 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.pmub_set_state.argtypes = [vp, vp, vp, vp, vp]
     lib.pmub_set_debug.argtypes = [vp, ip]
     lib.pmub_get_debug.argtypes = [vp, vp, vp]
+    lib.pmub_sequence_components.argtypes = [ip, vp, vp, C.c_uint, C.c_uint]
+    lib.pmub_c37118_frame_bytes.argtypes = [C.c_uint]
+    lib.pmub_c37118_pack.argtypes = [ip, vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
+    for fn in ("pmub_sequence_components", "pmub_c37118_frame_bytes", "pmub_c37118_pack"):
+        getattr(lib, fn).restype = ip
     for fn in ("pmub_validate", "pmub_parse_ini", "pmub_create", "pmub_create_ini", "pmub_destroy",
                "pmub_get_info", "pmub_estimate", "pmub_estimate_async", "pmub_estimate_frames",
                "pmub_estimate_frames_async", "pmub_stream_begin", "pmub_stream_push", "pmub_sync", "pmub_set_stream",
@@ -348,6 +353,44 @@ class BatchEstimator:
         shape = (self.n_instances, self.n_channels)
         return ((flags & 0xFFFF).reshape(shape), ((flags >> 16) & 1).astype(bool).reshape(shape),
                 (spec[..., 0] + 1j * spec[..., 1]).reshape(shape + (self.n_bins,)))
+
+
+def sequence_components(frames, lib=None):
+    """Symmetrical components of every three-phase channel group: frames ``[n_inst, n_ch, 4]`` (numpy or
+    torch, host or CUDA) -> ``[n_inst, n_ch // 3, 3, 2]`` = (amp, ph) of positive, negative, zero sequence."""
+    lib = lib or load_library()
+    n_inst, n_ch = int(frames.shape[0]), int(frames.shape[1])
+    if hasattr(frames, "data_ptr"):
+        import torch
+
+        code = PMUB_F64 if frames.dtype == torch.float64 else PMUB_F32
+        out = torch.empty((n_inst, n_ch // 3, 3, 2), dtype=frames.dtype, device=frames.device)
+        frames = frames.contiguous()
+    else:
+        frames = np.ascontiguousarray(frames)
+        code = PMUB_F64 if frames.dtype == np.float64 else PMUB_F32
+        out = np.empty((n_inst, n_ch // 3, 3, 2), dtype=frames.dtype)
+    if lib.pmub_sequence_components(code, _ptr(frames), _ptr(out), n_inst, n_ch) != 0:
+        raise RuntimeError(f"pmub_sequence_components failed: {last_error(lib)}")
+    return out
+
+
+def c37118_pack(frames, idcode0: int = 1, soc: int = 0, fracsec: int = 0, stat: int = 0, lib=None) -> np.ndarray:
+    """One IEEE C37.118.2 data frame per instance -> uint8 ``[n_inst, 26 + 8 n_ch]`` (host)."""
+    lib = lib or load_library()
+    n_inst, n_ch = int(frames.shape[0]), int(frames.shape[1])
+    if hasattr(frames, "data_ptr"):
+        import torch
+
+        code = PMUB_F64 if frames.dtype == torch.float64 else PMUB_F32
+        frames = frames.contiguous()
+    else:
+        frames = np.ascontiguousarray(frames)
+        code = PMUB_F64 if frames.dtype == np.float64 else PMUB_F32
+    out = np.empty((n_inst, lib.pmub_c37118_frame_bytes(n_ch)), dtype=np.uint8)
+    if lib.pmub_c37118_pack(code, _ptr(frames), out.ctypes.data, n_inst, n_ch, idcode0, soc, fracsec, stat) != 0:
+        raise RuntimeError(f"pmub_c37118_pack failed: {last_error(lib)}")
+    return out
 
 
 def shard_instances(n_instances: int, rank: int, world_size: int) -> tuple[int, int]:

@@ -337,10 +337,10 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
     a.n_stage = b->plan.n_stage; a.stage_bytes = b->plan.stage_bytes; a.n_cons = b->plan.n_cons;
     a.n_raw = b->plan.n_raw; a.raw_stride = b->plan.raw_stride; a.n_post = b->plan.n_post;
-    a.n_u = b->plan.n_u; a.scratch_global = 0;
+    a.n_u = b->plan.n_u;
     a.off_ctrl = b->plan.off_ctrl; a.off_U = b->plan.off_U; a.off_V = b->plan.off_V; a.off_trig = b->plan.off_trig;
     a.off_raw = b->plan.off_raw; a.off_post = b->plan.off_post; a.off_red = b->plan.off_red; a.off_stage = b->plan.off_stage;
-    a.U = b->dU; a.V = b->dV; a.trig = b->dT; a.scratch = nullptr;
+    a.U = b->dU; a.V = b->dV; a.trig = b->dT;
 
     if (pmub_reset(b)) { free_batch(b); return -1; }
     *out = b;

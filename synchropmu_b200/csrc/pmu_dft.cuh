@@ -12,7 +12,7 @@
 // FFT codelet in registers (compile-time twiddles), multiplies by the lane-uniform
 // twiddle W_N^{32 i k} (shared-memory broadcast) and accumulates; after the last residue
 // the sum is rotated by the lane twiddle W_N^{l k}.  The 32 partial spectra are then
-// summed by a transposing butterfly (pmu_kernel.cu).  The Hann window is applied
+// summed column-wise through shared memory (pmu_kernel.cuh).  The Hann window is applied
 // afterwards in the frequency domain, exact for the periodic Hann of :556:
 //     Xw[k] = X[k]/2 - (X[k-1] + X[k+1])/4,   X[-1] = conj X[1],
 // which is why KC must cover n_bins + 1 bins.  The same code is the mixed-radix path for

@@ -5,8 +5,8 @@
 // mbarrier complete_tx); when windows are not 16-byte granular it falls back to per-element
 // cp.async from all 32 lanes.  Warps 1..NC are CONSUMERS: each claims the next window of
 // the CTA's contiguous range (shared-memory ticket), computes its pruned rectangular DFT
-// from the stage (pmu_dft.cuh), reduces the 32 lane-partials with a transposing shuffle
-// butterfly and drops the K+1 bins into the batch's raw buffer.  The warp that completes
+// from the stage (pmu_dft.cuh), sums the 32 lane-partials through a per-warp shared-memory
+// scratch and drops the K+1 bins into the batch's raw buffer.  The warp that completes
 // a batch of <= 32 consecutive windows becomes its POST-PROCESSOR: lane = window, Hann in
 // the frequency domain, IpDFT / e-IpDFT / interference iterations (pmu_math.cuh), ROCOF
 // state read-modify-write in HBM, frame store.  No block-wide barrier after start-up.
@@ -46,14 +46,12 @@ struct KernelArgs {
     int n_raw, raw_stride;       // raw-bin buffers in the ring, doubles per window slot
     int n_post;                  // post-processing scratch slots
     int n_u;                     // entries of U (complex)
-    int scratch_global;          // 1: X/W scratch lives in global memory (large n_bins)
     // shared-memory layout (byte offsets from the dynamic smem base)
     int off_ctrl, off_U, off_V, off_trig, off_raw, off_post, off_red, off_stage;
     // tables (global memory; copied to smem by the kernel)
     const pmu_c* U;              // [ceil(L/32)][KC]   W_N^{32 i k}
     const pmu_c* V;              // [KC][32]           W_N^{lane k}
     const pmu_c* trig;           // [jlo + jhi + 1]
-    pmu_c* scratch;              // global X/W scratch when scratch_global
     // batch
     const void* windows;         // InT [n_windows][N]
     const void* mid;             // InT [n_windows / C]
@@ -168,34 +166,6 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p)
 {
     return *reinterpret_cast<const volatile int*>(p);
 }
-
-// ---- transposing butterfly: 32 lanes x NV partial sums -> ceil(NV/32) totals per lane ----
-template <int n, int XOR>
-struct ReduceScatter {
-    __device__ __forceinline__ static void run(double* v, int lane, int& base, int& lim)
-    {
-        if constexpr (XOR >= 1) {
-            constexpr int h = (n + 1) / 2;
-            const bool up = (lane & XOR) != 0;
-            static_for<0, h>([&](auto jc) {
-                constexpr int j = jc.value;
-                double lo = v[j];
-                double hi = (j + h < n) ? v[j + h] : 0.0;
-                double send = up ? lo : hi;
-                double keep = up ? hi : lo;
-                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, XOR);
-            });
-            if (up) base += h;
-            else lim = min(lim, base + h);
-            ReduceScatter<h, XOR / 2>::run(v, lane, base, lim);
-        }
-    }
-};
-template <int NV>
-struct ReduceFinal {  // values left per lane after the five exchange steps
-    static constexpr int s1 = (NV + 1) / 2, s2 = (s1 + 1) / 2, s3 = (s2 + 1) / 2, s4 = (s3 + 1) / 2,
-                         value = (s4 + 1) / 2;
-};
 
 // ---- division by a run-time constant without the ~25-instruction integer-divide sequence ----
 // q = umulhi(x, floor((2^32-1)/d)) is the true quotient or one less (x < 2^31): one correction.
@@ -506,11 +476,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             const int a_lo = sl * a.W;
             const int w_s = min(a.W, a.L - a_lo);
             const int n_it = (w_s + PMU_WARP - 1) / PMU_WARP;
-#ifdef PMU_EXP_ALWAYS_MASK
-            const bool all_full = false;
-#else
             const bool all_full = (w_s % PMU_WARP) == 0;
-#endif
             for (int ii = 0; ii < n_it; ++ii) {
                 const int a_loc = lane + PMU_WARP * ii;
                 double x[M];

@@ -37,11 +37,7 @@ int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t
 template <typename T, int M>
 int launch_kc(int KC, const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
 {
-#ifdef PMU_EXP_NOPITCH
-    constexpr int PITCH = 0;
-#else
     constexpr int PITCH = (M == 16) ? PMU_PITCH16 : 0;
-#endif
     switch (KC) {
         case 8: return launch_inst<T, M, 8, PITCH>(a, grid, block, smem, s);
         case 12: return launch_inst<T, M, 12, PITCH>(a, grid, block, smem, s);

@@ -54,16 +54,6 @@ PMU_HD void pmu_sincospi(double x, double* s, double* c)
 #endif
 }
 
-PMU_HD void pmu_sincos(double x, double* s, double* c)
-{
-#if defined(__CUDA_ARCH__)
-    sincos(x, s, c);
-#else
-    *s = sin(x);
-    *c = cos(x);
-#endif
-}
-
 // Read-only parameters of the post-DFT stage (uniform over a batch).
 struct PostParams {
     int K;         // n_bins

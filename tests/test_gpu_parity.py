@@ -508,3 +508,55 @@ def test_single_call_latency_report(capsys):
         print(f"\n[latency] pmu_estimate (1 channel, 2048 samples, ctypes included): {us:.1f} us per call")
     assert us < 5000
     pmu.deinit()
+
+
+# ---------------------------------------------------------------------------------------
+# consumers of the frame stream (section 8(f)): checked against plain numpy restatements
+# ---------------------------------------------------------------------------------------
+def test_sequence_components_match_numpy():
+    rng = np.random.default_rng(4)
+    n_inst = 1000
+    fr = np.zeros((n_inst, 6, 4))
+    fr[..., 0] = rng.uniform(0.1, 400, (n_inst, 6))
+    fr[..., 1] = rng.uniform(-math.pi, math.pi, (n_inst, 6))
+    fr[0, :3, 0] = 230.0
+    fr[0, :3, 1] = [0.3, 0.3 - 2 * math.pi / 3, 0.3 + 2 * math.pi / 3]          # balanced abc: pure positive sequence
+    got = api.sequence_components(fr)
+    x = (fr[..., 0] * np.exp(1j * fr[..., 1])).reshape(n_inst, 2, 3)
+    a = np.exp(2j * math.pi / 3)
+    want = np.stack([(x[..., 0] + a * x[..., 1] + a * a * x[..., 2]) / 3,
+                     (x[..., 0] + a * a * x[..., 1] + a * x[..., 2]) / 3, x.sum(-1) / 3], axis=-1)
+    assert np.allclose(got[..., 0], np.abs(want), rtol=1e-12, atol=1e-12)
+    big = np.abs(want) > 1e-6
+    d = got[..., 1] - np.angle(want)
+    assert np.max(np.abs((d - 2 * math.pi * np.rint(d / (2 * math.pi)))[big])) < 1e-9
+    assert abs(got[0, 0, 0, 0] - 230.0) < 1e-9 and got[0, 0, 1, 0] < 1e-9 and got[0, 0, 2, 0] < 1e-9
+
+
+def test_c37118_data_frames_match_python_packer():
+    import struct
+
+    def crc_ccitt(data: bytes) -> int:
+        crc = 0xFFFF
+        for byte in data:
+            crc ^= byte << 8
+            for _ in range(8):
+                crc = ((crc << 1) ^ 0x1021) & 0xFFFF if crc & 0x8000 else (crc << 1) & 0xFFFF
+        return crc
+
+    assert crc_ccitt(b"123456789") == 0x29B1                                     # CRC-16/CCITT-FALSE check value
+    rng = np.random.default_rng(8)
+    n_inst, n_ch = 300, 6
+    fr = rng.uniform(-100, 100, (n_inst, n_ch, 4))
+    fr[..., 2] = 50 + rng.uniform(-1, 1, (n_inst, n_ch))
+    soc, fracsec, stat, id0 = 1_700_000_000, (0x0F << 24) | 123456, 0x0000, 7
+    got = api.c37118_pack(fr, idcode0=id0, soc=soc, fracsec=fracsec, stat=stat)
+    size = 26 + 8 * n_ch
+    assert got.shape == (n_inst, size)
+    for i in (0, 1, 150, 299):
+        body = struct.pack(">HHHIIH", 0xAA01, size, (id0 + i) & 0xFFFF, soc, fracsec, stat)
+        for c in range(n_ch):
+            body += struct.pack(">ff", fr[i, c, 0], fr[i, c, 1])
+        body += struct.pack(">ff", fr[i, 0, 2], fr[i, 0, 3])
+        body += struct.pack(">H", crc_ccitt(body))
+        assert bytes(got[i]) == body
