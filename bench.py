@@ -325,6 +325,56 @@ def main():
         single = dict(value=world * n_inst * n_ch / (ms1 * 1e-3), unit=UNIT, ms_per_launch=ms1,
                       note="one frame (%d estimates) per kernel launch" % (n_inst * n_ch))
 
+    # ---------------- frames written straight into rank 0's HBM by the kernel (P2P stores over NVLink,
+    # CUDA IPC buffer): the gather without a collective ------------------------------------------------
+    p2p = None
+    if dist is not None:
+        from synchropmu_b200 import api as _api
+
+        slice_bytes = F * n_inst * n_ch * 4 * itemsize
+        base, handle = (None, None)
+        if rank == 0:
+            base, handle = _api.peer_alloc(world * slice_bytes, local_rank)
+        box = [handle]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            base = _api.peer_open(box[0], local_rank)
+        remote = _api.RawDevicePtr(base + rank * slice_bytes)
+        est.reset()
+        for i in range(3):
+            est.estimate_frames_async(F, win_all[0:F], mid_all[0:F], remote)
+        torch.cuda.synchronize()
+        dist.barrier()
+        n2 = max(10, args.steps // 4)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for i in range(n2):
+            s0 = (i % args.sets) * F
+            est.estimate_frames_async(F, win_all[s0:s0 + F], mid_all[s0:s0 + F], remote)
+        p1.record(stream)
+        torch.cuda.synchronize()
+        tp = torch.tensor([p0.elapsed_time(p1)], device=dev)
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        # one more pass on a known set, into rank 0 and locally, to check that the remote copy is the same data
+        est.reset()
+        est.estimate_frames_async(F, win_all[0:F], mid_all[0:F], remote)
+        est.reset()
+        est.estimate_frames_async(F, win_all[0:F], mid_all[0:F], out)
+        torch.cuda.synchronize()
+        mine = out.double().sum(dim=(0, 1, 2)).cpu()
+        dist.barrier()
+        all_sums = [None] * world
+        dist.all_gather_object(all_sums, mine.tolist())
+        ok = None
+        if rank == 0:
+            got = _api.peer_read(base, (world, F, n_inst, n_ch, 4), npdt).astype(np.float64).sum(axis=(1, 2, 3))
+            ok = bool(np.allclose(got, np.array(all_sums), rtol=1e-12, atol=0))
+        p2p = dict(value=world * n_est_step * n2 / (float(tp.item()) * 1e-3), unit=UNIT, steps=n2, verified=ok,
+                   note="same launches with `frames` pointing into rank 0's HBM (CUDA IPC): frame stores cross NVLink, no collective")
+        dist.barrier()
+        if rank != 0:
+            _api.peer_close(base)
+
     # ---------------- e2e: pinned host buffers through the synchronous C-ABI call ----------------
     e2e = None
     if not args.no_e2e:
@@ -419,6 +469,7 @@ def main():
                 e2e_stream=e2e_stream)
     if gather_ms is not None:
         line["frame_gather_ms"] = gather_ms
+        line["frames_p2p_to_rank0"] = p2p
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -163,6 +163,19 @@ int pmub_c37118_pack(int dtype, const void *frames, void *out, unsigned n_instan
                      unsigned n_channels, unsigned idcode0, unsigned soc, unsigned fracsec,
                      unsigned stat);
 
+/* ---- frames straight into another GPU's memory (optional gather, no collective) ---------
+ * rank 0: pmub_peer_alloc -> device buffer + 64-byte CUDA IPC handle (ship the handle to the other
+ * processes by any means); rank r: pmub_peer_open(handle) -> a pointer valid in r's address space;
+ * pass (that pointer + r's offset) as `frames` to pmub_estimate*: the kernel's frame stores then go
+ * over NVLink / NVSwitch directly into rank 0's HBM.  Close with pmub_peer_close, free on the owner
+ * with pmub_peer_free. */
+#define PMUB_IPC_HANDLE_BYTES 64
+int pmub_peer_alloc(size_t bytes, int device, void **dptr, unsigned char *handle64);
+int pmub_peer_open(const unsigned char *handle64, int device, void **dptr);
+int pmub_peer_close(void *dptr);
+int pmub_peer_read(void *host_dst, const void *dptr, size_t bytes); /* synchronous D2H of (part of) such a buffer */
+int pmub_peer_free(void *dptr);
+
 /* ---- parity / debug observability ------------------------------------------------ */
 /* After pmub_set_debug(b, 1) every estimate also records, per (instance, channel):
  *   flags    int    : bits 0-15 = peak bin km of the first ipDFT, bit 16 = interference

@@ -123,7 +123,13 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.pmub_sequence_components.argtypes = [ip, vp, vp, C.c_uint, C.c_uint]
     lib.pmub_c37118_frame_bytes.argtypes = [C.c_uint]
     lib.pmub_c37118_pack.argtypes = [ip, vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
-    for fn in ("pmub_sequence_components", "pmub_c37118_frame_bytes", "pmub_c37118_pack"):
+    lib.pmub_peer_alloc.argtypes = [C.c_size_t, ip, C.POINTER(vp), vp]
+    lib.pmub_peer_open.argtypes = [vp, ip, C.POINTER(vp)]
+    lib.pmub_peer_close.argtypes = [vp]
+    lib.pmub_peer_read.argtypes = [vp, vp, C.c_size_t]
+    lib.pmub_peer_free.argtypes = [vp]
+    for fn in ("pmub_sequence_components", "pmub_c37118_frame_bytes", "pmub_c37118_pack", "pmub_peer_alloc",
+               "pmub_peer_open", "pmub_peer_close", "pmub_peer_read", "pmub_peer_free"):
         getattr(lib, fn).restype = ip
     for fn in ("pmub_validate", "pmub_parse_ini", "pmub_create", "pmub_create_ini", "pmub_destroy",
                "pmub_get_info", "pmub_estimate", "pmub_estimate_async", "pmub_estimate_frames",
@@ -391,6 +397,51 @@ def c37118_pack(frames, idcode0: int = 1, soc: int = 0, fracsec: int = 0, stat: 
     if lib.pmub_c37118_pack(code, _ptr(frames), out.ctypes.data, n_inst, n_ch, idcode0, soc, fracsec, stat) != 0:
         raise RuntimeError(f"pmub_c37118_pack failed: {last_error(lib)}")
     return out
+
+
+class RawDevicePtr:
+    """A bare device address handed to the C ABI (e.g. a slice of a peer-visible buffer)."""
+
+    def __init__(self, address: int):
+        self.address = int(address)
+
+    def data_ptr(self) -> int:
+        return self.address
+
+
+def peer_alloc(n_bytes: int, device: int = -1, lib=None):
+    """-> (device address, 64-byte IPC handle) of a zeroed buffer other processes can open."""
+    lib = lib or load_library()
+    ptr = C.c_void_p()
+    handle = (C.c_ubyte * 64)()
+    if lib.pmub_peer_alloc(n_bytes, device, C.byref(ptr), handle) != 0:
+        raise RuntimeError(f"pmub_peer_alloc failed: {last_error(lib)}")
+    return int(ptr.value), bytes(handle)
+
+
+def peer_open(handle: bytes, device: int = -1, lib=None) -> int:
+    lib = lib or load_library()
+    ptr = C.c_void_p()
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+    if lib.pmub_peer_open(buf, device, C.byref(ptr)) != 0:
+        raise RuntimeError(f"pmub_peer_open failed: {last_error(lib)}")
+    return int(ptr.value)
+
+
+def peer_read(address: int, shape, dtype, lib=None) -> np.ndarray:
+    """Synchronous copy of (part of) a peer-visible buffer into a new numpy array."""
+    out = np.empty(shape, dtype=dtype)
+    if (lib or load_library()).pmub_peer_read(out.ctypes.data, C.c_void_p(address), out.nbytes) != 0:
+        raise RuntimeError("pmub_peer_read failed")
+    return out
+
+
+def peer_close(address: int, lib=None) -> None:
+    (lib or load_library()).pmub_peer_close(C.c_void_p(address))
+
+
+def peer_free(address: int, lib=None) -> None:
+    (lib or load_library()).pmub_peer_free(C.c_void_p(address))
 
 
 def shard_instances(n_instances: int, rank: int, world_size: int) -> tuple[int, int]:

@@ -184,4 +184,50 @@ int pmub_c37118_pack(int dtype, const void* frames, void* out, unsigned n_instan
     });
 }
 
+// ---- peer-visible frame buffers (multi-GPU gather without a collective) --------------------------------
+// A buffer allocated here on one GPU can be opened by the other ranks' processes (CUDA IPC); passing the
+// opened pointer as `frames` to pmub_estimate* makes the kernel's 128-bit frame stores land directly in
+// the owner's HBM over NVLink - the gather of pmu_frame[] to rank 0 becomes part of the kernel epilogue.
+int pmub_peer_alloc(size_t bytes, int device, void** dptr, unsigned char* handle64)
+{
+    if (!dptr || !handle64 || bytes == 0) { set_error("[pmu_peer] ERROR: bad argument"); return -1; }
+    if (device >= 0) POST_OK(cudaSetDevice(device));
+    POST_OK(cudaMalloc(dptr, bytes));
+    POST_OK(cudaMemset(*dptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    POST_OK(cudaIpcGetMemHandle(&h, *dptr));
+    static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+    memcpy(handle64, &h, sizeof h);
+    return 0;
+}
+
+int pmub_peer_open(const unsigned char* handle64, int device, void** dptr)
+{
+    if (!dptr || !handle64) { set_error("[pmu_peer] ERROR: bad argument"); return -1; }
+    if (device >= 0) POST_OK(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    POST_OK(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int pmub_peer_close(void* dptr)
+{
+    POST_OK(cudaIpcCloseMemHandle(dptr));
+    return 0;
+}
+
+int pmub_peer_read(void* host_dst, const void* dptr, size_t bytes)
+{
+    POST_OK(cudaDeviceSynchronize());
+    POST_OK(cudaMemcpy(host_dst, dptr, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int pmub_peer_free(void* dptr)
+{
+    POST_OK(cudaFree(dptr));
+    return 0;
+}
+
 }  // extern "C"

@@ -560,3 +560,27 @@ def test_c37118_data_frames_match_python_packer():
         body += struct.pack(">ff", fr[i, 0, 2], fr[i, 0, 3])
         body += struct.pack(">H", crc_ccitt(body))
         assert bytes(got[i]) == body
+
+
+def test_frames_land_in_another_process_buffer():
+    """The optional gather without a collective: a second process opens this process's CUDA-IPC buffer and its
+    kernel writes the frames directly there (on a multi-GPU box the same stores cross NVLink)."""
+    import subprocess
+    import sys
+
+    cfg = configs.DEFAULT_INI
+    n_inst = 50
+    nbytes = n_inst * 6 * 4 * 8
+    base, handle = api.peer_alloc(2 * nbytes, 0)
+    try:
+        r = subprocess.run([sys.executable, str(GOLD.parent / "peer_child.py"), handle.hex(), str(nbytes), str(n_inst)],
+                           capture_output=True, text=True, timeout=240)
+        assert r.returncode == 0, r.stderr[-2000:]
+        prm = signals.three_phase_params(n_inst, seed=12)
+        x = signals.steady(cfg, 0, prm["amp"], prm["freq"], prm["phase"], ramp=prm["ramp"]).reshape(n_inst, 6, -1)
+        with BatchEstimator(cfg, n_inst, 6) as est:
+            want = est.estimate(x, np.zeros(n_inst))
+        got = api.peer_read(base, (2, n_inst, 6, 4), np.float64)
+        assert np.array_equal(got[1], want) and not got[0].any()
+    finally:
+        api.peer_free(base)
