@@ -52,9 +52,11 @@ struct pmub_batch {
     long long ring_wpos;        // next write position
     int hop, stream_max_frames;
     unsigned long long stream_origin, stream_pushed;  // absolute index of sample 0; samples pushed so far
-    unsigned char* d_push;      // staging for device-side mid / host mid of a push (lazy)
+    unsigned char* d_push;      // staging of a push's new samples when they are scattered by a kernel (lazy)
+    size_t d_push_cap;
     int* d_dbg;
     double* d_spec;
+    unsigned long long* d_timeline;   // profiling aid (pmub_debug_timeline)
     bool debug, mirror;
     // small-batch pinned staging
     unsigned char* h_in;
@@ -120,6 +122,7 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     a.dbg = b->debug ? b->d_dbg + w0 : nullptr;
     a.spec_out = b->debug ? b->d_spec + (size_t)w0 * b->cfg.n_bins * 2 : nullptr;
     a.state_export = d_export_base ? d_export_base + (size_t)w0 * 4 : nullptr;
+    a.timeline = b->d_timeline;
     // TMA bulk copies need 16-byte aligned sources; otherwise per-element cp.async
     bool ok16 = b->plan.aligned16 && (((uintptr_t)a.windows) % 16 == 0);
     if (ring) ok16 = ok16 && ((size_t)b->ring_cap * sz) % 16 == 0 && ((size_t)b->hop * sz) % 16 == 0;
@@ -183,6 +186,26 @@ static int ensure_cap(unsigned char** p, size_t* cap, size_t need)
     return 0;
 }
 
+// Ingest of the streaming front end when the per-stream block is too narrow for an efficient 2-D DMA:
+// the new samples arrive as one contiguous copy and this kernel scatters them into the rings.
+//   src [n_frames][n_streams][hop] -> ring[w][(wpos + f*hop + j) mod cap]   (elements of `esz` bytes)
+template <typename T>
+__global__ void ring_scatter_kernel(T* __restrict__ ring, const T* __restrict__ src, long long n_streams, long long w0,
+                                    long long w1, int n_frames, int hop, long long cap, long long wpos)
+{
+    const long long per_frame = (w1 - w0) * hop;
+    const long long total = per_frame * n_frames;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i / per_frame);
+        const long long r = i - (long long)f * per_frame;
+        const long long w = w0 + r / hop;
+        const int j = (int)(r % hop);
+        long long p = wpos + (long long)f * hop + j;
+        p %= cap;
+        ring[w * cap + p] = src[((long long)f * n_streams + w) * hop + j];
+    }
+}
+
 static bool is_device_ptr(const void* p)
 {
     cudaPointerAttributes at;
@@ -205,8 +228,8 @@ static int free_batch(pmub_batch* b)
     cudaSetDevice(b->device);
     cudaFree(b->dU); cudaFree(b->dV); cudaFree(b->dT);
     cudaFree(b->st_fold); cudaFree(b->st_dl0); cudaFree(b->st_dl1); cudaFree(b->st_state);
-    cudaFree(b->d_windows); cudaFree(b->d_mid); cudaFree(b->d_out); cudaFree(b->d_frames); cudaFree(b->d_ring);
-    cudaFree(b->d_dbg); cudaFree(b->d_spec);
+    cudaFree(b->d_windows); cudaFree(b->d_mid); cudaFree(b->d_out); cudaFree(b->d_frames); cudaFree(b->d_ring); cudaFree(b->d_push);
+    cudaFree(b->d_dbg); cudaFree(b->d_spec); cudaFree(b->d_timeline);
     if (b->h_in) cudaFreeHost(b->h_in);
     if (b->h_out) cudaFreeHost(b->h_out);
     for (int i = 0; i < 2; ++i)
@@ -526,6 +549,7 @@ int pmub_stream_push(pmub_batch* b, int n_frames, const void* new_samples, const
     const bool in_dev = is_device_ptr(new_samples), mid_dev = mid ? is_device_ptr(mid) : true, fr_dev = is_device_ptr(frames);
     if (mid && !mid_dev && ensure_cap(&b->d_mid, &b->d_mid_cap, mid_bytes * n_frames)) return -1;
     if (!fr_dev && ensure_cap(&b->d_frames, &b->d_frames_cap, fr_bytes * n_frames)) return -1;
+    if (!in_dev && (size_t)hop * sz < 2048 && ensure_cap(&b->d_push, &b->d_push_cap, n * (size_t)hop * sz * n_frames)) return -1;
     const unsigned char* dM = mid ? (mid_dev ? (const unsigned char*)mid : b->d_mid) : nullptr;
     unsigned char* dF = fr_dev ? (unsigned char*)frames : b->d_frames;
     RingSrc ring;
@@ -551,11 +575,34 @@ int pmub_stream_push(pmub_batch* b, int n_frames, const void* new_samples, const
         const long long i0 = (long long)b->n_inst * c / n_chunks, i1 = (long long)b->n_inst * (c + 1) / n_chunks;
         const long long w0 = i0 * b->C, w1 = i1 * b->C;
         // ingest: frame f's hop samples of every stream go to ring position (wpos + f*hop) mod cap
-        for (int f = 0; f < n_frames; ++f) {
-            const long long p = (b->ring_wpos + (long long)f * hop) % cap;
-            CUDA_OK(cudaMemcpy2DAsync(b->d_ring + ((size_t)w0 * (size_t)cap + (size_t)p) * sz, (size_t)cap * sz,
-                                      (const unsigned char*)new_samples + ((size_t)f * n + (size_t)w0) * (size_t)hop * sz, (size_t)hop * sz,
-                                      (size_t)hop * sz, (size_t)(w1 - w0), cudaMemcpyDefault, s));
+        if ((size_t)hop * sz >= 2048) {
+            // wide rows: 2-D DMA straight from the caller's buffer into the rings
+            for (int f = 0; f < n_frames; ++f) {
+                const long long p = (b->ring_wpos + (long long)f * hop) % cap;
+                CUDA_OK(cudaMemcpy2DAsync(b->d_ring + ((size_t)w0 * (size_t)cap + (size_t)p) * sz, (size_t)cap * sz,
+                                          (const unsigned char*)new_samples + ((size_t)f * n + (size_t)w0) * (size_t)hop * sz,
+                                          (size_t)hop * sz, (size_t)hop * sz, (size_t)(w1 - w0), cudaMemcpyDefault, s));
+            }
+        } else {
+            // narrow rows: contiguous copies into a staging area (host input), then a scatter kernel
+            const unsigned char* src = (const unsigned char*)new_samples;
+            if (!in_dev) {
+                for (int f = 0; f < n_frames; ++f)
+                    CUDA_OK(cudaMemcpyAsync(b->d_push + ((size_t)f * n + (size_t)w0) * (size_t)hop * sz,
+                                            (const unsigned char*)new_samples + ((size_t)f * n + (size_t)w0) * (size_t)hop * sz,
+                                            (size_t)(w1 - w0) * (size_t)hop * sz, cudaMemcpyHostToDevice, s));
+                src = b->d_push;
+            }
+            const long long total = (w1 - w0) * hop * n_frames;
+            int blocks = (int)((total + 255) / 256);
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            if (sz == 8)
+                ring_scatter_kernel<double><<<blocks, 256, 0, s>>>((double*)b->d_ring, (const double*)src, (long long)n, w0, w1, n_frames,
+                                                                    (int)hop, cap, b->ring_wpos);
+            else
+                ring_scatter_kernel<float><<<blocks, 256, 0, s>>>((float*)b->d_ring, (const float*)src, (long long)n, w0, w1, n_frames,
+                                                                   (int)hop, cap, b->ring_wpos);
+            CUDA_OK(cudaGetLastError());
         }
         if (launch_frames(b, w0, w1, n_frames, nullptr, dM, dF, nullptr, s, &ring)) return -1;
         if (!fr_dev)
@@ -616,6 +663,29 @@ int pmub_get_debug(pmub_batch* b, int* flags, double* spectrum)
     const size_t n = (size_t)b->n_windows;
     if (flags) CUDA_OK(cudaMemcpy(flags, b->d_dbg, n * sizeof(int), cudaMemcpyDeviceToHost));
     if (spectrum) CUDA_OK(cudaMemcpy(spectrum, b->d_spec, n * b->cfg.n_bins * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+/* Profiling aid: with enable != 0 every following launch records, per CTA and warp, four globaltimer stamps (ns):
+ * consumer set-up done, first window available, tickets exhausted, warp exit.  pmub_debug_timeline copies the
+ * stamps of the LAST launch to `out` ([n_ctas][warps][4]) and returns the number of CTAs x warps via the pointers. */
+int pmub_debug_timeline(pmub_batch* b, int enable, unsigned long long* out, int* n_ctas, int* n_warps)
+{
+    if (!b) return -1;
+    CUDA_OK(cudaSetDevice(b->device));
+    if (pmub_sync(b)) return -1;
+    const int warps = PMU_BLOCK_THREADS / PMU_WARP;
+    const size_t bytes = (size_t)b->num_sms * warps * 4 * sizeof(unsigned long long);
+    if (out && b->d_timeline) CUDA_OK(cudaMemcpy(out, b->d_timeline, bytes, cudaMemcpyDeviceToHost));
+    if (n_ctas) *n_ctas = b->num_sms;
+    if (n_warps) *n_warps = warps;
+    if (enable && !b->d_timeline) {
+        CUDA_OK(cudaMalloc(&b->d_timeline, bytes));
+        CUDA_OK(cudaMemset(b->d_timeline, 0, bytes));
+    } else if (!enable && b->d_timeline) {
+        cudaFree(b->d_timeline);
+        b->d_timeline = nullptr;
+    }
     return 0;
 }
 

@@ -21,6 +21,17 @@
 
 #include "pmu_math.cuh"
 
+// ---- compute type of the DFT stage -----------------------------------------------
+// double for the float_p = double build.  The float build may run the DFT stage in FP32 (inputs are
+// floats, the reference's float build rounds every intermediate to float anyway); everything after
+// the lane reduction stays in double.
+struct pmu_cf {
+    float x, y;
+};
+template <typename R> struct CplxOf;
+template <> struct CplxOf<double> { typedef pmu_c type; };
+template <> struct CplxOf<float> { typedef pmu_cf type; };
+
 // ---- compile-time loop ---------------------------------------------------------
 template <int I>
 struct IC {
@@ -59,28 +70,32 @@ PMU_HD constexpr double sin16(int k) { return cos16(k - 4); }
 #if defined(__CUDACC__)
 static __constant__ double pmu_tw16[3] = {0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173};
 #endif
-template <int K16>
-PMU_HD double cosv16()
+template <int K16, typename R = double>
+PMU_HD R cosv16()
 {
     constexpr int k = K16 & 15;
 #if defined(__CUDA_ARCH__)
-    if constexpr (k == 1 || k == 15) return pmu_tw16[0];
-    else if constexpr (k == 2 || k == 14) return pmu_tw16[1];
-    else if constexpr (k == 3 || k == 13) return pmu_tw16[2];
-    else if constexpr (k == 5 || k == 11) return -pmu_tw16[2];
-    else if constexpr (k == 6 || k == 10) return -pmu_tw16[1];
-    else if constexpr (k == 7 || k == 9) return -pmu_tw16[0];
-    else return cos16(k);
+    if constexpr (sizeof(R) == 8) {
+        if constexpr (k == 1 || k == 15) return pmu_tw16[0];
+        else if constexpr (k == 2 || k == 14) return pmu_tw16[1];
+        else if constexpr (k == 3 || k == 13) return pmu_tw16[2];
+        else if constexpr (k == 5 || k == 11) return -pmu_tw16[2];
+        else if constexpr (k == 6 || k == 10) return -pmu_tw16[1];
+        else if constexpr (k == 7 || k == 9) return -pmu_tw16[0];
+        else return cos16(k);
+    } else {
+        return (R)cos16(k);   // 32-bit literals are instruction immediates
+    }
 #else
-    return cos16(k);
+    return (R)cos16(k);
 #endif
 }
-template <int K16>
-PMU_HD double sinv16() { return cosv16<K16 - 4>(); }
+template <int K16, typename R = double>
+PMU_HD R sinv16() { return cosv16<K16 - 4, R>(); }
 
 // (tr, ti) = W_M^K * (orr, oi),  W_M = exp(-2 pi i / M), M | 16; trivial twiddles cost nothing.
-template <int K, int M>
-PMU_HD void tw_mul(double orr, double oi, double* tr, double* ti)
+template <int K, int M, typename R>
+PMU_HD void tw_mul(R orr, R oi, R* tr, R* ti)
 {
     constexpr int k16 = (K * (16 / M)) & 15;
     if constexpr (k16 == 0) { *tr = orr; *ti = oi; }
@@ -88,7 +103,7 @@ PMU_HD void tw_mul(double orr, double oi, double* tr, double* ti)
     else if constexpr (k16 == 8) { *tr = -orr; *ti = -oi; }       // -1
     else if constexpr (k16 == 12) { *tr = -oi; *ti = orr; }       // +i
     else {
-        const double wr = cosv16<k16>(), wi = -sinv16<k16>();
+        const R wr = cosv16<k16, R>(), wi = -sinv16<k16, R>();
         *tr = wr * orr - wi * oi;
         *ti = wr * oi + wi * orr;
     }
@@ -96,46 +111,46 @@ PMU_HD void tw_mul(double orr, double oi, double* tr, double* ti)
 
 // Real-input FFT codelet: x[0..M) -> bins 0..M/2 (re[], im[]).  Radix-2 decimation in
 // time on real data, conjugate symmetry of the half-size transforms used throughout.
-template <int M>
+template <int M, typename R = double>
 struct RFFT {
     static_assert(M == 1 || M == 2 || M == 4 || M == 8 || M == 16, "codelet sizes");
-    PMU_HD static void run(const double* x, double* re, double* im)
+    PMU_HD static void run(const R* x, R* re, R* im)
     {
         if constexpr (M == 1) {
-            re[0] = x[0]; im[0] = 0.0;
+            re[0] = x[0]; im[0] = 0;
         } else if constexpr (M == 2) {
-            re[0] = x[0] + x[1]; im[0] = 0.0;
-            re[1] = x[0] - x[1]; im[1] = 0.0;
+            re[0] = x[0] + x[1]; im[0] = 0;
+            re[1] = x[0] - x[1]; im[1] = 0;
         } else {
             constexpr int H = M / 2;
-            double ev[H], od[H];
+            R ev[H], od[H];
             static_for<0, H>([&](auto i) {
                 ev[i.value] = x[2 * i.value];
                 od[i.value] = x[2 * i.value + 1];
             });
-            double er[H / 2 + 1], ei[H / 2 + 1], qr[H / 2 + 1], qi[H / 2 + 1];
-            RFFT<H>::run(ev, er, ei);
-            RFFT<H>::run(od, qr, qi);
+            R er[H / 2 + 1], ei[H / 2 + 1], qr[H / 2 + 1], qi[H / 2 + 1];
+            RFFT<H, R>::run(ev, er, ei);
+            RFFT<H, R>::run(od, qr, qi);
             static_for<0, H + 1>([&](auto kc) {
                 constexpr int k = kc.value;
                 constexpr int kk = (k <= H / 2) ? k : H - k;
                 constexpr bool cj = (k > H / 2);
                 // E[0], E[H/2], O[0], O[H/2] are real by symmetry: drop their zero parts
                 constexpr bool real_in = (kk == 0) || (2 * kk == H);
-                double Er = er[kk], Ei = real_in ? 0.0 : (cj ? -ei[kk] : ei[kk]);
-                double Or = qr[kk], Oi = real_in ? 0.0 : (cj ? -qi[kk] : qi[kk]);
+                R Er = er[kk], Ei = real_in ? (R)0 : (cj ? -ei[kk] : ei[kk]);
+                R Or = qr[kk], Oi = real_in ? (R)0 : (cj ? -qi[kk] : qi[kk]);
                 if constexpr (real_in) {
                     constexpr int k16 = (k * (16 / M)) & 15;
-                    if constexpr (k16 == 0) { re[k] = Er + Or; im[k] = 0.0; }
-                    else if constexpr (k16 == 8) { re[k] = Er - Or; im[k] = 0.0; }
+                    if constexpr (k16 == 0) { re[k] = Er + Or; im[k] = 0; }
+                    else if constexpr (k16 == 8) { re[k] = Er - Or; im[k] = 0; }
                     else if constexpr (k16 == 4) { re[k] = Er; im[k] = -Or; }
                     else {
-                        const double wr = cosv16<k16>(), wi = -sinv16<k16>();
+                        const R wr = cosv16<k16, R>(), wi = -sinv16<k16, R>();
                         re[k] = Er + wr * Or; im[k] = wi * Or;
                     }
                 } else {
-                    double tr, ti;
-                    tw_mul<k, M>(Or, Oi, &tr, &ti);
+                    R tr, ti;
+                    tw_mul<k, M, R>(Or, Oi, &tr, &ti);
                     re[k] = Er + tr; im[k] = Ei + ti;
                 }
             });
@@ -144,8 +159,8 @@ struct RFFT {
 };
 
 // Bin k (compile-time) of the M-periodic, conjugate-symmetric codelet output.
-template <int K, int M>
-PMU_HD void ysel(const double* re, const double* im, double* yr, double* yi, bool* is_real)
+template <int K, int M, typename R>
+PMU_HD void ysel(const R* re, const R* im, R* yr, R* yi, bool* is_real)
 {
     constexpr int r = K % M;
     constexpr int idx = (r <= M / 2) ? r : M - r;
@@ -158,25 +173,25 @@ PMU_HD void ysel(const double* re, const double* im, double* yr, double* yi, boo
 // Accumulate one residue: acc[k] (+)= U[k] * Y[k mod M], k < KC.
 //   FIRST : U == 1 for every k (i == 0), acc is initialised instead of accumulated.
 //   u     : lane-uniform twiddles W_N^{32 i k} (broadcast loads), ignored when FIRST.
-template <int M, int KC, bool FIRST>
-PMU_HD void accumulate_residue(const double* x, const pmu_c* u, double* ar, double* ai)
+template <int M, int KC, bool FIRST, typename R>
+PMU_HD void accumulate_residue(const R* x, const typename CplxOf<R>::type* u, R* ar, R* ai)
 {
-    double re[M / 2 + 1], im[M / 2 + 1];
-    RFFT<M>::run(x, re, im);
+    R re[M / 2 + 1], im[M / 2 + 1];
+    RFFT<M, R>::run(x, re, im);
     static_for<0, KC>([&](auto kc) {
         constexpr int k = kc.value;
-        double yr, yi;
+        R yr, yi;
         bool rl;
-        ysel<k, M>(re, im, &yr, &yi, &rl);
+        ysel<k, M, R>(re, im, &yr, &yi, &rl);
         constexpr int r = k % M;
         constexpr bool is_real = (r == 0) || (2 * r == M) || (M == 1);
         if constexpr (FIRST) {
             ar[k] = yr;
-            ai[k] = is_real ? 0.0 : yi;
+            ai[k] = is_real ? (R)0 : yi;
         } else if constexpr (k == 0) {
             ar[0] += yr;  // W^0 = 1, Y[0] real
         } else {
-            pmu_c w = u[k];
+            const typename CplxOf<R>::type w = u[k];
             if constexpr (is_real) {
                 ar[k] += w.x * yr;
                 ai[k] += w.y * yr;
@@ -189,14 +204,14 @@ PMU_HD void accumulate_residue(const double* x, const pmu_c* u, double* ar, doub
 }
 
 // Rotate the lane's partial spectrum by its own twiddle V[k] = W_N^{lane k}.
-template <int KC>
-PMU_HD void rotate_lane(const pmu_c* v, int v_stride, double* ar, double* ai)
+template <int KC, typename R>
+PMU_HD void rotate_lane(const typename CplxOf<R>::type* v, int v_stride, R* ar, R* ai)
 {
     static_for<1, KC>([&](auto kc) {
         constexpr int k = kc.value;
-        pmu_c w = v[k * v_stride];
-        double r = ar[k] * w.x - ai[k] * w.y;
-        double i = ar[k] * w.y + ai[k] * w.x;
+        const typename CplxOf<R>::type w = v[k * v_stride];
+        R r = ar[k] * w.x - ai[k] * w.y;
+        R i = ar[k] * w.y + ai[k] * w.x;
         ar[k] = r;
         ai[k] = i;
     });

@@ -79,6 +79,9 @@ struct KernelArgs {
     int* dbg;                    // [n_frames][frame_stride]  km | flags
     double* spec_out;            // [n_frames][frame_stride][K][2] Hann-windowed bins
     double* state_export;        // [frame_stride][4]  f_old, dl0, dl1, state after the last frame
+    // profiling aid: [gridDim.x][warps][4] globaltimer stamps (setup done, first window ready,
+    // tickets exhausted, warp exit); null in normal operation
+    unsigned long long* timeline;
 };
 
 struct CtrlBlock {
@@ -161,6 +164,12 @@ __device__ __forceinline__ void cp_async_elem(void* dst, const void* src)
 __device__ __forceinline__ void cp_async_mbar_arrive(void* bar)
 {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ int ld_volatile_s32(const int* p)
 {
@@ -298,19 +307,19 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, int po
 
 // Load the M samples of one residue from a stage (row pitch in elements).  FULL: every lane of
 // the group is a valid residue, no masking.
-template <typename InT, int M, bool FULL>
-__device__ __forceinline__ void load_residue(const InT* xs, int pitch, int a_loc, int w_s, double* x)
+template <typename InT, typename CT, int M, bool FULL>
+__device__ __forceinline__ void load_residue(const InT* xs, int pitch, int a_loc, int w_s, CT* x)
 {
     if constexpr (FULL) {
 #pragma unroll
-        for (int b = 0; b < M; ++b) x[b] = (double)xs[b * pitch + a_loc];
+        for (int b = 0; b < M; ++b) x[b] = (CT)xs[b * pitch + a_loc];
     } else {
         const bool valid = a_loc < w_s;
         const int a_c = valid ? a_loc : 0;
 #pragma unroll
         for (int b = 0; b < M; ++b) {
-            double v = (double)xs[b * pitch + a_c];
-            x[b] = valid ? v : 0.0;
+            CT v = (CT)xs[b * pitch + a_c];
+            x[b] = valid ? v : (CT)0;
         }
     }
 }
@@ -318,13 +327,16 @@ __device__ __forceinline__ void load_residue(const InT* xs, int pitch, int a_loc
 // ---- the kernel ----------------------------------------------------------------------
 // PITCH > 0: stage rows are PITCH elements apart (compile-time: the sample loads need no address
 // arithmetic); PITCH == 0: row pitch = a.W at run time.
-template <typename InT, int M, int KC, int PITCH>
+// CT: arithmetic type of the DFT stage (double; float for the float_p = float build) - everything from
+// the lane reduction on is double.
+template <typename InT, typename CT, int M, int KC, int PITCH>
 __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const __grid_constant__ KernelArgs a)
 {
+    typedef typename CplxOf<CT>::type ccplx;
     unsigned char* smem = pmu_smem;
     CtrlBlock* ctrl = reinterpret_cast<CtrlBlock*>(smem + a.off_ctrl);
-    pmu_c* sU = reinterpret_cast<pmu_c*>(smem + a.off_U);
-    pmu_c* sV = reinterpret_cast<pmu_c*>(smem + a.off_V);
+    ccplx* sU = reinterpret_cast<ccplx*>(smem + a.off_U);
+    ccplx* sV = reinterpret_cast<ccplx*>(smem + a.off_V);
     pmu_c* sT = reinterpret_cast<pmu_c*>(smem + a.off_trig);
     unsigned char* stages = smem + a.off_stage;
 
@@ -355,8 +367,16 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         mbar_fence_init();
     }
     for (int i = tid; i < PMU_MAX_GROUPS; i += nthreads) ctrl->grp_done[i] = 0;
-    for (int i = tid; i < a.n_u; i += nthreads) sU[i] = a.U[i];
-    for (int i = tid; i < KC * PMU_WARP; i += nthreads) sV[i] = a.V[i];
+    for (int i = tid; i < a.n_u; i += nthreads) {
+        const pmu_c w = a.U[i];
+        ccplx c; c.x = (CT)w.x; c.y = (CT)w.y;
+        sU[i] = c;
+    }
+    for (int i = tid; i < KC * PMU_WARP; i += nthreads) {
+        const pmu_c w = a.V[i];
+        ccplx c; c.x = (CT)w.x; c.y = (CT)w.y;
+        sV[i] = c;
+    }
     for (int i = tid; i < a.post.jlo + a.post.jhi + 1; i += nthreads) sT[i] = a.trig[i];
     __syncthreads();
     if (n_local <= 0) return;
@@ -436,6 +456,8 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     if (warp > a.n_cons) return;
 
     // ================= CONSUMERS =================
+    unsigned long long* tl = a.timeline ? a.timeline + ((size_t)blockIdx.x * (PMU_BLOCK_THREADS / PMU_WARP) + warp) * 4 : nullptr;
+    if (tl && lane == 0) { tl[0] = global_ns(); tl[1] = 0; }
     BatchMap bm;
     bm.init(n_local);
     FastDiv by_nlocal, by_nstage;
@@ -448,7 +470,10 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         int item = 0;
         if (lane == 0) item = atomicAdd(&ctrl->ticket, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= n_items) break;
+        if (item >= n_items) {
+            if (tl && lane == 0) tl[2] = global_ns();
+            break;
+        }
         int f = 0, t = item;
         if (a.n_frames > 1) {
             unsigned r;
@@ -457,9 +482,9 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         }
 
         // ---- pruned rectangular DFT of stream t, frame f ----
-        double acc[2 * KC];  // ar = acc[0..KC), ai = acc[KC..2KC)
-        double* ar = acc;
-        double* ai = acc + KC;
+        CT acc[2 * KC];  // ar = acc[0..KC), ai = acc[KC..2KC)
+        CT* ar = acc;
+        CT* ai = acc + KC;
         bool first = true;
         for (int sl = 0; sl < a.nslab; ++sl) {
             const int idx = item * a.nslab + sl;
@@ -472,6 +497,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 while (ld_volatile_s32(&ctrl->stage_seq[st]) != use) __nanosleep(32);
             __syncwarp();
             mbar_wait(&ctrl->full[st], (uint32_t)(use & 1));
+            if (tl && lane == 0 && tl[1] == 0) tl[1] = global_ns();
             const InT* xs = reinterpret_cast<const InT*>(stages + (size_t)st * a.stage_bytes);
             const int a_lo = sl * a.W;
             const int w_s = min(a.W, a.L - a_lo);
@@ -479,15 +505,15 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             const bool all_full = (w_s % PMU_WARP) == 0;
             for (int ii = 0; ii < n_it; ++ii) {
                 const int a_loc = lane + PMU_WARP * ii;
-                double x[M];
-                if (all_full) load_residue<InT, M, true>(xs, pitch, a_loc, w_s, x);
-                else load_residue<InT, M, false>(xs, pitch, a_loc, w_s, x);
-                const pmu_c* u = sU + (size_t)(sl * w_per_it + ii) * KC;
+                CT x[M];
+                if (all_full) load_residue<InT, CT, M, true>(xs, pitch, a_loc, w_s, x);
+                else load_residue<InT, CT, M, false>(xs, pitch, a_loc, w_s, x);
+                const ccplx* u = sU + (size_t)(sl * w_per_it + ii) * KC;
                 if (first) {
-                    accumulate_residue<M, KC, true>(x, u, ar, ai);
+                    accumulate_residue<M, KC, true, CT>(x, u, ar, ai);
                     first = false;
                 } else {
-                    accumulate_residue<M, KC, false>(x, u, ar, ai);
+                    accumulate_residue<M, KC, false, CT>(x, u, ar, ai);
                 }
             }
             __syncwarp();
@@ -496,18 +522,21 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 mbar_arrive(&ctrl->empty[st]);
             }
         }
-        rotate_lane<KC>(sV + lane, PMU_WARP, ar, ai);
+        rotate_lane<KC, CT>(sV + lane, PMU_WARP, ar, ai);
 
         // ---- sum the 32 lane partials through shared memory: every lane drops its KC complex
         //      partials into its row of the warp's scratch (128-bit stores, conflict-free row
         //      stride), then lane c adds up column c of the 32 rows and deposits the total ----
-        constexpr int RS = 2 * KC + 2;  // row stride in doubles: an odd number of 16-byte units
-        double* red = reinterpret_cast<double*>(smem + a.off_red) + (size_t)(warp - 1) * PMU_WARP * RS;
+        constexpr int RS = 2 * KC + 2;  // row stride in CT elements: an odd number of complex slots
+        CT* red = reinterpret_cast<CT*>(smem + a.off_red) + (size_t)(warp - 1) * PMU_WARP * RS;
         {
-            double2* my = reinterpret_cast<double2*>(red + (size_t)lane * RS);
+            ccplx* my = reinterpret_cast<ccplx*>(red + (size_t)lane * RS);
 #pragma unroll
             for (int k = 0; k < KC; ++k)
-                if (k < a.Kp) my[k] = make_double2(ar[k], ai[k]);
+                if (k < a.Kp) {
+                    ccplx c; c.x = ar[k]; c.y = ai[k];
+                    my[k] = c;
+                }
         }
         int g, slot, bsz, first_t;
         bm.locate(t, &g, &slot, &bsz, &first_t);
@@ -520,14 +549,14 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         __threadfence_block();
         double* row = reinterpret_cast<double*>(smem + a.off_raw) + ((size_t)rb * PMU_WARP + slot) * a.raw_stride;
         for (int c = lane; c < 2 * a.Kp; c += PMU_WARP) {
-            const double* col = red + c;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            const CT* col = red + c;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;   // the column sums are always double
 #pragma unroll
             for (int l = 0; l < PMU_WARP; l += 4) {
-                s0 += col[(l + 0) * RS];
-                s1 += col[(l + 1) * RS];
-                s2 += col[(l + 2) * RS];
-                s3 += col[(l + 3) * RS];
+                s0 += (double)col[(l + 0) * RS];
+                s1 += (double)col[(l + 1) * RS];
+                s2 += (double)col[(l + 2) * RS];
+                s3 += (double)col[(l + 3) * RS];
             }
             row[c] = (s0 + s1) + (s2 + s3);
         }
@@ -563,6 +592,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             }
         }
     }
+    if (tl && lane == 0) tl[3] = global_ns();
 }
 
 #endif  // __CUDACC__

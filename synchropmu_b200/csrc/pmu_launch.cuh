@@ -1,4 +1,4 @@
-// pmu_launch.cuh — instantiates pmu_fused_kernel for one float_p width (PMU_LAUNCH_T) and
+// pmu_launch.cuh — instantiates pmu_fused_kernel for one float_p width (DFT arithmetic in that width) and
 // every (codelet size M, bins per lane KC) specialisation, and dispatches at run time.
 // Included by pmu_kernels_f64.cu / pmu_kernels_f32.cu so the two widths compile in parallel.
 #pragma once
@@ -18,11 +18,11 @@ int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess && (dev < 0 || dev >= 64 || configured[dev] != smem)) {
-        e = cudaFuncSetAttribute(pmu_fused_kernel<T, M, KC, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(pmu_fused_kernel<T, T, M, KC, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev] = smem;
     }
     if (e == cudaSuccess) {
-        pmu_fused_kernel<T, M, KC, PITCH><<<grid, block, smem, s>>>(a);
+        pmu_fused_kernel<T, T, M, KC, PITCH><<<grid, block, smem, s>>>(a);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) {

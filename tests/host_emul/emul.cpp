@@ -11,15 +11,21 @@
 
 #include "../../synchropmu_b200/csrc/pmu_host.hpp"
 
-template <typename InT, int M, int KC>
-static void window_bins(const pmu::Plan& p, const std::vector<pmu_c>& U, const std::vector<pmu_c>& V,
-                        const InT* x, double* raw /* 2*KC */)
+static int g_fp32_dft = 1;   // the float build runs its DFT stage in FP32 (like the kernel)
+
+template <typename InT, int M, int KC, typename R>
+static void window_bins_r(const pmu::Plan& p, const std::vector<pmu_c>& Ud, const std::vector<pmu_c>& Vd,
+                          const InT* x, double* raw /* 2*KC */)
 {
+    typedef typename CplxOf<R>::type cplx;
+    std::vector<cplx> U(Ud.size()), V(Vd.size());
+    for (size_t i = 0; i < Ud.size(); ++i) { U[i].x = (R)Ud[i].x; U[i].y = (R)Ud[i].y; }
+    for (size_t i = 0; i < Vd.size(); ++i) { V[i].x = (R)Vd[i].x; V[i].y = (R)Vd[i].y; }
     double sum_r[KC], sum_i[KC];
     for (int k = 0; k < KC; ++k) sum_r[k] = sum_i[k] = 0.0;
     const int w_per_it = p.W / 32;
     for (int lane = 0; lane < 32; ++lane) {
-        double ar[KC], ai[KC];
+        R ar[KC], ai[KC];
         bool first = true;
         for (int sl = 0; sl < p.nslab; ++sl) {
             const int a_lo = sl * p.W;
@@ -28,17 +34,24 @@ static void window_bins(const pmu::Plan& p, const std::vector<pmu_c>& U, const s
             for (int ii = 0; ii < n_it; ++ii) {
                 const int a_loc = lane + 32 * ii;
                 const bool valid = a_loc < w_s;
-                double xv[M];
-                for (int b = 0; b < M; ++b) xv[b] = valid ? (double)x[(size_t)(a_lo + a_loc) + (size_t)p.L * b] : 0.0;
-                const pmu_c* u = U.data() + (size_t)(sl * w_per_it + ii) * KC;
-                if (first) { accumulate_residue<M, KC, true>(xv, u, ar, ai); first = false; }
-                else accumulate_residue<M, KC, false>(xv, u, ar, ai);
+                R xv[M];
+                for (int b = 0; b < M; ++b) xv[b] = valid ? (R)x[(size_t)(a_lo + a_loc) + (size_t)p.L * b] : (R)0;
+                const cplx* u = U.data() + (size_t)(sl * w_per_it + ii) * KC;
+                if (first) { accumulate_residue<M, KC, true, R>(xv, u, ar, ai); first = false; }
+                else accumulate_residue<M, KC, false, R>(xv, u, ar, ai);
             }
         }
-        rotate_lane<KC>(V.data() + lane, 32, ar, ai);
-        for (int k = 0; k < KC; ++k) { sum_r[k] += ar[k]; sum_i[k] += ai[k]; }
+        rotate_lane<KC, R>(V.data() + lane, 32, ar, ai);
+        for (int k = 0; k < KC; ++k) { sum_r[k] += (double)ar[k]; sum_i[k] += (double)ai[k]; }   // column sums in double
     }
     for (int k = 0; k < KC; ++k) { raw[2 * k] = sum_r[k]; raw[2 * k + 1] = sum_i[k]; }
+}
+
+template <typename InT, int M, int KC>
+static void window_bins(const pmu::Plan& p, const std::vector<pmu_c>& U, const std::vector<pmu_c>& V, const InT* x, double* raw)
+{
+    if (g_fp32_dft && sizeof(InT) == 4) window_bins_r<InT, M, KC, float>(p, U, V, x, raw);
+    else window_bins_r<InT, M, KC, double>(p, U, V, x, raw);
 }
 
 template <typename InT, int M>
@@ -118,6 +131,7 @@ int emul_run(const pmub_config* cfg, int dtype, int n_channels, long n_streams, 
     return 0;
 }
 
+void emul_set_fp32_dft(int on) { g_fp32_dft = on; }
 int emul_parse_ini(const char* path, pmub_config* out) { return pmu::parse_ini(path, out); }
 int emul_validate(const pmub_config* c) { return pmu::validate(*c); }
 
