@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== pytest" ; timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+echo "== tune" ; timeout 600 python tools/tune.py --tag v8 > gpurun_out/tune_v8.log 2>&1; grep -vE "post_slots|stages=|consumers=" gpurun_out/tune_v8.log
+echo "== bench"; timeout 600 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/b.log 2> gpurun_out/b.err; echo "rc=$?"; python -c "
+import json;d=json.loads(open('gpurun_out/b.log').read());print({k:d[k] for k in ('value','ms_per_step')}, d['roofline']['frac'], d['single_frame_launch']['value'], d['clocks'])"
