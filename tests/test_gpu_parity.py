@@ -584,3 +584,40 @@ def test_frames_land_in_another_process_buffer():
         assert np.array_equal(got[1], want) and not got[0].any()
     finally:
         api.peer_free(base)
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's own caller programs, compiled unchanged against our header + libraries
+# (oracle/Makefile `callers`; the binaries travel with the snapshot, the sources do not)
+# ---------------------------------------------------------------------------------------
+CALLERS = GOLD.parent.parent / "oracle" / "_ref" / "callers"
+
+
+@pytest.mark.skipif(not (CALLERS / "simple_example2").exists(), reason="reference callers were not built on this host")
+def test_reference_callers_run_unchanged(tmp_path):
+    import re
+    import shutil
+    import subprocess
+
+    pat = re.compile(r"\[Synchrophasor\] amplitude: ([-\d.]+), phase: ([-\d.]+), frequency: ([-\d.]+), rocof: ([-\d.]+)")
+    # examples/simple_example2.c (struct config) and examples/simple_example.c (config_example.ini in the cwd):
+    # 2 V / 50 Hz / 1 rad tone -> the frame the reference prints
+    shutil.copy(GOLD.parent.parent / "config" / "config.ini", tmp_path / "config_example.ini")
+    for exe in ("simple_example2", "simple_example"):
+        r = subprocess.run([str(CALLERS / exe)], capture_output=True, text=True, cwd=tmp_path, timeout=120)
+        assert r.returncode == 0, r.stderr
+        amp, ph, freq, rocof = map(float, pat.search(r.stdout).groups())
+        assert abs(amp - 2.0) < 1e-6 and abs(ph - 1.0) < 1e-6 and abs(freq - 50.0) < 1e-6 and abs(rocof) < 1e-6
+    # test/test.c: 1000 timed calls on 51 Hz + 10 % 75 Hz with Q = 22 (float build); prints FREQ / AMP / PH
+    r = subprocess.run([str(CALLERS / "test_c")], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"FREQ: ([-\d.]+) \(Hertz\) \| AMP: ([-\d.]+) \(Volt\) \| PH: ([-\d.]+) \(deg\)", r.stdout)
+    freq, amp, ph_deg = map(float, m.groups())
+    assert abs(freq - 51.0) < 1e-3 and abs(amp - 2.0) < 1e-3 and abs(ph_deg) < 1e-2
+    avg_ms = float(re.search(r"Avg Estimation Time per Call \(ms\): ([\d.]+)", r.stdout).group(1))
+    assert avg_ms < 5.0
+    # test/test2.c: the reference's timing sweep (fs x n_cycles x Q), writes pmu_perf.csv next to it
+    r = subprocess.run([str(CALLERS / "test2_c")], capture_output=True, text=True, cwd=tmp_path, timeout=600)
+    assert r.returncode == 0, r.stderr
+    rows = (tmp_path / "pmu_perf.csv").read_text().strip().splitlines()
+    assert len(rows) == 1 + 2 * 4 * 5                                   # header + 2 fs x 4 n_cycles x 5 Q values
