@@ -621,3 +621,46 @@ def test_reference_callers_run_unchanged(tmp_path):
     assert r.returncode == 0, r.stderr
     rows = (tmp_path / "pmu_perf.csv").read_text().strip().splitlines()
     assert len(rows) == 1 + 2 * 4 * 5                                   # header + 2 fs x 4 n_cycles x 5 Q values
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE config 4 in full: the C37.118.1-style sweep of SURVEY.md section 8(d), both parameter sets
+# ---------------------------------------------------------------------------------------
+def _config4_streams(f0):
+    s = []
+    for f in np.arange(f0 - 5.0, f0 + 5.01, 0.5):                                   # off-nominal
+        s.append(dict(kind="steady", amp=1.0, freq=float(f), phase=0.1 * f, harm=[]))
+    for h in range(2, 51):                                                           # single harmonic, 1 % and 10 %
+        for lvl in (0.01, 0.10):
+            s.append(dict(kind="steady", amp=57.7, freq=f0 + 0.05, phase=0.4, harm=[(lvl, (f0 + 0.05) * h, 0.2 * h)]))
+    for fi in (10.0, 15.0, 20.0, 25.0, 75.0, 80.0, 85.0, 90.0, 95.0, 100.0):        # out-of-band interharmonics, 10 %
+        for f in (f0 - 2.5, f0, f0 + 2.5):
+            s.append(dict(kind="steady", amp=2.0, freq=f, phase=-0.7, harm=[(0.10, fi * f0 / 50.0, 0.1)]))
+    for fm in (0.1, 0.5, 1.0, 2.0, 3.0, 4.0, 5.0):                                   # AM + PM
+        s.append(dict(kind="mod", amp=10.0, freq=f0, fm=fm, phase=0.3))
+    for f in np.arange(f0 - 5.0, f0 + 5.01, 1.0):                                   # +-1 Hz/s ramps
+        s.append(dict(kind="steady", amp=1.0, freq=float(f), phase=0.0, harm=[], ramp=1.0 if f < f0 else -1.0))
+    return s
+
+
+@pytest.mark.parametrize("cfgname", ["config.ini", "m_class_config.ini"])
+def test_config4_full_sweep_matches_oracle(cfgname):
+    cfg = configs.NAMED[cfgname]
+    streams = _config4_streams(float(cfg["f0"]))
+    sc = dict(name="config4", cfg=cfgname, frames=4, streams=streams)
+    win, mid = stream_case_windows(sc)
+    T, S = mid.shape
+    want, km_want, _ = checker(np.float64, 1).run(cfg, win, mid, n_threads=0)
+    got = np.zeros_like(want)
+    km = np.zeros((T, S), dtype=np.int64)
+    n_trig = 0
+    with BatchEstimator(cfg, S, 1) as est:
+        est.set_debug(True)
+        for t in range(T):
+            got[t] = est.estimate(win[t], mid[t])
+            k, trig, _ = est.get_debug()
+            km[t] = k[:, 0]
+            n_trig += int(trig.sum())
+    assert_frames_close(got, want, "f64", f"config 4 sweep / {cfgname}")
+    assert np.array_equal(km, km_want[:, :, 0])
+    assert S == 21 + 98 + 30 + 7 + 11 and n_trig > 50          # the interharmonic / harmonic cases run the Q loop
