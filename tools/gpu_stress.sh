@@ -1,0 +1,7 @@
+#!/bin/bash
+# the parity suite under starved kernel resources (2 ring stages, 2 raw buffers, 1 estimator slot; then 3 consumer warps):
+# exercises every wait path (stage_seq, raw_owner, post_lock, grp_done) much harder than the default plan
+mkdir -p gpurun_out
+echo "== starved scratch"; PMU_STAGES=2 PMU_RAW_BUFFERS=2 PMU_POST_SLOTS=1 timeout 900 python -m pytest tests -x -q -m gpu -k "not latency" > gpurun_out/pytest_stress1.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/pytest_stress1.log
+echo "== 3 consumer warps, 3 stages"; PMU_STAGES=3 PMU_CONSUMER_WARPS=3 PMU_POST_SLOTS=2 timeout 900 python -m pytest tests -x -q -m gpu -k "not latency" > gpurun_out/pytest_stress2.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/pytest_stress2.log
+echo "== per-element loader everywhere"; PMU_FORCE_ELEM_LOAD=1 timeout 900 python -m pytest tests -x -q -m gpu -k "not latency" > gpurun_out/pytest_stress3.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/pytest_stress3.log
