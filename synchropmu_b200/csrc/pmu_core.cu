@@ -123,13 +123,17 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     a.spec_out = b->debug ? b->d_spec + (size_t)w0 * b->cfg.n_bins * 2 : nullptr;
     a.state_export = d_export_base ? d_export_base + (size_t)w0 * 4 : nullptr;
     a.timeline = b->d_timeline;
+    // a handful of windows (the single-instance drop-in path): one warp per window end to end
+    static const int wpw_max = getenv("PMU_WARP_PER_WINDOW_MAX") ? atoi(getenv("PMU_WARP_PER_WINDOW_MAX")) : 64;
+    a.warp_per_window = (a.n_windows <= wpw_max && a.n_windows <= PMU_MAX_GROUPS && b->cfg.n_bins <= PMU_WARP) ? 1 : 0;
     // TMA bulk copies need 16-byte aligned sources; otherwise per-element cp.async
     bool ok16 = b->plan.aligned16 && (((uintptr_t)a.windows) % 16 == 0);
     if (ring) ok16 = ok16 && ((size_t)b->ring_cap * sz) % 16 == 0 && ((size_t)b->hop * sz) % 16 == 0;
     a.load_mode = ok16 ? PMU_LOAD_BULK : PMU_LOAD_ELEM;
     static const int force_elem = getenv("PMU_FORCE_ELEM_LOAD") ? atoi(getenv("PMU_FORCE_ELEM_LOAD")) : 0;
     if (force_elem) a.load_mode = PMU_LOAD_ELEM;
-    const int grid = grid_for(b, a.n_windows);
+    int grid = grid_for(b, a.n_windows);
+    if (a.warp_per_window && !getenv("PMU_GRID")) grid = (int)(a.n_windows < b->num_sms ? a.n_windows : b->num_sms);
     const int block = PMU_WARP * (1 + b->plan.n_cons);
     int rc = (b->dtype == PMUB_F64) ? pmu_launch_f64(b->plan.M, b->plan.KC, a, grid, block, b->plan.smem_bytes, s)
                                     : pmu_launch_f32(b->plan.M, b->plan.KC, a, grid, block, b->plan.smem_bytes, s);
@@ -451,6 +455,17 @@ int pmub_estimate_frames(pmub_batch* b, int n_frames, const void* windows, const
         cudaStream_t s = main_stream(b);
         memcpy(b->h_in, windows, win_bytes);
         memcpy(b->h_in + win_bytes, mid, mid_bytes);
+        // A few windows: the kernel reads the pinned staging buffer and writes the pinned result buffer itself
+        // (mapped host memory, bulk copies straight over PCIe) - one submission instead of three.
+        static const size_t zc_max = getenv("PMU_ZERO_COPY_MAX") ? (size_t)atoll(getenv("PMU_ZERO_COPY_MAX")) : (size_t)(512 << 10);
+        if (win_bytes <= zc_max) {
+            if (launch_range(b, 0, b->n_windows, 1, b->h_in, b->h_in + win_bytes, b->h_out,
+                             b->mirror ? reinterpret_cast<double*>(b->h_out + fr_bytes) : nullptr, s))
+                return -1;
+            CUDA_OK(cudaStreamSynchronize(s));
+            memcpy(frames, b->h_out, fr_bytes);
+            return 0;
+        }
         CUDA_OK(cudaMemcpyAsync(b->d_windows, b->h_in, win_bytes, cudaMemcpyHostToDevice, s));
         CUDA_OK(cudaMemcpyAsync(b->d_mid, b->h_in + win_bytes, mid_bytes, cudaMemcpyHostToDevice, s));
         if (launch_range(b, 0, b->n_windows, 1, b->d_windows, b->d_mid, b->d_out, b->mirror ? d_export : nullptr, s)) return -1;

@@ -79,6 +79,9 @@ struct KernelArgs {
     int* dbg;                    // [n_frames][frame_stride]  km | flags
     double* spec_out;            // [n_frames][frame_stride][K][2] Hann-windowed bins
     double* state_export;        // [frame_stride][4]  f_old, dl0, dl1, state after the last frame
+    // small launches (a few windows, e.g. the single-instance pmu_estimate): each warp runs the estimator of
+    // the window it has just transformed, lane = bin (peak search = warp-shuffle argmax), no batching
+    int warp_per_window;
     // profiling aid: [gridDim.x][warps][4] globaltimer stamps (setup done, first window ready,
     // tickets exhausted, warp exit); null in normal operation
     unsigned long long* timeline;
@@ -220,6 +223,146 @@ struct BatchMap {
         }
     }
 };
+
+// ---- estimator with lane = bin: one window per warp (small launches) ---------------------------------
+// Same arithmetic as pmu_math.cuh, bin j evaluated by lane j: the reference's find3LargestIndx (:705-720)
+// becomes a warp-shuffle argmax that keeps the first strict maximum (and lets a NaN win only at bin 0), the
+// energy sums (:219-220) become shuffle reductions; everything scalar is computed redundantly by all lanes.
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+__device__ __forceinline__ int ipdft_warp(const PostParams& p, double yr, double yi, int j, bool valid, Tone* out, int* km_out)
+{
+    const double v = yr * yr + yi * yi;
+    const double v0 = __shfl_sync(0xffffffffu, v, 0);
+    double key = (valid && v == v) ? v : -INFINITY;   // NaN never wins ...
+    int idx = j;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double ok = __shfl_xor_sync(0xffffffffu, key, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        if (ok > key || (ok == key && oi < idx)) { key = ok; idx = oi; }   // first maximum on ties
+    }
+    const int km = (v0 != v0) ? 0 : idx;                // ... unless it sits at bin 0
+    Peak pk;
+    pk.km = km;
+    pk.best = __shfl_sync(0xffffffffu, v, km);
+    pk.left = __shfl_sync(0xffffffffu, v, km > 0 ? km - 1 : 0);
+    pk.right = __shfl_sync(0xffffffffu, v, km + 1 < p.K ? km + 1 : km);
+    pk.yr = __shfl_sync(0xffffffffu, yr, km);
+    pk.yi = __shfl_sync(0xffffffffu, yi, km);
+    pk.prev = 0.0;
+    if (km_out) *km_out = km;
+    return ipdft_finish(p, pk, out);
+}
+
+// value at bin j of wf(j, f, z) for this lane (three reciprocals, no sliding window)
+__device__ __forceinline__ void sweep_bin(const PostParams& p, const Sweep& sw, int j, double* wr, double* wi)
+{
+    const int m = j - sw.kstar;
+    sw.eval(p, j, sw.inv_den(p, m - 1), sw.inv_den(p, m), sw.inv_den(p, m + 1), wr, wi);
+}
+
+__device__ __forceinline__ void e_ipdft_warp(const PostParams& p, double yr, double yi, int j, bool valid, Tone* t, int* km_first)
+{
+    Tone cur = *t;
+    if (!ipdft_warp(p, yr, yi, j, valid, &cur, km_first)) {
+        for (int it = 0; it < p.P; ++it) {
+            Sweep sw;
+            sw.init(p, -cur.freq, cur.amp * cur.cr, -cur.amp * cur.ci);
+            double wr, wi;
+            sweep_bin(p, sw, j, &wr, &wi);
+            Tone nxt;
+            const int done = ipdft_warp(p, yr - wr, yi - wi, j, valid, &nxt, nullptr);
+            cur = nxt;
+            if (done) break;
+        }
+    }
+    *t = cur;
+}
+
+// X - pureTone(t) at this lane's bin
+__device__ __forceinline__ void residual_bin(const PostParams& p, double xr, double xi, int j, const Tone& t, double* wr_, double* wi_)
+{
+    Sweep sp, sn;
+    sp.init(p, t.freq, t.amp * t.cr, t.amp * t.ci);
+    sn.init(p, -t.freq, t.amp * t.cr, -t.amp * t.ci);
+    double ar, ai, br, bi;
+    sweep_bin(p, sp, j, &ar, &ai);
+    sweep_bin(p, sn, j, &br, &bi);
+    *wr_ = xr - (ar + br);
+    *wi_ = xi - (ai + bi);
+}
+
+template <typename InT>
+__device__ __noinline__ void post_window_warp(const KernelArgs& a, const double* row, long long w, int frame, int lane)
+{
+    const PostParams& pp = a.post;
+    const int K = pp.K;
+    const bool valid = lane < K;
+    const int j = valid ? lane : K - 1;
+    const long long wf = (long long)frame * a.frame_stride + w;
+    const pmu_c xw = hann_combine(row, j);
+    const double xr = xw.x, xi = xw.y;
+    if (a.spec_out && valid) {
+        a.spec_out[((size_t)wf * K + j) * 2] = xr;
+        a.spec_out[((size_t)wf * K + j) * 2 + 1] = xi;
+    }
+    Tone f;
+    f.amp = 0; f.cr = 1; f.ci = 0; f.freq = 0;
+    int km = 0;
+    e_ipdft_warp(pp, xr, xi, j, valid, &f, &km);                       // :205
+    int dbg = km & PMU_DBG_KM_MASK;
+    if (pp.iter_en) {
+        double wr, wi;
+        residual_bin(pp, xr, xi, j, f, &wr, &wi);                      // :206-215  Xi
+        const double Ed = warp_sum(valid ? wr * wr + wi * wi : 0.0);   // :219
+        const double E = warp_sum(valid ? xr * xr + xi * xi : 0.0);    // :220
+        if (Ed > pp.eps * E) {                                         // :229
+            dbg |= PMU_DBG_TRIGGERED;
+            Tone it;
+            it.amp = 0; it.cr = 1; it.ci = 0; it.freq = 0;
+            for (int i = 0; i < pp.Q; ++i) {                           // :675-696
+                e_ipdft_warp(pp, wr, wi, j, valid, &it, nullptr);
+                residual_bin(pp, xr, xi, j, it, &wr, &wi);
+                e_ipdft_warp(pp, wr, wi, j, valid, &f, nullptr);
+                if (i + 1 < pp.Q) residual_bin(pp, xr, xi, j, f, &wr, &wi);
+            }
+        }
+    }
+    if (lane == 0) {
+        RocofState rs;
+        rs.f_old = __ldcg(&a.st_fold[w]);
+        rs.dl0 = __ldcg(&a.st_dl0[w]);
+        rs.dl1 = __ldcg(&a.st_dl1[w]);
+        rs.st = __ldcg(&a.st_state[w]);
+        const double y = rocof_step(pp, f.freq, &rs);
+        a.st_fold[w] = rs.f_old;
+        a.st_dl0[w] = rs.dl0;
+        a.st_dl1[w] = rs.dl1;
+        a.st_state[w] = (unsigned char)rs.st;
+        double mid;
+        if (a.mid) {
+            mid = (double)reinterpret_cast<const InT*>(a.mid)[(long long)frame * a.mid_frame_stride + w / pp.C];
+        } else {
+            const unsigned long long c = (a.t0_samples + (unsigned long long)frame * (unsigned)a.hop + (unsigned)(a.N / 2)) % (unsigned)a.fs;
+            mid = (double)(InT)((double)c / (double)a.fs);
+        }
+        double fr[4];
+        fill_frame(pp, f, y, mid, fr);
+        InT* out = reinterpret_cast<InT*>(a.frames) + (size_t)wf * 4;
+        out[0] = (InT)fr[0]; out[1] = (InT)fr[1]; out[2] = (InT)fr[2]; out[3] = (InT)fr[3];
+        if (a.dbg) a.dbg[wf] = dbg;
+        if (a.state_export && frame == a.n_frames - 1) {
+            double* e = a.state_export + (size_t)w * 4;
+            e[0] = rs.f_old; e[1] = rs.dl0; e[2] = rs.dl1; e[3] = (double)rs.st;
+        }
+    }
+}
 
 // ---- post-processing of one batch (lane = window) --------------------------------------
 // Batch = <= 32 consecutive streams of this CTA at frame f.  w_first = index (within this
@@ -537,6 +680,41 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                     ccplx c; c.x = ar[k]; c.y = ai[k];
                     my[k] = c;
                 }
+        }
+        if (a.warp_per_window) {
+            // small launch: this warp finishes its own window right away, lane = bin
+            double* myrow = reinterpret_cast<double*>(smem + a.off_raw) + (size_t)(warp - 1) * a.raw_stride;
+            __syncwarp();
+            for (int c = lane; c < 2 * a.Kp; c += PMU_WARP) {
+                const CT* col = red + c;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int l = 0; l < PMU_WARP; l += 4) {
+                    s0 += (double)col[(l + 0) * RS];
+                    s1 += (double)col[(l + 1) * RS];
+                    s2 += (double)col[(l + 2) * RS];
+                    s3 += (double)col[(l + 3) * RS];
+                }
+                myrow[c] = (s0 + s1) + (s2 + s3);
+            }
+            __syncwarp();
+            // frames of one stream are claimed by tickets in frame order, but by different warps: frame f waits
+            // for the ROCOF state written by frame f-1 of the same stream
+            if (a.n_frames > 1) {
+                if (lane == 0)
+                    while (ld_volatile_s32(&ctrl->grp_done[t]) != f) __nanosleep(64);
+                __syncwarp();
+                __threadfence_block();
+            }
+            post_window_warp<InT>(a, myrow, w_begin + t, f, lane);
+            if (a.n_frames > 1) {
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    *reinterpret_cast<volatile int*>(&ctrl->grp_done[t]) = f + 1;
+                }
+            }
+            continue;
         }
         int g, slot, bsz, first_t;
         bm.locate(t, &g, &slot, &bsz, &first_t);

@@ -357,6 +357,37 @@ def test_multi_frame_launch_equals_sequential_calls(cfgname, n_inst):
     assert_frames_close(got_dev[:, :want.shape[1]], want, "f64", cfgname)
 
 
+@pytest.mark.parametrize("cfgname", ["config.ini", "cfg5_600", "m_class_config.ini"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_warp_per_window_path_equals_batched_path(cfgname, dtype):
+    """Launches of <= 64 windows (the pmu_estimate drop-in path) run the estimator with lane = bin and a warp-shuffle
+    argmax; bigger launches run it with lane = window.  Same arithmetic per bin: the first 8 instances must come out
+    bit-identical whether they are estimated alone or inside a batch of 40, frame after frame (ROCOF state included)."""
+    cfg = configs.NAMED[cfgname]
+    T = 6
+    win, mid = three_phase_batch(cfg, 40, T, seed=77, interharmonic_frames=(2, 4))
+    win, mid = win.astype(dtype), mid.astype(dtype)
+    with BatchEstimator(cfg, 8, 6, dtype=dtype) as small, BatchEstimator(cfg, 40, 6, dtype=dtype) as big, \
+            BatchEstimator(cfg, 8, 6, dtype=dtype) as small_multi:
+        small.set_debug(True)
+        big.set_debug(True)
+        for t in range(T):
+            a = small.estimate(np.ascontiguousarray(win[t, :8]), np.ascontiguousarray(mid[t, :8]))
+            b = big.estimate(win[t], mid[t])
+            kma, tra, spa = small.get_debug()
+            kmb, trb, spb = big.get_debug()
+            assert np.array_equal(kma, kmb[:8]) and np.array_equal(tra, trb[:8]), (cfgname, t)
+            assert np.array_equal(spa, spb[:8]), (cfgname, t)
+            assert np.array_equal(a, b[:8], equal_nan=True), (cfgname, t, np.abs(a - b[:8]).max())
+        # several frames in one small launch: frame-to-frame state hand-over between warps
+        c = small_multi.estimate_frames(np.ascontiguousarray(win[:, :8]), np.ascontiguousarray(mid[:, :8]))
+        assert small_multi.launches == 1
+        assert np.array_equal(c[-1], a, equal_nan=True)
+        sa_, sb_ = small.get_state(), small_multi.get_state()
+        for k in sa_:
+            assert np.array_equal(sa_[k], sb_[k])
+
+
 # ---------------------------------------------------------------------------------------
 # C callers: compile against include/ and run against the in-tree libraries
 # ---------------------------------------------------------------------------------------
@@ -491,23 +522,25 @@ def test_hostile_inputs_match_reference_nan_pattern():
 
 
 def test_single_call_latency_report(capsys):
-    """Not a gate: prints the drop-in pmu_estimate latency (one H2D, one launch, one D2H)."""
+    """Not a gate: prints the drop-in pmu_estimate latency (pinned staging, one launch that reads and writes mapped
+    host memory, one stream synchronisation), Python/ctypes overhead included."""
     import time
 
-    pmu = PMUEstimator()
-    assert pmu.configure_from_class(EstimatorConfig.from_dict(configs.DEFAULT_INI)) == 0
-    x = signals.steady(configs.DEFAULT_INI, 0, [2.0], [50.0], [1.0])[0]
-    for _ in range(20):
-        pmu.estimate(x, 0.0)
-    t0 = time.perf_counter()
-    n = 300
-    for _ in range(n):
-        pmu.estimate(x, 0.0)
-    us = (time.perf_counter() - t0) / n * 1e6
-    with capsys.disabled():
-        print(f"\n[latency] pmu_estimate (1 channel, 2048 samples, ctypes included): {us:.1f} us per call")
-    assert us < 5000
-    pmu.deinit()
+    for n_ch in (1, 6):
+        pmu = PMUEstimator(n_channels=n_ch)
+        assert pmu.configure_from_class(EstimatorConfig.from_dict(configs.DEFAULT_INI)) == 0
+        x = np.stack([signals.steady(configs.DEFAULT_INI, 0, [2.0], [50.0], [1.0 + c])[0] for c in range(n_ch)])
+        for _ in range(20):
+            pmu.estimate(x, 0.0)
+        t0 = time.perf_counter()
+        n = 300
+        for _ in range(n):
+            pmu.estimate(x, 0.0)
+        us = (time.perf_counter() - t0) / n * 1e6
+        with capsys.disabled():
+            print(f"\n[latency] pmu_estimate ({n_ch} channel(s), 2048 samples, ctypes included): {us:.1f} us per call")
+        assert us < 5000
+        pmu.deinit()
 
 
 # ---------------------------------------------------------------------------------------
@@ -594,7 +627,7 @@ CALLERS = GOLD.parent.parent / "oracle" / "_ref" / "callers"
 
 
 @pytest.mark.skipif(not (CALLERS / "simple_example2").exists(), reason="reference callers were not built on this host")
-def test_reference_callers_run_unchanged(tmp_path):
+def test_reference_callers_run_unchanged(tmp_path, capsys):
     import re
     import shutil
     import subprocess
@@ -616,6 +649,15 @@ def test_reference_callers_run_unchanged(tmp_path):
     assert abs(freq - 51.0) < 1e-3 and abs(amp - 2.0) < 1e-3 and abs(ph_deg) < 1e-2
     avg_ms = float(re.search(r"Avg Estimation Time per Call \(ms\): ([\d.]+)", r.stdout).group(1))
     assert avg_ms < 5.0
+    # the same program linked with the unmodified reference (CPU): same answer, its per-call time for the record
+    r = subprocess.run([str(CALLERS / "test_c_cpu")], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"FREQ: ([-\d.]+) \(Hertz\) \| AMP: ([-\d.]+) \(Volt\) \| PH: ([-\d.]+) \(deg\)", r.stdout)
+    assert abs(float(m.group(1)) - freq) < 1e-3 and abs(float(m.group(2)) - amp) < 1e-3
+    cpu_ms = float(re.search(r"Avg Estimation Time per Call \(ms\): ([\d.]+)", r.stdout).group(1))
+    with capsys.disabled():
+        print(f"\n[latency] reference test/test.c (Q = 22, float, 1 channel): {avg_ms * 1e3:.1f} us per pmu_estimate call on "
+              f"the B200 library, {cpu_ms * 1e3:.1f} us with the reference on one host core")
     # test/test2.c: the reference's timing sweep (fs x n_cycles x Q), writes pmu_perf.csv next to it
     r = subprocess.run([str(CALLERS / "test2_c")], capture_output=True, text=True, cwd=tmp_path, timeout=600)
     assert r.returncode == 0, r.stderr
