@@ -62,12 +62,14 @@ typedef struct {
     double df;             /* fs / win_len                                               */
     double norm_factor;    /* sequential Hann sum, src/pmu_estimator.c:549-560           */
     /* how the kernel was specialised for this configuration */
-    int dft_radix;         /* M: in-register real-FFT codelet size                       */
+    int dft_radix;         /* M: in-register real-FFT codelet size; 0 = the general kernel
+                              (n_bins > 23: direct summation, one CTA per window)        */
     int dft_bins;          /* KC: rectangular bins accumulated per lane                  */
     int n_stages;          /* shared-memory ring depth                                   */
     int stage_bytes;
     int slabs_per_window;
-    int load_mode;         /* 0 = TMA bulk copies, 1 = per-element cp.async              */
+    int load_mode;         /* 0 = TMA bulk copies, 1 = per-element cp.async, 2 = plain loads
+                              (general kernel)                                            */
     int grid;              /* CTAs launched for a full batch                             */
     int block;             /* threads per CTA                                            */
     int smem_bytes;        /* dynamic shared memory per CTA                              */

@@ -133,6 +133,11 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     static const int force_elem = getenv("PMU_FORCE_ELEM_LOAD") ? atoi(getenv("PMU_FORCE_ELEM_LOAD")) : 0;
     if (force_elem) a.load_mode = PMU_LOAD_ELEM;
     int grid = grid_for(b, a.n_windows);
+    if (b->plan.M == 0) {   // general kernel: one CTA per window, several resident per SM
+        a.warp_per_window = 0;
+        const long long cap = (long long)b->num_sms * 8;
+        grid = (int)(a.n_windows < cap ? a.n_windows : cap);
+    }
     if (a.warp_per_window && !getenv("PMU_GRID")) grid = (int)(a.n_windows < b->num_sms ? a.n_windows : b->num_sms);
     const int block = PMU_WARP * (1 + b->plan.n_cons);
     int rc = (b->dtype == PMUB_F64) ? pmu_launch_f64(b->plan.M, b->plan.KC, a, grid, block, b->plan.smem_bytes, s)
@@ -146,7 +151,7 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
 // keeps one frame of observations.
 static int frames_per_launch(const pmub_batch* b, long long n, int n_frames)
 {
-    if (n_frames <= 1 || b->debug) return 1;
+    if (n_frames <= 1 || b->debug || b->plan.M == 0) return 1;
     const int grid = grid_for(b, n);
     const long long n_local = (n + grid - 1) / grid;
     if ((n_local + PMU_WARP - 1) / PMU_WARP > PMU_MAX_GROUPS) return 1;
@@ -395,7 +400,7 @@ int pmub_get_info(const pmub_batch* b, pmub_info* o)
     o->dtype = b->dtype; o->device = b->device; o->df = b->d.df; o->norm_factor = b->d.S;
     o->dft_radix = b->plan.M; o->dft_bins = b->plan.KC; o->n_stages = b->plan.n_stage;
     o->stage_bytes = b->plan.stage_bytes; o->slabs_per_window = b->plan.nslab;
-    o->load_mode = b->plan.aligned16 ? PMU_LOAD_BULK : PMU_LOAD_ELEM;
+    o->load_mode = b->plan.M == 0 ? 2 : (b->plan.aligned16 ? PMU_LOAD_BULK : PMU_LOAD_ELEM);
     o->grid = grid_for(b, b->n_windows); o->block = PMU_WARP * (1 + b->plan.n_cons);
     o->smem_bytes = b->plan.smem_bytes;
     o->bytes_per_estimate = pmu::bytes_per_estimate(b->d.N, b->dtype, b->C);

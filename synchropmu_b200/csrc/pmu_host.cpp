@@ -241,6 +241,40 @@ static int env_int(const char* name, int dflt)
     return (s && *s) ? atoi(s) : dflt;
 }
 
+// Plan of the general kernel (pmu_wide.cuh, M == 0): one CTA per window, direct summation of the K+1 lowest bins
+// with a full table of W_N^m, estimator scratch in shared memory.  Takes every configuration the fused kernel
+// cannot (n_bins > 23), as long as the per-window scratch fits.
+static int make_wide_plan(const pmub_config& c, int max_smem, Plan* out)
+{
+    Plan p;
+    memset(&p, 0, sizeof p);
+    const int N = (int)win_len(c);
+    const int K = (int)c.n_bins;
+    p.M = 0;
+    p.Kp = K + 1;
+    p.KC = p.Kp;
+    p.L = N; p.W = N; p.nslab = 1; p.pitch = N;
+    p.n_u = N;                  // U = W_N^m, m < N
+    p.jlo = K + 2;
+    p.jhi = 2 * K + 1;
+    p.raw_stride = 2 * p.Kp;
+    p.n_cons = 7;               // block = 32 * (1 + n_cons) = 256 threads
+    int off = 0;
+    p.off_ctrl = off;
+    p.off_U = off; p.off_V = off;
+    p.off_trig = off; off += align_up((p.jlo + p.jhi + 1) * 16, 128);
+    p.off_raw = off;  off += align_up(2 * p.Kp * 8, 128);
+    p.off_post = off; off += align_up(2 * K * 16, 128);
+    p.off_red = off; p.off_stage = off;
+    p.smem_bytes = off;
+    if (off > max_smem) {
+        set_error("[pmu_init] ERROR: number of dft bins too large for the CUDA estimator's per-window scratch (about 2300 bins)");
+        return -1;
+    }
+    *out = p;
+    return 0;
+}
+
 int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
 {
     Plan p;
@@ -253,10 +287,7 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
     else if (p.Kp <= 12) p.KC = 12;
     else if (p.Kp <= 16) p.KC = 16;
     else if (p.Kp <= 24) p.KC = 24;
-    else {
-        set_error("[pmu_init] ERROR: number of dft bins > 23 is not supported by this build of the CUDA estimator");
-        return -1;
-    }
+    else return make_wide_plan(c, max_smem, out);
     // codelet size: largest supported power of two dividing N that still leaves >= 32 residues
     const int cand[4] = {16, 8, 4, 1};
     p.M = 1;
@@ -342,10 +373,7 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
             if (layout(nc, nr < 2 ? 2 : nr, np < 1 ? 1 : np) >= min_stages) { ok = true; break; }
         }
     }
-    if (!ok) {
-        set_error("[pmu_init] ERROR: configuration does not fit the shared-memory budget of the CUDA estimator (window too long or too many bins)");
-        return -1;
-    }
+    if (!ok) return make_wide_plan(c, max_smem, out);   // e.g. very long windows with many bins
     *out = p;
     return 0;
 }
@@ -361,12 +389,17 @@ void build_tables(const Plan& p, unsigned N, std::vector<pmu_c>* U, std::vector<
         o.y = (double)(-sinl(ang));
         return o;
     };
-    const int n_groups = p.n_u / p.KC;
-    U->resize((size_t)p.n_u);
+    if (p.M == 0) {   // general kernel: the full twiddle table, no lane table
+        U->resize((size_t)N);
+        for (unsigned m = 0; m < N; ++m) (*U)[m] = w(m);
+        V->assign(1, w(0));
+    }
+    const int n_groups = p.M == 0 ? 0 : p.n_u / p.KC;
+    if (p.M != 0) U->resize((size_t)p.n_u);
     for (int g = 0; g < n_groups; ++g)
         for (int k = 0; k < p.KC; ++k) (*U)[(size_t)g * p.KC + k] = w(32ull * (unsigned long long)g * (unsigned long long)k);
-    V->resize((size_t)p.KC * 32);
-    for (int k = 0; k < p.KC; ++k)
+    if (p.M != 0) V->resize((size_t)p.KC * 32);
+    for (int k = 0; p.M != 0 && k < p.KC; ++k)
         for (int l = 0; l < 32; ++l) (*V)[(size_t)k * 32 + l] = w((unsigned long long)l * (unsigned long long)k);
     trig->resize((size_t)(p.jlo + p.jhi + 1));
     for (int j = -p.jlo; j <= p.jhi; ++j) {

@@ -298,6 +298,40 @@ __device__ __forceinline__ void residual_bin(const PostParams& p, double xr, dou
     *wi_ = xi - (ai + bi);
 }
 
+// ROCOF stage, frame fill and stores for one window (src/pmu_estimator.c:236-265); one thread.
+template <typename InT>
+__device__ __forceinline__ void finish_window(const KernelArgs& a, const Tone& f, int dbg, long long w, int frame)
+{
+    const PostParams& pp = a.post;
+    const long long wf = (long long)frame * a.frame_stride + w;
+    RocofState rs;
+    rs.f_old = __ldcg(&a.st_fold[w]);
+    rs.dl0 = __ldcg(&a.st_dl0[w]);
+    rs.dl1 = __ldcg(&a.st_dl1[w]);
+    rs.st = __ldcg(&a.st_state[w]);
+    const double y = rocof_step(pp, f.freq, &rs);
+    a.st_fold[w] = rs.f_old;
+    a.st_dl0[w] = rs.dl0;
+    a.st_dl1[w] = rs.dl1;
+    a.st_state[w] = (unsigned char)rs.st;
+    double mid;
+    if (a.mid) {
+        mid = (double)reinterpret_cast<const InT*>(a.mid)[(long long)frame * a.mid_frame_stride + w / pp.C];
+    } else {
+        const unsigned long long c = (a.t0_samples + (unsigned long long)frame * (unsigned)a.hop + (unsigned)(a.N / 2)) % (unsigned)a.fs;
+        mid = (double)(InT)((double)c / (double)a.fs);
+    }
+    double fr[4];
+    fill_frame(pp, f, y, mid, fr);
+    InT* out = reinterpret_cast<InT*>(a.frames) + (size_t)wf * 4;
+    out[0] = (InT)fr[0]; out[1] = (InT)fr[1]; out[2] = (InT)fr[2]; out[3] = (InT)fr[3];
+    if (a.dbg) a.dbg[wf] = dbg;
+    if (a.state_export && frame == a.n_frames - 1) {
+        double* e = a.state_export + (size_t)w * 4;
+        e[0] = rs.f_old; e[1] = rs.dl0; e[2] = rs.dl1; e[3] = (double)rs.st;
+    }
+}
+
 template <typename InT>
 __device__ __noinline__ void post_window_warp(const KernelArgs& a, const double* row, long long w, int frame, int lane)
 {
@@ -334,34 +368,7 @@ __device__ __noinline__ void post_window_warp(const KernelArgs& a, const double*
             }
         }
     }
-    if (lane == 0) {
-        RocofState rs;
-        rs.f_old = __ldcg(&a.st_fold[w]);
-        rs.dl0 = __ldcg(&a.st_dl0[w]);
-        rs.dl1 = __ldcg(&a.st_dl1[w]);
-        rs.st = __ldcg(&a.st_state[w]);
-        const double y = rocof_step(pp, f.freq, &rs);
-        a.st_fold[w] = rs.f_old;
-        a.st_dl0[w] = rs.dl0;
-        a.st_dl1[w] = rs.dl1;
-        a.st_state[w] = (unsigned char)rs.st;
-        double mid;
-        if (a.mid) {
-            mid = (double)reinterpret_cast<const InT*>(a.mid)[(long long)frame * a.mid_frame_stride + w / pp.C];
-        } else {
-            const unsigned long long c = (a.t0_samples + (unsigned long long)frame * (unsigned)a.hop + (unsigned)(a.N / 2)) % (unsigned)a.fs;
-            mid = (double)(InT)((double)c / (double)a.fs);
-        }
-        double fr[4];
-        fill_frame(pp, f, y, mid, fr);
-        InT* out = reinterpret_cast<InT*>(a.frames) + (size_t)wf * 4;
-        out[0] = (InT)fr[0]; out[1] = (InT)fr[1]; out[2] = (InT)fr[2]; out[3] = (InT)fr[3];
-        if (a.dbg) a.dbg[wf] = dbg;
-        if (a.state_export && frame == a.n_frames - 1) {
-            double* e = a.state_export + (size_t)w * 4;
-            e[0] = rs.f_old; e[1] = rs.dl0; e[2] = rs.dl1; e[3] = (double)rs.st;
-        }
-    }
+    if (lane == 0) finish_window<InT>(a, f, dbg, w, frame);
 }
 
 // ---- post-processing of one batch (lane = window) --------------------------------------

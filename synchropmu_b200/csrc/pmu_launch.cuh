@@ -8,6 +8,7 @@
 
 #include "pmu_host.hpp"
 #include "pmu_kernel.cuh"
+#include "pmu_wide.cuh"
 
 namespace {
 
@@ -48,10 +49,33 @@ int launch_kc(int KC, const KernelArgs& a, int grid, int block, int smem, cudaSt
     return -1;
 }
 
+// The general kernel (pmu_wide.cuh): plans with M == 0.
+template <typename T>
+int launch_wide(const KernelArgs& a, int grid, int smem, cudaStream_t s)
+{
+    static int configured[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && smem > 48 * 1024 && (dev < 0 || dev >= 64 || configured[dev] != smem)) {
+        e = cudaFuncSetAttribute(pmu_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev] = smem;
+    }
+    if (e == cudaSuccess) {
+        pmu_wide_kernel<T><<<grid, PMU_WIDE_THREADS, smem, s>>>(a);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        pmu::set_error(std::string("[pmu_estimate] CUDA ERROR launching the general estimator kernel: ") + cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
 template <typename T>
 int launch_m(int M, int KC, const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
 {
     switch (M) {
+        case 0: return launch_wide<T>(a, grid, smem, s);
         case 16: return launch_kc<T, 16>(KC, a, grid, block, smem, s);
         case 8: return launch_kc<T, 8>(KC, a, grid, block, smem, s);
         case 4: return launch_kc<T, 4>(KC, a, grid, block, smem, s);

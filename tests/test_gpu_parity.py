@@ -163,8 +163,70 @@ def test_odd_window_length_and_wide_bins():
         assert_frames_close(got, want, "f64", f"N={N}")
 
 
+@pytest.mark.parametrize("over,dtype", [
+    (dict(n_bins=24), np.float64),                                   # first bin count past the fused kernel
+    (dict(n_bins=100, Q=2), np.float64),                             # many bins on the default window
+    (dict(n_cycles=30, n_bins=40, Q=2), np.float64),                 # N = 15360, 30-cycle window
+    (dict(fs=4750, n_cycles=9, n_bins=33), np.float64),              # N = 855 (odd)
+    (dict(n_bins=64, Q=2), np.float32),
+])
+def test_many_bins_run_on_the_general_kernel(over, dtype):
+    """n_bins > 23 (legal per check_config_validity :386-449) is served by the one-CTA-per-window kernel: same parity bar,
+    explicit windows, a multi-frame call and the streaming front end."""
+    cfg = dict(configs.DEFAULT_INI, **over)
+    N, hop = configs.win_len(cfg), configs.hop(cfg)
+    S, T = 7, 4
+    rng = np.random.default_rng(N + cfg["n_bins"])
+    f = 50 + rng.uniform(-2, 2, S)
+    amp, ph = 1 + rng.uniform(0, 1, S), rng.uniform(-3, 3, S)
+    win = np.zeros((T, S, 1, N), dtype=dtype)
+    mid = np.zeros((T, S), dtype=dtype)
+    for t in range(T):
+        harm = [(0.1, 75.0, 0.0)] if t == 2 else [(0.002, 150.0, 0.3)]
+        win[t, :, 0, :] = signals.steady(cfg, t, amp, f, ph, harmonics=harm)
+        mid[t] = signals.mid_fracsec(cfg, t)
+    want, km_want, _ = checker(dtype, 1).run(cfg, win, mid)
+    tol = "f64" if dtype == np.float64 else "f32"
+    with BatchEstimator(cfg, S, 1, dtype=dtype) as est, BatchEstimator(cfg, S, 1, dtype=dtype) as multi:
+        assert est.info.dft_radix == 0 and est.info.load_mode == 2
+        est.set_debug(True)
+        got = np.zeros_like(want)
+        trig = np.zeros((T, S), dtype=bool)
+        for t in range(T):
+            got[t] = est.estimate(win[t], mid[t])
+            km, tr, _ = est.get_debug()
+            trig[t] = tr[:, 0]
+            if dtype == np.float64:
+                assert np.array_equal(km, km_want[t])
+        assert_frames_close(got, want, tol, f"N={N} K={cfg['n_bins']}")
+        if 75.0 < (cfg["n_bins"] - 2) * cfg["fs"] / N:                # interharmonic inside the analysed band:
+            assert trig[2].all()                                      # that frame ran the Q loop
+        again = multi.estimate_frames(win, mid)                       # one call, T launches
+        assert multi.launches == T
+        assert np.array_equal(again, got, equal_nan=True)
+
+
+def test_streaming_on_the_general_kernel():
+    cfg = dict(configs.DEFAULT_INI, n_bins=30, Q=2)
+    N, hop = configs.win_len(cfg), configs.hop(cfg)
+    S, T = 5, 6
+    rng = np.random.default_rng(3)
+    n_tot = N + (T - 1) * hop
+    tt = np.arange(n_tot) / cfg["fs"]
+    x = np.stack([(1 + 0.2 * s) * np.cos(2 * np.pi * (49.5 + 0.25 * s) * tt + 0.3 * s) for s in range(S)])
+    x += 1e-3 * rng.standard_normal(x.shape)
+    win = np.stack([x[:, t * hop:t * hop + N] for t in range(T)])[:, :, None, :]
+    mid = np.stack([np.full(S, ((t * hop + N // 2) % cfg["fs"]) / cfg["fs"]) for t in range(T)])
+    with BatchEstimator(cfg, S, 1) as a, BatchEstimator(cfg, S, 1) as b:
+        ref = np.stack([a.estimate(np.ascontiguousarray(win[t]), mid[t]) for t in range(T)])
+        b.stream_begin(hop=hop, max_frames_per_push=3, history=np.ascontiguousarray(x[:, None, :N - hop]), first_sample_index=0)
+        new = np.stack([x[:, N - hop + t * hop:N + t * hop] for t in range(T)])[:, :, None, :]
+        out = np.concatenate([b.stream_push(np.ascontiguousarray(new[i:i + 3])) for i in range(0, T, 3)])
+    assert np.array_equal(out, ref, equal_nan=True)
+
+
 def test_unsupported_configuration_fails_loudly():
-    cfg = dict(configs.DEFAULT_INI, n_cycles=30, n_bins=40)
+    cfg = dict(configs.DEFAULT_INI, fs=51200, n_cycles=8, n_bins=3000)     # legal for the reference (<= N/2 = 4096)
     with pytest.raises(RuntimeError):
         BatchEstimator(cfg, 2, 1)
 
