@@ -355,7 +355,7 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     const pmu::Derived& d = b->d;
     pp.K = (int)cfg->n_bins; pp.P = (int)cfg->P; pp.Q = (int)cfg->Q; pp.iter_en = cfg->iter_eipdft ? 1 : 0;
     pp.jlo = b->plan.jlo; pp.jhi = b->plan.jhi; pp.C = (int)n_channels; pp.f0 = (int)cfg->f0;
-    pp.df = d.df; pp.S = d.S; pp.invS = d.invS; pp.eps = d.eps; pp.invN = 1.0 / (double)d.N;
+    pp.df = d.df; pp.inv_df = 1.0 / d.df; pp.S = d.S; pp.invS = d.invS; pp.eps = d.eps; pp.invN = 1.0 / (double)d.N;
     {
         const long double pi = 3.14159265358979323846264338327950288L;
         pp.c3q = (double)(-0.25L * cosl(pi / (long double)d.N));  // cos(pi C3) = -cos(pi/N)

@@ -54,6 +54,80 @@ PMU_HD void pmu_sincospi(double x, double* s, double* c)
 #endif
 }
 
+#ifndef PMU_FAST_TRIG
+#define PMU_FAST_TRIG 1
+#endif
+
+// sin(pi x), cos(pi x) for |x| <= 1/2 (the Dirichlet anchor r of a sweep): Taylor polynomials of the half angle
+// (|pi x / 2| <= pi/4: truncation < 5e-17) and one angle doubling, 21 FMAs in two independent chains instead of
+// the general-range library routine.  x == 0 gives sin = 0 exactly, NaN propagates.
+PMU_HD void pmu_sincospi_half(double x, double* s, double* c)
+{
+#if PMU_FAST_TRIG
+    const double t = (0.5 * PMU_PI) * x;
+    const double u = t * t;
+    double sp = -7.6471637318198164759e-13;          // -1/15!
+    sp = fma(sp, u, 1.6059043836821614599e-10);      //  1/13!
+    sp = fma(sp, u, -2.5052108385441718775e-08);     // -1/11!
+    sp = fma(sp, u, 2.7557319223985890653e-06);      //  1/9!
+    sp = fma(sp, u, -1.9841269841269841270e-04);     // -1/7!
+    sp = fma(sp, u, 8.3333333333333333333e-03);      //  1/5!
+    sp = fma(sp, u, -1.6666666666666666667e-01);     // -1/3!
+    const double sh = fma(sp * u, t, t);
+    double cp = 4.7794773323873852974e-14;           //  1/16!
+    cp = fma(cp, u, -1.1470745597729724714e-11);     // -1/14!
+    cp = fma(cp, u, 2.0876756987868098979e-09);      //  1/12!
+    cp = fma(cp, u, -2.7557319223985890653e-07);     // -1/10!
+    cp = fma(cp, u, 2.4801587301587301587e-05);      //  1/8!
+    cp = fma(cp, u, -1.3888888888888888889e-03);     // -1/6!
+    cp = fma(cp, u, 4.1666666666666666667e-02);      //  1/4!
+    cp = fma(cp, u, -0.5);
+    const double ch = fma(cp, u, 1.0);
+    *s = 2.0 * sh * ch;
+    *c = (ch - sh) * (ch + sh);
+#else
+    pmu_sincospi(x, s, c);
+#endif
+}
+
+// sin(pi x), cos(pi x) for |pi x| <= 0.1 (the r/N arguments of windows of >= 16 samples): truncation < 3e-17.
+PMU_HD void pmu_sincospi_small(double x, double* s, double* c)
+{
+#if PMU_FAST_TRIG
+    const double t = PMU_PI * x;
+    const double u = t * t;
+    double sp = 2.7557319223985890653e-06;
+    sp = fma(sp, u, -1.9841269841269841270e-04);
+    sp = fma(sp, u, 8.3333333333333333333e-03);
+    sp = fma(sp, u, -1.6666666666666666667e-01);
+    *s = fma(sp * u, t, t);
+    double cp = -2.7557319223985890653e-07;
+    cp = fma(cp, u, 2.4801587301587301587e-05);
+    cp = fma(cp, u, -1.3888888888888888889e-03);
+    cp = fma(cp, u, 4.1666666666666666667e-02);
+    cp = fma(cp, u, -0.5);
+    *c = fma(cp, u, 1.0);
+#else
+    pmu_sincospi(x, s, c);
+#endif
+}
+
+// 1/x: hardware seed (~20 bits, full exponent range) + two Newton steps; 1/0 and 1/NaN give NaN here, which is what
+// the callers turn an infinite Dirichlet term into anyway (0 * inf).
+PMU_HD double pmu_rcp(double x)
+{
+#if PMU_FAST_TRIG && defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
+
 // Read-only parameters of the post-DFT stage (uniform over a batch).
 struct PostParams {
     int K;         // n_bins
@@ -62,7 +136,7 @@ struct PostParams {
     int jlo, jhi;  // trig table covers j in [-jlo, jhi]
     int C;         // channels per instance (mid_fracsec is per instance)
     int f0;
-    double df;
+    double df, inv_df;
     double S, invS;       // norm_factor and 1/norm_factor (src/pmu_estimator.c:150,160)
     double eps;           // interf_trig
     double invN;
@@ -107,7 +181,11 @@ struct Sweep {
 
     PMU_HD void init(const PostParams& p, double f, double z_re, double z_im)
     {
-        double q = f / p.df;  // same division as x = k - f/df (src/pmu_estimator.c:61)
+#if PMU_FAST_TRIG
+        double q = f * p.inv_df;  // x = k - f/df (src/pmu_estimator.c:61), to within an ulp of q
+#else
+        double q = f / p.df;
+#endif
         double ks = rint(q);
         const double lim = (double)(p.K + 1);
         if (!(ks >= -lim)) ks = -lim;  // also catches NaN: keeps table indices in range
@@ -115,8 +193,9 @@ struct Sweep {
         kstar = (int)ks;
         double r = ks - q;
         double spr, cpr;
-        pmu_sincospi(r, &spr, &cpr);
-        pmu_sincospi(r * p.invN, &sr, &cr);
+        pmu_sincospi_half(r, &spr, &cpr);
+        if (p.invN <= 1.0 / 16.0) pmu_sincospi_small(r * p.invN, &sr, &cr);
+        else pmu_sincospi_half(r * p.invN, &sr, &cr);
         // exp(-i pi C3 r) = exp(-i pi r) exp(+i pi r/N)
         double er = cpr * cr + spr * sr;
         double ei = cpr * sr - spr * cr;
@@ -129,7 +208,7 @@ struct Sweep {
     PMU_HD double inv_den(const PostParams& p, int j) const
     {
         pmu_c t = pmu_trig(p, j + p.jlo);
-        return 1.0 / (sr * t.x + cr * t.y);
+        return pmu_rcp(sr * t.x + cr * t.y);
     }
 
     // value at bin k given I[m-1], I[m], I[m+1]
@@ -173,9 +252,9 @@ PMU_HD int ipdft_finish(const PostParams& p, const Peak& pk, Tone* t)
     double mk = sqrt(pk.best);
     double ml = (pk.km == 0) ? mk : sqrt(pk.left);              // kl = km when km == 0 (:718)
     double mr = (pk.km == p.K - 1) ? ml : sqrt(pk.right);       // kr = km-1 at the last bin (:719)
-    double d = 2 * (mr - ml) / (ml + mr + 2 * mk);              // :598
+    double d = 2 * (mr - ml) * pmu_rcp(ml + mr + 2 * mk);       // :598
     t->freq = (pk.km + d) * p.df;                               // :601
-    double inv = 1.0 / mk;
+    double inv = pmu_rcp(mk);
     double ur = pk.yr * inv, ui = pk.yi * inv;                  // exp(i arg Y)
     if (fabs(d) <= 10e-12) {                                    // :603-613
         t->amp = mk;
@@ -184,8 +263,9 @@ PMU_HD int ipdft_finish(const PostParams& p, const Peak& pk, Tone* t)
         return 1;
     }
     double sd, cd;
-    pmu_sincospi(d, &sd, &cd);
-    t->amp = mk * fabs((d * d - 1) * (PMU_PI * d) / sd);        // :616
+    if (fabs(d) <= 0.5) pmu_sincospi_half(d, &sd, &cd);         // the usual case: the peak bin is the nearest one
+    else pmu_sincospi(d, &sd, &cd);
+    t->amp = mk * fabs((d * d - 1) * (PMU_PI * d) * pmu_rcp(sd));  // :616
     t->cr = ur * cd + ui * sd;                                  // :617  exp(i(arg Y - pi d))
     t->ci = ui * cd - ur * sd;
     return 0;

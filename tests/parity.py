@@ -16,6 +16,8 @@ TOL = {
     "f32": dict(amp_rel=1e-5, ph=1e-5, freq=1e-4, rocof=1e-2),
     # checker-vs-checker (same arithmetic, same libm): essentially bit-exact
     "tight": dict(amp_rel=1e-12, ph=1e-12, freq=1e-11, rocof=1e-9),
+    # two code paths of the float build with the same arithmetic: outputs may differ in the last float bit
+    "f32_ulp": dict(amp_rel=2.5e-7, ph=1e-6, freq=1e-5, rocof=1e-3),
 }
 
 
