@@ -64,10 +64,41 @@ static void window_bins_kc(int KC, const pmu::Plan& p, const std::vector<pmu_c>&
         case 24: window_bins<InT, M, 24>(p, U, V, x, raw); break;
     }
 }
+// The general kernel's bins (pmu_wide.cuh): a warp per bin, lane l sums the samples n = l + 32 i into four partial
+// sums with the table twiddle W_N^(k n mod N), then a butterfly over the lanes.
+template <typename InT>
+static void window_bins_wide(const pmu::Plan& p, const std::vector<pmu_c>& U, const InT* x, double* raw)
+{
+    const unsigned N = (unsigned)p.L;
+    for (int k = 0; k < p.Kp; ++k) {
+        double lr[32], li[32];
+        for (unsigned l = 0; l < 32; ++l) {
+            double sr[4] = {0, 0, 0, 0}, si[4] = {0, 0, 0, 0};
+            unsigned i = 0;
+            for (unsigned n = l; n < N; n += 32, ++i) {
+                const pmu_c tw = U[(size_t)(((unsigned long long)k * n) % N)];
+                sr[i & 3] += (double)x[n] * tw.x;
+                si[i & 3] += (double)x[n] * tw.y;
+            }
+            lr[l] = (sr[0] + sr[1]) + (sr[2] + sr[3]);
+            li[l] = (si[0] + si[1]) + (si[2] + si[3]);
+        }
+        for (int off = 16; off >= 1; off >>= 1) {
+            double nr[32], ni[32];
+            for (int l = 0; l < 32; ++l) { nr[l] = lr[l] + lr[l ^ off]; ni[l] = li[l] + li[l ^ off]; }
+            memcpy(lr, nr, sizeof lr);
+            memcpy(li, ni, sizeof li);
+        }
+        raw[2 * k] = lr[0];
+        raw[2 * k + 1] = li[0];
+    }
+}
+
 template <typename InT>
 static void window_bins_m(const pmu::Plan& p, const std::vector<pmu_c>& U, const std::vector<pmu_c>& V, const InT* x, double* raw)
 {
     switch (p.M) {
+        case 0: window_bins_wide<InT>(p, U, x, raw); break;
         case 16: window_bins_kc<InT, 16>(p.KC, p, U, V, x, raw); break;
         case 8: window_bins_kc<InT, 8>(p.KC, p, U, V, x, raw); break;
         case 4: window_bins_kc<InT, 4>(p.KC, p, U, V, x, raw); break;

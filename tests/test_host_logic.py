@@ -168,6 +168,10 @@ def test_kernel_arithmetic_golden_single_calls_and_spectrum():
     (dict(configs.DEFAULT_INI, fs=51200, n_cycles=16, n_bins=18), dict(M=16, KC=24, nslab=8)),
     (dict(configs.DEFAULT_INI, fs=51200, n_cycles=8, n_bins=18), dict(M=16, KC=24, nslab=4)),
     (dict(configs.DEFAULT_INI, f0=60, fs=4800, frame_rate=60, n_cycles=5, n_bins=9), dict(M=8, KC=12, nslab=1)),
+    # more than 23 bins: the general kernel's plan (M = 0, direct bins with the full twiddle table)
+    (dict(configs.DEFAULT_INI, n_bins=24), dict(M=0, KC=25, nslab=1)),
+    (dict(configs.DEFAULT_INI, n_cycles=30, n_bins=40, Q=2), dict(M=0, KC=41, nslab=1)),
+    (dict(configs.DEFAULT_INI, fs=4750, n_cycles=9, n_bins=33), dict(M=0, KC=34, nslab=1)),
 ])
 def test_plan_and_arithmetic_for_other_window_lengths(cfg, expect):
     N = configs.win_len(cfg)
