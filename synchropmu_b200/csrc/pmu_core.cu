@@ -4,6 +4,7 @@
 // device tables and per-stream ROCOF state resident in HBM — and launches the fused
 // kernel of pmu_kernel.cuh.  No CPU estimation path exists here: without a CUDA device
 // pmub_create fails.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -74,6 +75,48 @@ struct pmub_batch {
 int pmu_launch_f64(int M, int KC, const KernelArgs& a, int grid, int block, int smem, cudaStream_t s);
 int pmu_launch_f32(int M, int KC, const KernelArgs& a, int grid, int block, int smem, cudaStream_t s);
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder()
+{
+    static tmap_encode_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (tmap_encode_fn)p;
+    }();
+    return fn;
+}
+static_assert(sizeof(CUtensorMap) == sizeof(PmuTensorMap), "tensor map size");
+
+// Describe `rows` windows at `base` as the tensor [rows][M][L] with a box of one slab [1][M][W].  Returns false when the
+// geometry does not qualify (then the producer issues one bulk copy per row).
+static bool encode_window_tensor(const pmub_batch* b, const void* base, long long rows, PmuTensorMap* out)
+{
+    const pmu::Plan& p = b->plan;
+    static const int off = getenv("PMU_NO_TENSOR_MAP") ? atoi(getenv("PMU_NO_TENSOR_MAP")) : 0;
+    const bool whole = (p.nslab == 1 && p.pitch == p.L);   // one plain bulk copy per window already
+    if (off || p.M < 2 || whole || !p.aligned16 || p.pitch > 256 || p.W > p.pitch || rows < 1 || rows > 0x7fffffffll) return false;
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc || ((uintptr_t)base & 15u)) return false;
+    const cuuint64_t s = (cuuint64_t)b->dtype;
+    const cuuint64_t gdim[3] = {(cuuint64_t)p.L, (cuuint64_t)p.M, (cuuint64_t)rows};
+    const cuuint64_t gstride[2] = {(cuuint64_t)p.L * s, (cuuint64_t)b->d.N * s};
+    const cuuint32_t box[3] = {(cuuint32_t)p.pitch, (cuuint32_t)p.M, 1u};   // columns past L are zero-filled
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUtensorMap m;
+    const CUresult r = enc(&m, b->dtype == PMUB_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                           const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    memcpy(out, &m, sizeof m);
+    return true;
+}
+
 static int grid_for(const pmub_batch* b, long long n)
 {
     static const int forced = getenv("PMU_GRID") ? atoi(getenv("PMU_GRID")) : 0;
@@ -132,6 +175,10 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     a.load_mode = ok16 ? PMU_LOAD_BULK : PMU_LOAD_ELEM;
     static const int force_elem = getenv("PMU_FORCE_ELEM_LOAD") ? atoi(getenv("PMU_FORCE_ELEM_LOAD")) : 0;
     if (force_elem) a.load_mode = PMU_LOAD_ELEM;
+    a.use_tmap = 0;
+    if (!ring && a.load_mode == PMU_LOAD_BULK &&
+        encode_window_tensor(b, a.windows, (long long)(n_frames - 1) * b->n_windows + (w1 - w0), &a.tmap))
+        a.use_tmap = 1;
     int grid = grid_for(b, a.n_windows);
     if (b->plan.M == 0) {   // general kernel: one CTA per window, several resident per SM
         a.warp_per_window = 0;
@@ -366,7 +413,7 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     pp.lp0 = d.lp[0]; pp.lp1 = d.lp[1]; pp.lp2 = d.lp[2];
     pp.trig = b->dT;
     pp.trig_off = (unsigned)b->plan.off_trig;
-    a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
+    a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.pitch = b->plan.pitch; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
     a.n_stage = b->plan.n_stage; a.stage_bytes = b->plan.stage_bytes; a.n_cons = b->plan.n_cons;
     a.n_raw = b->plan.n_raw; a.raw_stride = b->plan.raw_stride; a.n_post = b->plan.n_post;
     a.n_u = b->plan.n_u;

@@ -298,7 +298,7 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
     if (p.M == 16) {
         // fixed row pitch: slabs are at most PMU_PITCH16 residues wide, rows PMU_PITCH16 elements apart
         p.pitch = PMU_PITCH16;
-        p.W = p.L < PMU_PITCH16 ? p.L : PMU_PITCH16;
+        p.W = p.L < p.pitch ? p.L : p.pitch;
         p.nslab = (p.L + p.W - 1) / p.W;
         p.stage_bytes = align_up(p.M * p.pitch * s, 128);
     } else {
@@ -335,9 +335,11 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
     int want_cons = env_int("PMU_CONSUMER_WARPS", PMU_MAX_CONSUMERS);
     if (want_cons < 1) want_cons = 1;
     if (want_cons > PMU_MAX_CONSUMERS) want_cons = PMU_MAX_CONSUMERS;
-    int want_raw = env_int("PMU_RAW_BUFFERS", 4);   // powers of two only (the kernel masks)
+    // Measured (profiles/r1_sweep_smem.jsonl): ring depth is worth more than spare estimator scratch - two raw-bin
+    // buffers and two estimator slots keep the seven consumer warps busy and leave room for two more stages.
+    int want_raw = env_int("PMU_RAW_BUFFERS", 2);   // powers of two only (the kernel masks)
     want_raw = want_raw >= 8 ? 8 : (want_raw >= 4 ? 4 : 2);
-    int want_post = env_int("PMU_POST_SLOTS", 4);
+    int want_post = env_int("PMU_POST_SLOTS", 2);
     if (want_post < 1) want_post = 1;
     if (want_post > PMU_MAX_POST) want_post = PMU_MAX_POST;
     int ns_cap = env_int("PMU_STAGES", PMU_MAX_STAGES);

@@ -36,10 +36,20 @@
 
 enum { PMU_LOAD_BULK = 0, PMU_LOAD_ELEM = 1 };
 
+// A CUtensorMap (driver API, 128 bytes, 64-byte aligned), kept opaque here so that this header needs no <cuda.h>.
+struct alignas(64) PmuTensorMap {
+    unsigned long long opaque[16];
+};
+
 struct KernelArgs {
+    // TMA descriptor of the launch's windows viewed as a 3-D tensor [rows][M][L] (row = frame * frame_stride + stream):
+    // one cp.async.bulk.tensor per slab instead of M row copies.  Valid when use_tmap != 0.
+    PmuTensorMap tmap;
+    int use_tmap;
     PostParams post;
     // DFT geometry
     int N, L, W, nslab, Kp;      // window length, residues (N/M), slab width, slabs per window, n_bins+1
+    int pitch;                   // stage row pitch in elements (compile-time in the 16-point-codelet kernels)
     int load_mode;               // PMU_LOAD_BULK / PMU_LOAD_ELEM
     int n_stage, stage_bytes;
     int n_cons;                  // consumer warps
@@ -138,6 +148,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// One box [1][M][W] of the windows tensor -> shared memory (rows W elements apart); out-of-range columns of the last
+// slab are zero-filled and still counted in the transaction bytes.
+__device__ __forceinline__ void tma_load_slab(void* dst, const PmuTensorMap* tmap, int col, int row, void* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(col), "r"(0), "r"(row)
+        : "memory");
 }
 // Copy `len` elements starting `off` elements into a window that begins at ring position `start`
 // of a ring of `cap` elements (cap == 0: plain linear window at `base`): one bulk copy, or two when
@@ -539,36 +559,48 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     if (warp == 0) {
         // ================= PRODUCER =================
         if (a.load_mode == PMU_LOAD_BULK) {
-            if (lane == 0) {
-                int st = 0, sl = 0, t = 0, f = 0;      // running (stage, slab, stream, frame) of slab i
-                uint32_t par = 0;
-                for (int i = 0; i < total_slabs; ++i) {
-                    mbar_wait(&ctrl->empty[st], par ^ 1u);
-                    unsigned char* dst = stages + (size_t)st * a.stage_bytes;
-                    const InT* src;
-                    long long start = 0;
-                    if (a.ring_cap == 0) {
-                        src = reinterpret_cast<const InT*>(a.windows) + ((size_t)f * a.frame_stride + (size_t)(w_begin + t)) * a.N;
-                    } else {
-                        src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + t) * a.ring_cap;
-                        start = (a.ring_start + (long long)f * a.hop) % a.ring_cap;
-                    }
-                    if (a.nslab == 1 && pitch == a.L) {
+            // A window that is already laid out at the stage pitch is one bulk copy (lane 0).  A slab is M row copies:
+            // lane b issues row b, so the address arithmetic of the rows runs in parallel instead of as one thread's
+            // serial chain (which capped multi-slab windows at ~13 M copies/s per SM).
+            const bool whole = (a.nslab == 1 && pitch == a.L);
+            int st = 0, sl = 0, t = 0, f = 0;      // running (stage, slab, stream, frame) of slab i
+            uint32_t par = 0;
+            for (int i = 0; i < total_slabs; ++i) {
+                if (lane == 0) mbar_wait(&ctrl->empty[st], par ^ 1u);
+                __syncwarp();
+                unsigned char* dst = stages + (size_t)st * a.stage_bytes;
+                const InT* src;
+                long long start = 0;
+                if (a.ring_cap == 0) {
+                    src = reinterpret_cast<const InT*>(a.windows) + ((size_t)f * a.frame_stride + (size_t)(w_begin + t)) * a.N;
+                } else {
+                    src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + t) * a.ring_cap;
+                    start = (a.ring_start + (long long)f * a.hop) % a.ring_cap;
+                }
+                if (whole) {
+                    if (lane == 0) {
                         mbar_expect_tx(&ctrl->full[st], (uint32_t)win_bytes);
                         bulk_segment<InT>(dst, src, start, a.ring_cap, 0, a.N, &ctrl->full[st]);
-                    } else {
-                        const int a_lo = sl * a.W;
-                        const int w_s = min(a.W, a.L - a_lo);
-                        mbar_expect_tx(&ctrl->full[st], (uint32_t)(w_s * sizeof(InT)) * M);
-                        for (int b = 0; b < M; ++b)
-                            bulk_segment<InT>(dst + (size_t)b * pitch * sizeof(InT), src, start, a.ring_cap, a_lo + a.L * b, w_s,
-                                              &ctrl->full[st]);
                     }
-                    if (++st == a.n_stage) { st = 0; par ^= 1u; }
-                    if (++sl == a.nslab) {
-                        sl = 0;
-                        if (++t == n_local) { t = 0; ++f; }
+                } else if (a.use_tmap) {
+                    // TMA-tiled: the copy engine walks the M rows of the slab itself
+                    if (lane == 0) {
+                        mbar_expect_tx(&ctrl->full[st], (uint32_t)(pitch * sizeof(InT)) * M);
+                        tma_load_slab(dst, &a.tmap, sl * a.W, (int)((long long)f * a.frame_stride + w_begin + t), &ctrl->full[st]);
                     }
+                } else {
+                    const int a_lo = sl * a.W;
+                    const int w_s = min(a.W, a.L - a_lo);
+                    if (lane == 0) mbar_expect_tx(&ctrl->full[st], (uint32_t)(w_s * sizeof(InT)) * M);
+                    __syncwarp();
+                    for (int b = lane; b < M; b += PMU_WARP)
+                        bulk_segment<InT>(dst + (size_t)b * pitch * sizeof(InT), src, start, a.ring_cap, a_lo + a.L * b, w_s,
+                                          &ctrl->full[st]);
+                }
+                if (++st == a.n_stage) { st = 0; par ^= 1u; }
+                if (++sl == a.nslab) {
+                    sl = 0;
+                    if (++t == n_local) { t = 0; ++f; }
                 }
             }
         } else {

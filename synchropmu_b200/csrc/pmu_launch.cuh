@@ -33,12 +33,12 @@ int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t
     return 0;
 }
 
-// The 16-point codelet always runs on stages with a fixed row pitch of PMU_PITCH16 elements
-// (the plan never makes its slabs wider), so its sample loads carry immediate offsets.
-template <typename T, int M>
+// The 16-point codelet always runs on stages with a fixed row pitch of PMU_PITCH16 elements (the plan never makes
+// its slabs wider), so its sample loads carry immediate offsets.  (A 64-element pitch for 1024- and 3072-sample
+// windows was measured and dropped: no gain for 1024, 16 % slower for 3072 - profiles/r1_sweep_smem.jsonl.)
+template <typename T, int M, int PITCH>
 int launch_kc(int KC, const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
 {
-    constexpr int PITCH = (M == 16) ? PMU_PITCH16 : 0;
     switch (KC) {
         case 8: return launch_inst<T, M, 8, PITCH>(a, grid, block, smem, s);
         case 12: return launch_inst<T, M, 12, PITCH>(a, grid, block, smem, s);
@@ -76,10 +76,10 @@ int launch_m(int M, int KC, const KernelArgs& a, int grid, int block, int smem, 
 {
     switch (M) {
         case 0: return launch_wide<T>(a, grid, smem, s);
-        case 16: return launch_kc<T, 16>(KC, a, grid, block, smem, s);
-        case 8: return launch_kc<T, 8>(KC, a, grid, block, smem, s);
-        case 4: return launch_kc<T, 4>(KC, a, grid, block, smem, s);
-        case 1: return launch_kc<T, 1>(KC, a, grid, block, smem, s);
+        case 16: return launch_kc<T, 16, PMU_PITCH16>(KC, a, grid, block, smem, s);
+        case 8: return launch_kc<T, 8, 0>(KC, a, grid, block, smem, s);
+        case 4: return launch_kc<T, 4, 0>(KC, a, grid, block, smem, s);
+        case 1: return launch_kc<T, 1, 0>(KC, a, grid, block, smem, s);
     }
     pmu::set_error("[pmu_estimate] ERROR: unsupported DFT codelet specialisation");
     return -1;
