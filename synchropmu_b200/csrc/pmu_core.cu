@@ -38,6 +38,8 @@ struct pmub_batch {
     int num_sms;
     // device memory
     pmu_c *dU, *dV, *dT;
+    pmu_c* dU1;                 // U for one window per warp pass (small launches of a plan that packs windows)
+    int n_u1;
     double *st_fold, *st_dl0, *st_dl1;
     unsigned char* st_state;
     unsigned char* d_windows;   // staging for host inputs (lazy, grows with the frame count)
@@ -169,6 +171,11 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     // a handful of windows (the single-instance drop-in path): one warp per window end to end
     static const int wpw_max = getenv("PMU_WARP_PER_WINDOW_MAX") ? atoi(getenv("PMU_WARP_PER_WINDOW_MAX")) : 64;
     a.warp_per_window = (a.n_windows <= wpw_max && a.n_windows <= PMU_MAX_GROUPS && b->cfg.n_bins <= PMU_WARP) ? 1 : 0;
+    if (a.warp_per_window && b->plan.wp > 1) {   // the unpacked instantiation of the same plan
+        a.wp = 1;
+        a.U = b->dU1;
+        a.n_u = b->n_u1;
+    }
     // TMA bulk copies need 16-byte aligned sources; otherwise per-element cp.async
     bool ok16 = b->plan.aligned16 && (((uintptr_t)a.windows) % 16 == 0);
     if (ring) ok16 = ok16 && ((size_t)b->ring_cap * sz) % 16 == 0 && ((size_t)b->hop * sz) % 16 == 0;
@@ -282,7 +289,7 @@ static int free_batch(pmub_batch* b)
 {
     if (!b) return 0;
     cudaSetDevice(b->device);
-    cudaFree(b->dU); cudaFree(b->dV); cudaFree(b->dT);
+    cudaFree(b->dU); cudaFree(b->dV); cudaFree(b->dT); cudaFree(b->dU1);
     cudaFree(b->st_fold); cudaFree(b->st_dl0); cudaFree(b->st_dl1); cudaFree(b->st_state);
     cudaFree(b->d_windows); cudaFree(b->d_mid); cudaFree(b->d_out); cudaFree(b->d_frames); cudaFree(b->d_ring); cudaFree(b->d_push);
     cudaFree(b->d_dbg); cudaFree(b->d_spec); cudaFree(b->d_timeline);
@@ -372,6 +379,17 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     CK(cudaMemcpy(b->dU, U.data(), U.size() * sizeof(pmu_c), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(b->dV, V.data(), V.size() * sizeof(pmu_c), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(b->dT, T.data(), T.size() * sizeof(pmu_c), cudaMemcpyHostToDevice));
+    if (b->plan.wp > 1) {
+        // small launches run one window per warp (lane = bin estimator): same plan, twiddles for 32 lanes per window
+        pmu::Plan p1 = b->plan;
+        p1.wp = 1;
+        p1.n_u = ((p1.L + 31) / 32) * p1.KC;
+        std::vector<pmu_c> U1, V1, T1;
+        pmu::build_tables(p1, b->d.N, &U1, &V1, &T1);
+        b->n_u1 = p1.n_u;
+        CK(cudaMalloc(&b->dU1, U1.size() * sizeof(pmu_c)));
+        CK(cudaMemcpy(b->dU1, U1.data(), U1.size() * sizeof(pmu_c), cudaMemcpyHostToDevice));
+    }
     const size_t n = (size_t)b->n_windows;
     CK(cudaMalloc(&b->st_fold, n * sizeof(double)));
     CK(cudaMalloc(&b->st_dl0, n * sizeof(double)));
@@ -413,7 +431,7 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     pp.lp0 = d.lp[0]; pp.lp1 = d.lp[1]; pp.lp2 = d.lp[2];
     pp.trig = b->dT;
     pp.trig_off = (unsigned)b->plan.off_trig;
-    a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.pitch = b->plan.pitch; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
+    a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.pitch = b->plan.pitch; a.wp = b->plan.wp; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
     a.n_stage = b->plan.n_stage; a.stage_bytes = b->plan.stage_bytes; a.n_cons = b->plan.n_cons;
     a.n_raw = b->plan.n_raw; a.raw_stride = b->plan.raw_stride; a.n_post = b->plan.n_post;
     a.n_u = b->plan.n_u;

@@ -296,8 +296,9 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
     p.L = N / p.M;
 
     if (p.M == 16) {
-        // fixed row pitch: slabs are at most PMU_PITCH16 residues wide, rows PMU_PITCH16 elements apart
-        p.pitch = PMU_PITCH16;
+        // fixed row pitch: slabs are at most PMU_PITCH16 residues wide, rows PMU_PITCH16 elements apart; 1024-sample
+        // windows (64 residues) are kept at their natural pitch so that two of them share a warp pass (below)
+        p.pitch = (p.L == PMU_PITCH16_SHORT && env_int("PMU_PACK", 4) >= 2) ? PMU_PITCH16_SHORT : PMU_PITCH16;
         p.W = p.L < p.pitch ? p.L : p.pitch;
         p.nslab = (p.L + p.W - 1) / p.W;
         p.stage_bytes = align_up(p.M * p.pitch * s, 128);
@@ -316,6 +317,18 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
         p.pitch = p.W;
         p.stage_bytes = align_up(p.M * p.W * s, 128);
     }
+    // Short windows: four per warp pass (8 lanes each) - one bulk copy and one round of bookkeeping for four
+    // windows, no idle lanes in the last residue group.  Needs the natural-pitch layout of the 8-point-codelet
+    // kernels and a stage that still leaves the ring deep enough.
+    p.wp = 1;
+    if (p.M == 8 && p.nslab == 1 && p.pitch == p.L && env_int("PMU_PACK", 4) >= 4 && 4 * N * s <= 20 * 1024) {
+        p.wp = 4;
+        p.stage_bytes = align_up(p.wp * N * s, 128);
+    } else if (p.M == 16 && p.nslab == 1 && p.pitch == p.L && env_int("PMU_PACK", 4) >= 2 && 2 * N * s <= 16 * 1024) {
+        p.wp = 2;   // 1024-sample windows, and 2048-sample windows of the float build
+        p.stage_bytes = align_up(p.wp * N * s, 128);
+    }
+    const int lanes_per_window = 32 / p.wp;
     // TMA bulk copies: whole window when its rows are already contiguous at the stage pitch,
     // otherwise one copy per row; both need 16-byte granularity
     const bool whole = (p.nslab == 1 && p.pitch == p.L);
@@ -323,7 +336,8 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
                         : ((N * s) % 16 == 0 && (p.L * s) % 16 == 0 && (p.W * s) % 16 == 0 &&
                            ((p.L - (p.nslab - 1) * p.W) * s) % 16 == 0 && (p.pitch * s) % 16 == 0);
 
-    const int n_groups = (p.nslab == 1) ? (p.L + 31) / 32 : (p.nslab - 1) * (p.W / 32) + ((p.L - (p.nslab - 1) * p.W) + 31) / 32;
+    const int n_groups = (p.nslab == 1) ? (p.L + lanes_per_window - 1) / lanes_per_window
+                                        : (p.nslab - 1) * (p.W / 32) + ((p.L - (p.nslab - 1) * p.W) + 31) / 32;
     p.n_u = n_groups * p.KC;
     p.jlo = K + 2;
     p.jhi = 2 * K + 1;
@@ -399,7 +413,8 @@ void build_tables(const Plan& p, unsigned N, std::vector<pmu_c>* U, std::vector<
     const int n_groups = p.M == 0 ? 0 : p.n_u / p.KC;
     if (p.M != 0) U->resize((size_t)p.n_u);
     for (int g = 0; g < n_groups; ++g)
-        for (int k = 0; k < p.KC; ++k) (*U)[(size_t)g * p.KC + k] = w(32ull * (unsigned long long)g * (unsigned long long)k);
+        for (int k = 0; k < p.KC; ++k)
+            (*U)[(size_t)g * p.KC + k] = w((unsigned long long)(32 / p.wp) * (unsigned long long)g * (unsigned long long)k);
     if (p.M != 0) V->resize((size_t)p.KC * 32);
     for (int k = 0; p.M != 0 && k < p.KC; ++k)
         for (int l = 0; l < 32; ++l) (*V)[(size_t)k * 32 + l] = w((unsigned long long)l * (unsigned long long)k);

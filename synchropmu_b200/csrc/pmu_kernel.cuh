@@ -29,7 +29,8 @@
 #endif
 #define PMU_MAX_CONSUMERS (PMU_BLOCK_THREADS / PMU_WARP - 1)
 #define PMU_MAX_STAGES 16
-#define PMU_PITCH16 128  // stage row pitch (elements) of the 16-point-codelet kernels
+#define PMU_PITCH16 128       // stage row pitch (elements) of the 16-point-codelet kernels
+#define PMU_PITCH16_SHORT 64  // ... for 1024-sample windows, stored at their natural pitch, two per warp pass
 #define PMU_MAX_RAW 8
 #define PMU_MAX_POST 8
 #define PMU_MAX_GROUPS 256  // groups of <= 32 streams per CTA when a launch carries several frames
@@ -50,6 +51,7 @@ struct KernelArgs {
     // DFT geometry
     int N, L, W, nslab, Kp;      // window length, residues (N/M), slab width, slabs per window, n_bins+1
     int pitch;                   // stage row pitch in elements (compile-time in the 16-point-codelet kernels)
+    int wp;                      // windows per warp pass (1, or 4 for short windows: 8 lanes per window)
     int load_mode;               // PMU_LOAD_BULK / PMU_LOAD_ELEM
     int n_stage, stage_bytes;
     int n_cons;                  // consumer warps
@@ -222,9 +224,9 @@ struct FastDiv {
 struct BatchMap {
     int nb, q, rem;  // batches, base size, number of batches with q+1 windows
     FastDiv by_q, by_q1;
-    __device__ __forceinline__ void init(int n)
+    __device__ __forceinline__ void init(int n, int cap = PMU_WARP)
     {
-        nb = (n + PMU_WARP - 1) / PMU_WARP;
+        nb = (n + cap - 1) / cap;
         if (nb < 1) nb = 1;
         q = n / nb;
         rem = n - q * nb;
@@ -499,9 +501,15 @@ __device__ __forceinline__ void load_residue(const InT* xs, int pitch, int a_loc
 // arithmetic); PITCH == 0: row pitch = a.W at run time.
 // CT: arithmetic type of the DFT stage (double; float for the float_p = float build) - everything from
 // the lane reduction on is double.
-template <typename InT, typename CT, int M, int KC, int PITCH>
+// WP: windows per warp pass.  Short windows (a few KB) are processed WP = 4 (or 2) at a time, 8 (16) lanes per window: the
+// per-pass costs (ticket, barrier round trip, stage release, batch bookkeeping) are paid once for four windows, no
+// lane idles in a masked residue group, and the four windows arrive in one bulk copy.  Only for single-slab windows
+// stored at their natural pitch (PITCH == 0 kernels).
+template <typename InT, typename CT, int M, int KC, int PITCH, int WP = 1>
 __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const __grid_constant__ KernelArgs a)
 {
+    // packed windows lie in the stage exactly as in memory (natural pitch); the plan guarantees pitch == L for them
+    constexpr int G = PMU_WARP / WP;   // lanes per window
     typedef typename CplxOf<CT>::type ccplx;
     unsigned char* smem = pmu_smem;
     CtrlBlock* ctrl = reinterpret_cast<CtrlBlock*>(smem + a.off_ctrl);
@@ -552,43 +560,53 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     if (n_local <= 0) return;
 
     const size_t win_bytes = (size_t)a.N * sizeof(InT);
-    const int n_items = n_local * a.n_frames;   // (frame, stream) pairs, frame-major
+    const int n_packs = (n_local + WP - 1) / WP;   // warp passes per frame (= streams when WP == 1)
+    const int n_items = n_packs * a.n_frames;      // (frame, pass) pairs, frame-major
     const int total_slabs = n_items * a.nslab;
     const int pitch = PITCH > 0 ? PITCH : a.W;
 
     if (warp == 0) {
         // ================= PRODUCER =================
         if (a.load_mode == PMU_LOAD_BULK) {
-            // A window that is already laid out at the stage pitch is one bulk copy (lane 0).  A slab is M row copies:
+            // A window that is already laid out at the stage pitch is one bulk copy (lane 0); WP such windows are
+            // consecutive in the caller's array and still one copy.  A slab is one tiled TMA copy, or M row copies:
             // lane b issues row b, so the address arithmetic of the rows runs in parallel instead of as one thread's
             // serial chain (which capped multi-slab windows at ~13 M copies/s per SM).
             const bool whole = (a.nslab == 1 && pitch == a.L);
-            int st = 0, sl = 0, t = 0, f = 0;      // running (stage, slab, stream, frame) of slab i
+            int st = 0, sl = 0, t = 0, f = 0;      // running (stage, slab, pass, frame) of slab i
             uint32_t par = 0;
             for (int i = 0; i < total_slabs; ++i) {
                 if (lane == 0) mbar_wait(&ctrl->empty[st], par ^ 1u);
                 __syncwarp();
                 unsigned char* dst = stages + (size_t)st * a.stage_bytes;
+                const int tw = t * WP;                                   // first stream of the pass
+                const int cnt = (WP == 1) ? 1 : min(WP, n_local - tw);   // streams in it
                 const InT* src;
                 long long start = 0;
                 if (a.ring_cap == 0) {
-                    src = reinterpret_cast<const InT*>(a.windows) + ((size_t)f * a.frame_stride + (size_t)(w_begin + t)) * a.N;
+                    src = reinterpret_cast<const InT*>(a.windows) + ((size_t)f * a.frame_stride + (size_t)(w_begin + tw)) * a.N;
                 } else {
-                    src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + t) * a.ring_cap;
+                    src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + tw) * a.ring_cap;
                     start = (a.ring_start + (long long)f * a.hop) % a.ring_cap;
                 }
                 if (whole) {
                     if (lane == 0) {
-                        mbar_expect_tx(&ctrl->full[st], (uint32_t)win_bytes);
-                        bulk_segment<InT>(dst, src, start, a.ring_cap, 0, a.N, &ctrl->full[st]);
+                        mbar_expect_tx(&ctrl->full[st], (uint32_t)(win_bytes * cnt));
+                        if (a.ring_cap == 0) {
+                            bulk_g2s(dst, src, (uint32_t)(win_bytes * cnt), &ctrl->full[st]);
+                        } else {
+                            for (int c = 0; c < cnt; ++c)
+                                bulk_segment<InT>(dst + (size_t)c * win_bytes, src + (size_t)c * a.ring_cap, start, a.ring_cap, 0, a.N,
+                                                  &ctrl->full[st]);
+                        }
                     }
-                } else if (a.use_tmap) {
+                } else if (WP == 1 && a.use_tmap) {
                     // TMA-tiled: the copy engine walks the M rows of the slab itself
                     if (lane == 0) {
                         mbar_expect_tx(&ctrl->full[st], (uint32_t)(pitch * sizeof(InT)) * M);
                         tma_load_slab(dst, &a.tmap, sl * a.W, (int)((long long)f * a.frame_stride + w_begin + t), &ctrl->full[st]);
                     }
-                } else {
+                } else if (WP == 1) {
                     const int a_lo = sl * a.W;
                     const int w_s = min(a.W, a.L - a_lo);
                     if (lane == 0) mbar_expect_tx(&ctrl->full[st], (uint32_t)(w_s * sizeof(InT)) * M);
@@ -600,7 +618,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 if (++st == a.n_stage) { st = 0; par ^= 1u; }
                 if (++sl == a.nslab) {
                     sl = 0;
-                    if (++t == n_local) { t = 0; ++f; }
+                    if (++t == n_packs) { t = 0; ++f; }
                 }
             }
         } else {
@@ -609,27 +627,40 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             for (int i = 0; i < total_slabs; ++i) {
                 mbar_wait(&ctrl->empty[st], par ^ 1u);
                 InT* dst = reinterpret_cast<InT*>(stages + (size_t)st * a.stage_bytes);
+                const int tw = t * WP;
+                const int cnt = (WP == 1) ? 1 : min(WP, n_local - tw);
                 const InT* src;
                 long long start = 0;
                 if (a.ring_cap == 0) {
-                    src = reinterpret_cast<const InT*>(a.windows) + ((size_t)f * a.frame_stride + (size_t)(w_begin + t)) * a.N;
+                    src = reinterpret_cast<const InT*>(a.windows) + ((size_t)f * a.frame_stride + (size_t)(w_begin + tw)) * a.N;
                 } else {
-                    src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + t) * a.ring_cap;
+                    src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + tw) * a.ring_cap;
                     start = (a.ring_start + (long long)f * a.hop) % a.ring_cap;
                 }
-                const int a_lo = sl * a.W;
-                const int w_s = min(a.W, a.L - a_lo);
-                for (int b = 0; b < M; ++b)
-                    for (int e = lane; e < w_s; e += PMU_WARP) {
-                        long long p = start + a_lo + (long long)a.L * b + e;
-                        if (a.ring_cap != 0 && p >= a.ring_cap) p -= a.ring_cap;
-                        cp_async_elem<(int)sizeof(InT)>(dst + (size_t)b * pitch + e, src + p);
-                    }
+                if constexpr (WP == 1) {
+                    const int a_lo = sl * a.W;
+                    const int w_s = min(a.W, a.L - a_lo);
+                    for (int b = 0; b < M; ++b)
+                        for (int e = lane; e < w_s; e += PMU_WARP) {
+                            long long p = start + a_lo + (long long)a.L * b + e;
+                            if (a.ring_cap != 0 && p >= a.ring_cap) p -= a.ring_cap;
+                            cp_async_elem<(int)sizeof(InT)>(dst + (size_t)b * pitch + e, src + p);
+                        }
+                } else {
+                    // natural pitch: the stage holds the cnt windows back to back, exactly as they lie in memory
+                    const size_t wstride = a.ring_cap == 0 ? (size_t)a.N : (size_t)a.ring_cap;
+                    for (int c = 0; c < cnt; ++c)
+                        for (int e = lane; e < a.N; e += PMU_WARP) {
+                            long long p = start + e;
+                            if (a.ring_cap != 0 && p >= a.ring_cap) p -= a.ring_cap;
+                            cp_async_elem<(int)sizeof(InT)>(dst + (size_t)c * a.N + e, src + (size_t)c * wstride + p);
+                        }
+                }
                 cp_async_mbar_arrive(&ctrl->full[st]);
                 if (++st == a.n_stage) { st = 0; par ^= 1u; }
                 if (++sl == a.nslab) {
                     sl = 0;
-                    if (++t == n_local) { t = 0; ++f; }
+                    if (++t == n_packs) { t = 0; ++f; }
                 }
             }
         }
@@ -640,10 +671,12 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     // ================= CONSUMERS =================
     unsigned long long* tl = a.timeline ? a.timeline + ((size_t)blockIdx.x * (PMU_BLOCK_THREADS / PMU_WARP) + warp) * 4 : nullptr;
     if (tl && lane == 0) { tl[0] = global_ns(); tl[1] = 0; }
-    BatchMap bm;
-    bm.init(n_local);
+    BatchMap bm;                          // batches of <= 32 streams = <= 32 / WP passes
+    bm.init(n_packs, PMU_WARP / WP);
     FastDiv by_nlocal, by_nstage;
-    by_nlocal.init((unsigned)n_local);
+    by_nlocal.init((unsigned)n_packs);
+    const int sub = lane / G;             // which stream of the pass this lane works on (0 when WP == 1)
+    const int gl = lane % G;              // its lane index within that stream's group
     by_nstage.init((unsigned)a.n_stage);
     const int w_per_it = a.W / PMU_WARP;  // full-slab residue groups (W % 32 == 0 when nslab > 1)
     const int raw_mask = a.n_raw - 1;     // n_raw is a power of two
@@ -663,7 +696,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             t = (int)r;
         }
 
-        // ---- pruned rectangular DFT of stream t, frame f ----
+        // ---- pruned rectangular DFT of pass t (streams t*WP ... t*WP + WP-1 of this CTA), frame f ----
         CT acc[2 * KC];  // ar = acc[0..KC), ai = acc[KC..2KC)
         CT* ar = acc;
         CT* ai = acc + KC;
@@ -680,13 +713,13 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             __syncwarp();
             mbar_wait(&ctrl->full[st], (uint32_t)(use & 1));
             if (tl && lane == 0 && tl[1] == 0) tl[1] = global_ns();
-            const InT* xs = reinterpret_cast<const InT*>(stages + (size_t)st * a.stage_bytes);
+            const InT* xs = reinterpret_cast<const InT*>(stages + (size_t)st * a.stage_bytes) + (WP == 1 ? 0 : sub * a.N);
             const int a_lo = sl * a.W;
             const int w_s = min(a.W, a.L - a_lo);
-            const int n_it = (w_s + PMU_WARP - 1) / PMU_WARP;
-            const bool all_full = (w_s % PMU_WARP) == 0;
+            const int n_it = (w_s + G - 1) / G;
+            const bool all_full = (w_s % G) == 0;
             for (int ii = 0; ii < n_it; ++ii) {
-                const int a_loc = lane + PMU_WARP * ii;
+                const int a_loc = gl + G * ii;
                 CT x[M];
                 if (all_full) load_residue<InT, CT, M, true>(xs, pitch, a_loc, w_s, x);
                 else load_residue<InT, CT, M, false>(xs, pitch, a_loc, w_s, x);
@@ -704,7 +737,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 mbar_arrive(&ctrl->empty[st]);
             }
         }
-        rotate_lane<KC, CT>(sV + lane, PMU_WARP, ar, ai);
+        rotate_lane<KC, CT>(sV + gl, PMU_WARP, ar, ai);
 
         // ---- sum the 32 lane partials through shared memory: every lane drops its KC complex
         //      partials into its row of the warp's scratch (128-bit stores, conflict-free row
@@ -720,7 +753,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                     my[k] = c;
                 }
         }
-        if (a.warp_per_window) {
+        if (WP == 1 && a.warp_per_window) {
             // small launch: this warp finishes its own window right away, lane = bin
             double* myrow = reinterpret_cast<double*>(smem + a.off_raw) + (size_t)(warp - 1) * a.raw_stride;
             __syncwarp();
@@ -755,7 +788,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             }
             continue;
         }
-        int g, slot, bsz, first_t;
+        int g, slot, bsz, first_t;                 // in passes; converted to streams below when WP > 1
         bm.locate(t, &g, &slot, &bsz, &first_t);
         const int gb = f * bm.nb + g;              // batch id over the whole launch, in ticket order
         const int rb = gb & raw_mask;
@@ -764,18 +797,22 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         }
         __syncwarp();
         __threadfence_block();
-        double* row = reinterpret_cast<double*>(smem + a.off_raw) + ((size_t)rb * PMU_WARP + slot) * a.raw_stride;
-        for (int c = lane; c < 2 * a.Kp; c += PMU_WARP) {
-            const CT* col = red + c;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;   // the column sums are always double
+        double* row = reinterpret_cast<double*>(smem + a.off_raw) + ((size_t)rb * PMU_WARP + slot * WP) * a.raw_stride;
 #pragma unroll
-            for (int l = 0; l < PMU_WARP; l += 4) {
-                s0 += (double)col[(l + 0) * RS];
-                s1 += (double)col[(l + 1) * RS];
-                s2 += (double)col[(l + 2) * RS];
-                s3 += (double)col[(l + 3) * RS];
+        for (int s2 = 0; s2 < WP; ++s2) {          // stream s2 of the pass: rows s2*G ... s2*G + G-1 of the scratch
+            if (WP > 1 && t * WP + s2 >= n_local) break;   // the CTA's last pass may be short
+            for (int c = lane; c < 2 * a.Kp; c += PMU_WARP) {
+                const CT* col = red + (size_t)s2 * G * RS + c;
+                double s0 = 0.0, s1 = 0.0, s2_ = 0.0, s3 = 0.0;   // the column sums are always double
+#pragma unroll
+                for (int l = 0; l < G; l += 4) {
+                    s0 += (double)col[(l + 0) * RS];
+                    s1 += (double)col[(l + 1) * RS];
+                    s2_ += (double)col[(l + 2) * RS];
+                    s3 += (double)col[(l + 3) * RS];
+                }
+                row[(size_t)s2 * a.raw_stride + c] = (s0 + s1) + (s2_ + s3);
             }
-            row[c] = (s0 + s1) + (s2 + s3);
         }
         __syncwarp();
         int done = 0;
@@ -785,6 +822,10 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         }
         done = __shfl_sync(0xffffffffu, done, 0);
         if (done == bsz) {
+            if constexpr (WP > 1) {                // passes -> streams
+                first_t *= WP;
+                bsz = min(bsz * WP, n_local - first_t);
+            }
             // ---- this warp post-processes batch (f, g) ----
             __threadfence_block();
             int ps = 0;

@@ -12,18 +12,18 @@
 
 namespace {
 
-template <typename T, int M, int KC, int PITCH>
+template <typename T, int M, int KC, int PITCH, int WP = 1>
 int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
 {
     static int configured[64];  // per device: dynamic smem already opted in for this instantiation
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess && (dev < 0 || dev >= 64 || configured[dev] != smem)) {
-        e = cudaFuncSetAttribute(pmu_fused_kernel<T, T, M, KC, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(pmu_fused_kernel<T, T, M, KC, PITCH, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev] = smem;
     }
     if (e == cudaSuccess) {
-        pmu_fused_kernel<T, T, M, KC, PITCH><<<grid, block, smem, s>>>(a);
+        pmu_fused_kernel<T, T, M, KC, PITCH, WP><<<grid, block, smem, s>>>(a);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) {
@@ -36,14 +36,14 @@ int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t
 // The 16-point codelet always runs on stages with a fixed row pitch of PMU_PITCH16 elements (the plan never makes
 // its slabs wider), so its sample loads carry immediate offsets.  (A 64-element pitch for 1024- and 3072-sample
 // windows was measured and dropped: no gain for 1024, 16 % slower for 3072 - profiles/r1_sweep_smem.jsonl.)
-template <typename T, int M, int PITCH>
+template <typename T, int M, int PITCH, int WP = 1>
 int launch_kc(int KC, const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
 {
     switch (KC) {
-        case 8: return launch_inst<T, M, 8, PITCH>(a, grid, block, smem, s);
-        case 12: return launch_inst<T, M, 12, PITCH>(a, grid, block, smem, s);
-        case 16: return launch_inst<T, M, 16, PITCH>(a, grid, block, smem, s);
-        case 24: return launch_inst<T, M, 24, PITCH>(a, grid, block, smem, s);
+        case 8: return launch_inst<T, M, 8, PITCH, WP>(a, grid, block, smem, s);
+        case 12: return launch_inst<T, M, 12, PITCH, WP>(a, grid, block, smem, s);
+        case 16: return launch_inst<T, M, 16, PITCH, WP>(a, grid, block, smem, s);
+        case 24: return launch_inst<T, M, 24, PITCH, WP>(a, grid, block, smem, s);
     }
     pmu::set_error("[pmu_estimate] ERROR: unsupported bin-count specialisation");
     return -1;
@@ -76,8 +76,18 @@ int launch_m(int M, int KC, const KernelArgs& a, int grid, int block, int smem, 
 {
     switch (M) {
         case 0: return launch_wide<T>(a, grid, smem, s);
-        case 16: return launch_kc<T, 16, PMU_PITCH16>(KC, a, grid, block, smem, s);
-        case 8: return launch_kc<T, 8, 0>(KC, a, grid, block, smem, s);
+        case 16:
+            // 1024-sample windows (64 residues): two per warp pass at their natural pitch
+            if (a.wp == 2 && a.pitch == PMU_PITCH16_SHORT) return launch_kc<T, 16, PMU_PITCH16_SHORT, 2>(KC, a, grid, block, smem, s);
+            if (a.pitch == PMU_PITCH16_SHORT) return launch_kc<T, 16, PMU_PITCH16_SHORT, 1>(KC, a, grid, block, smem, s);   // its small launches
+            if constexpr (sizeof(T) == 4) {   // 2048 floats = 8 KB: two windows per 16 KB stage
+                if (a.wp == 2 && a.pitch == PMU_PITCH16) return launch_kc<T, 16, PMU_PITCH16, 2>(KC, a, grid, block, smem, s);
+            }
+            return launch_kc<T, 16, PMU_PITCH16>(KC, a, grid, block, smem, s);
+        case 8:
+            // short windows: four per warp pass
+            if (a.wp == 4) return launch_kc<T, 8, 0, 4>(KC, a, grid, block, smem, s);
+            return launch_kc<T, 8, 0>(KC, a, grid, block, smem, s);
         case 4: return launch_kc<T, 4, 0>(KC, a, grid, block, smem, s);
         case 1: return launch_kc<T, 1, 0>(KC, a, grid, block, smem, s);
     }

@@ -63,10 +63,10 @@ def run(cfg: dict, windows: np.ndarray, mid: np.ndarray, dtype=np.float64, n_cha
     frames = np.zeros((T, S, 4))
     flags = np.zeros((T, S), dtype=np.int32)
     spec = np.zeros((T, S, K, 2))
-    plan = np.zeros(4, dtype=np.int32)
+    plan = np.zeros(5, dtype=np.int32)
     rc = lib.emul_run(C.byref(core_config(cfg)), np.dtype(dtype).itemsize, n_channels, S, T, w.ctypes.data,
                       m.ctypes.data, frames.ctypes.data, flags.ctypes.data, spec.ctypes.data, plan.ctypes.data)
     if rc != 0:
         raise RuntimeError("emul_run rejected the configuration")
     return frames, flags, spec[..., 0] + 1j * spec[..., 1], dict(M=int(plan[0]), KC=int(plan[1]),
-                                                                   nslab=int(plan[2]), W=int(plan[3]))
+                                                                   nslab=int(plan[2]), W=int(plan[3]), wp=int(plan[4]))

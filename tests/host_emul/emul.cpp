@@ -24,15 +24,16 @@ static void window_bins_r(const pmu::Plan& p, const std::vector<pmu_c>& Ud, cons
     double sum_r[KC], sum_i[KC];
     for (int k = 0; k < KC; ++k) sum_r[k] = sum_i[k] = 0.0;
     const int w_per_it = p.W / 32;
-    for (int lane = 0; lane < 32; ++lane) {
+    const int G = 32 / p.wp;   // lanes per window (8 when four short windows share a warp pass)
+    for (int lane = 0; lane < G; ++lane) {
         R ar[KC], ai[KC];
         bool first = true;
         for (int sl = 0; sl < p.nslab; ++sl) {
             const int a_lo = sl * p.W;
             const int w_s = (p.W < p.L - a_lo) ? p.W : p.L - a_lo;
-            const int n_it = (w_s + 31) / 32;
+            const int n_it = (w_s + G - 1) / G;
             for (int ii = 0; ii < n_it; ++ii) {
-                const int a_loc = lane + 32 * ii;
+                const int a_loc = lane + G * ii;
                 const bool valid = a_loc < w_s;
                 R xv[M];
                 for (int b = 0; b < M; ++b) xv[b] = valid ? (R)x[(size_t)(a_lo + a_loc) + (size_t)p.L * b] : (R)0;
@@ -111,7 +112,7 @@ extern "C" {
 // windows [T][S][N] (dtype), mid [T][S/C] (double), frames [T][S][4] (double),
 // flags [T][S], spectrum [T][S][K][2].  State starts fresh.  Returns 0 / -1.
 int emul_run(const pmub_config* cfg, int dtype, int n_channels, long n_streams, long n_frames, const void* windows,
-             const double* mid, double* frames, int* flags, double* spectrum, int* plan_out /* M, KC, nslab, W */)
+             const double* mid, double* frames, int* flags, double* spectrum, int* plan_out /* M, KC, nslab, W, wp */)
 {
     if (pmu::validate(*cfg)) return -1;
     pmu::Plan p;
@@ -119,7 +120,7 @@ int emul_run(const pmub_config* cfg, int dtype, int n_channels, long n_streams, 
     pmu::Derived d = pmu::derive(*cfg, dtype);
     std::vector<pmu_c> U, V, T;
     pmu::build_tables(p, d.N, &U, &V, &T);
-    if (plan_out) { plan_out[0] = p.M; plan_out[1] = p.KC; plan_out[2] = p.nslab; plan_out[3] = p.W; }
+    if (plan_out) { plan_out[0] = p.M; plan_out[1] = p.KC; plan_out[2] = p.nslab; plan_out[3] = p.W; plan_out[4] = p.wp; }
 
     PostParams pp;
     memset(&pp, 0, sizeof pp);

@@ -425,7 +425,7 @@ def test_warp_per_window_path_equals_batched_path(cfgname, dtype):
     """Launches of <= 64 windows (the pmu_estimate drop-in path) run the estimator with lane = bin and a warp-shuffle
     argmax; bigger launches run it with lane = window.  Same formulas per bin (the compiler may contract the FMAs of the
     two instantiations differently): the first 8 instances must agree to ~1e-12 whether they are estimated alone or inside
-    a batch of 40, frame after frame, with identical peak bins, trigger decisions and spectra; a multi-frame small launch
+    a batch of 40, frame after frame, with identical peak bins and trigger decisions; a multi-frame small launch
     must reproduce the frame-by-frame small launches bit for bit (ROCOF state included)."""
     cfg = configs.NAMED[cfgname]
     T = 6
@@ -441,7 +441,9 @@ def test_warp_per_window_path_equals_batched_path(cfgname, dtype):
             kma, tra, spa = small.get_debug()
             kmb, trb, spb = big.get_debug()
             assert np.array_equal(kma, kmb[:8]) and np.array_equal(tra, trb[:8]), (cfgname, t)
-            assert np.array_equal(spa, spb[:8]), (cfgname, t)
+            # (plans that pack several short windows into a warp pass sum the lane partials in a different order)
+            scale = np.abs(spb[:8]).max()
+            assert np.abs(spa - spb[:8]).max() <= (1e-13 if dtype == np.float64 else 2e-6) * scale, (cfgname, t)
             assert_frames_close(a, b[:8], "tight" if dtype == np.float64 else "f32_ulp", f"{cfgname} frame {t}")
         # several frames in one small launch: frame-to-frame state hand-over between warps
         c = small_multi.estimate_frames(np.ascontiguousarray(win[:, :8]), np.ascontiguousarray(mid[:, :8]))

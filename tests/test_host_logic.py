@@ -162,8 +162,9 @@ def test_kernel_arithmetic_golden_single_calls_and_spectrum():
 @pytest.mark.parametrize("cfg,expect", [
     (configs.DEFAULT_INI, dict(M=16, KC=12, nslab=1)),
     (configs.M_CLASS_INI, dict(M=16, KC=12, nslab=2)),
-    (configs.CFG5_600, dict(M=8, KC=12, nslab=1)),
-    (configs.P_CLASS_INI, dict(M=16, KC=8, nslab=1)),
+    (configs.CFG5_600, dict(M=8, KC=12, nslab=1, wp=4)),             # short windows: four per warp pass
+    (configs.DEFAULT_INI, dict(wp=1)),
+    (configs.P_CLASS_INI, dict(M=16, KC=8, nslab=1, W=64, wp=2)),       # 1024 samples: two windows per warp pass
     (dict(configs.DEFAULT_INI, fs=4750, n_cycles=3, n_bins=7), dict(M=1, KC=8, nslab=1)),
     (dict(configs.DEFAULT_INI, fs=51200, n_cycles=16, n_bins=18), dict(M=16, KC=24, nslab=8)),
     (dict(configs.DEFAULT_INI, fs=51200, n_cycles=8, n_bins=18), dict(M=16, KC=24, nslab=4)),
