@@ -284,6 +284,7 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
     const int s = dtype;
     p.Kp = K + 1;
     if (p.Kp <= 8) p.KC = 8;
+    else if (p.Kp <= 10) p.KC = 10;
     else if (p.Kp <= 12) p.KC = 12;
     else if (p.Kp <= 16) p.KC = 16;
     else if (p.Kp <= 24) p.KC = 24;

@@ -41,6 +41,7 @@ int launch_kc(int KC, const KernelArgs& a, int grid, int block, int smem, cudaSt
 {
     switch (KC) {
         case 8: return launch_inst<T, M, 8, PITCH, WP>(a, grid, block, smem, s);
+        case 10: return launch_inst<T, M, 10, PITCH, WP>(a, grid, block, smem, s);
         case 12: return launch_inst<T, M, 12, PITCH, WP>(a, grid, block, smem, s);
         case 16: return launch_inst<T, M, 16, PITCH, WP>(a, grid, block, smem, s);
         case 24: return launch_inst<T, M, 24, PITCH, WP>(a, grid, block, smem, s);

@@ -60,6 +60,7 @@ static void window_bins_kc(int KC, const pmu::Plan& p, const std::vector<pmu_c>&
 {
     switch (KC) {
         case 8: window_bins<InT, M, 8>(p, U, V, x, raw); break;
+        case 10: window_bins<InT, M, 10>(p, U, V, x, raw); break;
         case 12: window_bins<InT, M, 12>(p, U, V, x, raw); break;
         case 16: window_bins<InT, M, 16>(p, U, V, x, raw); break;
         case 24: window_bins<InT, M, 24>(p, U, V, x, raw); break;

@@ -162,13 +162,13 @@ def test_kernel_arithmetic_golden_single_calls_and_spectrum():
 @pytest.mark.parametrize("cfg,expect", [
     (configs.DEFAULT_INI, dict(M=16, KC=12, nslab=1)),
     (configs.M_CLASS_INI, dict(M=16, KC=12, nslab=2)),
-    (configs.CFG5_600, dict(M=8, KC=12, nslab=1, wp=4)),             # short windows: four per warp pass
+    (configs.CFG5_600, dict(M=8, KC=10, nslab=1, wp=4)),             # short windows: four per warp pass
     (configs.DEFAULT_INI, dict(wp=1)),
     (configs.P_CLASS_INI, dict(M=16, KC=8, nslab=1, W=64, wp=2)),       # 1024 samples: two windows per warp pass
     (dict(configs.DEFAULT_INI, fs=4750, n_cycles=3, n_bins=7), dict(M=1, KC=8, nslab=1)),
     (dict(configs.DEFAULT_INI, fs=51200, n_cycles=16, n_bins=18), dict(M=16, KC=24, nslab=8)),
     (dict(configs.DEFAULT_INI, fs=51200, n_cycles=8, n_bins=18), dict(M=16, KC=24, nslab=4)),
-    (dict(configs.DEFAULT_INI, f0=60, fs=4800, frame_rate=60, n_cycles=5, n_bins=9), dict(M=8, KC=12, nslab=1)),
+    (dict(configs.DEFAULT_INI, f0=60, fs=4800, frame_rate=60, n_cycles=5, n_bins=9), dict(M=8, KC=10, nslab=1, wp=4)),
     # more than 23 bins: the general kernel's plan (M = 0, direct bins with the full twiddle table)
     (dict(configs.DEFAULT_INI, n_bins=24), dict(M=0, KC=25, nslab=1)),
     (dict(configs.DEFAULT_INI, n_cycles=30, n_bins=40, Q=2), dict(M=0, KC=41, nslab=1)),
