@@ -300,6 +300,8 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
         // fixed row pitch: slabs are at most PMU_PITCH16 residues wide, rows PMU_PITCH16 elements apart; 1024-sample
         // windows (64 residues) are kept at their natural pitch so that two of them share a warp pass (below)
         p.pitch = (p.L == PMU_PITCH16_SHORT && env_int("PMU_PACK", 4) >= 2) ? PMU_PITCH16_SHORT : PMU_PITCH16;
+        // a multiple of 96 residues that is not one of 128 (M-class: 3072 = 192 x 16): 96-wide slabs fill every stage
+        if (p.L % PMU_PITCH16_96 == 0 && p.L % PMU_PITCH16 != 0 && env_int("PMU_PITCH96", 1)) p.pitch = PMU_PITCH16_96;
         p.W = p.L < p.pitch ? p.L : p.pitch;
         p.nslab = (p.L + p.W - 1) / p.W;
         p.stage_bytes = align_up(p.M * p.pitch * s, 128);
@@ -325,7 +327,8 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
     if (p.M == 8 && p.nslab == 1 && p.pitch == p.L && env_int("PMU_PACK", 4) >= 4 && 4 * N * s <= 20 * 1024) {
         p.wp = 4;
         p.stage_bytes = align_up(p.wp * N * s, 128);
-    } else if (p.M == 16 && p.nslab == 1 && p.pitch == p.L && env_int("PMU_PACK", 4) >= 2 && 2 * N * s <= 16 * 1024) {
+    } else if (p.M == 16 && p.nslab == 1 && p.pitch == p.L && (p.pitch == PMU_PITCH16_SHORT || (p.pitch == PMU_PITCH16 && s == 4)) &&
+               env_int("PMU_PACK", 4) >= 2 && 2 * N * s <= 16 * 1024) {
         p.wp = 2;   // 1024-sample windows, and 2048-sample windows of the float build
         p.stage_bytes = align_up(p.wp * N * s, 128);
     }

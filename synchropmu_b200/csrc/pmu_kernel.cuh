@@ -31,6 +31,7 @@
 #define PMU_MAX_STAGES 16
 #define PMU_PITCH16 128       // stage row pitch (elements) of the 16-point-codelet kernels
 #define PMU_PITCH16_SHORT 64  // ... for 1024-sample windows, stored at their natural pitch, two per warp pass
+#define PMU_PITCH16_96 96     // ... for windows of a multiple of 96 (not 128) residues: M-class 3072 = 2 x 96 x 16
 #define PMU_MAX_RAW 8
 #define PMU_MAX_POST 8
 #define PMU_MAX_GROUPS 256  // groups of <= 32 streams per CTA when a launch carries several frames

@@ -81,6 +81,7 @@ int launch_m(int M, int KC, const KernelArgs& a, int grid, int block, int smem, 
             // 1024-sample windows (64 residues): two per warp pass at their natural pitch
             if (a.wp == 2 && a.pitch == PMU_PITCH16_SHORT) return launch_kc<T, 16, PMU_PITCH16_SHORT, 2>(KC, a, grid, block, smem, s);
             if (a.pitch == PMU_PITCH16_SHORT) return launch_kc<T, 16, PMU_PITCH16_SHORT, 1>(KC, a, grid, block, smem, s);   // its small launches
+            if (a.pitch == PMU_PITCH16_96) return launch_kc<T, 16, PMU_PITCH16_96, 1>(KC, a, grid, block, smem, s);
             if constexpr (sizeof(T) == 4) {   // 2048 floats = 8 KB: two windows per 16 KB stage
                 if (a.wp == 2 && a.pitch == PMU_PITCH16) return launch_kc<T, 16, PMU_PITCH16, 2>(KC, a, grid, block, smem, s);
             }

@@ -161,7 +161,7 @@ def test_kernel_arithmetic_golden_single_calls_and_spectrum():
 
 @pytest.mark.parametrize("cfg,expect", [
     (configs.DEFAULT_INI, dict(M=16, KC=12, nslab=1)),
-    (configs.M_CLASS_INI, dict(M=16, KC=12, nslab=2)),
+    (configs.M_CLASS_INI, dict(M=16, KC=12, nslab=2, W=96)),          # 192 residues: two full 96-wide slabs
     (configs.CFG5_600, dict(M=8, KC=10, nslab=1, wp=4)),             # short windows: four per warp pass
     (configs.DEFAULT_INI, dict(wp=1)),
     (configs.P_CLASS_INI, dict(M=16, KC=8, nslab=1, W=64, wp=2)),       # 1024 samples: two windows per warp pass

@@ -13,7 +13,7 @@ from synchropmu_b200 import api, configs  # noqa: E402
 import tune  # noqa: E402
 
 lib = api.load_library()
-for cfgname in ("m_class_config.ini", "p_class_config.ini"):
+for cfgname in ("m_class_config.ini",):
     cfg = configs.NAMED[cfgname]
     for post in (1, 2):
         for raw in (2,):
@@ -22,4 +22,4 @@ for cfgname in ("m_class_config.ini", "p_class_config.ini"):
             n_inst = 4096 if cfgname != "cfg5_600" else 16384
             for fpl in (1, 8):
                 us, info = tune.time_case(cfg, n_inst, 6, lib, fpl=fpl, steps=160)
-                print(json.dumps(dict(narrow_max_l=os.environ.get("PMU_NARROW_PITCH_MAX_L"), cfg=cfgname, post=post, raw=raw, fpl=fpl, stages=info.n_stages, us_per_frame=round(us, 2))), flush=True)
+                print(json.dumps(dict(pitch96=os.environ.get("PMU_PITCH96"), cfg=cfgname, post=post, raw=raw, fpl=fpl, stages=info.n_stages, us_per_frame=round(us, 2))), flush=True)
