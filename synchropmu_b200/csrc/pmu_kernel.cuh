@@ -722,7 +722,8 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             for (int ii = 0; ii < n_it; ++ii) {
                 const int a_loc = gl + G * ii;
                 CT x[M];
-                if (all_full) load_residue<InT, CT, M, true>(xs, pitch, a_loc, w_s, x);
+                // only the last residue group of a slab can be partly out of range
+                if (all_full || ii + 1 < n_it) load_residue<InT, CT, M, true>(xs, pitch, a_loc, w_s, x);
                 else load_residue<InT, CT, M, false>(xs, pitch, a_loc, w_s, x);
                 const ccplx* u = sU + (size_t)(sl * w_per_it + ii) * KC;
                 if (first) {
