@@ -396,7 +396,7 @@ def test_config5_sharded_slice_600_samples():
 # several consecutive frames in one launch == the same frames one call at a time
 # ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cfgname,n_inst", [("config.ini", 7), ("config.ini", 900), ("m_class_config.ini", 150),
-                                           ("cfg5_600", 333)])
+                                           ("cfg5_600", 333), ("p_class_config.ini", 301)])
 def test_multi_frame_launch_equals_sequential_calls(cfgname, n_inst):
     torch = pytest.importorskip("torch")
     cfg = configs.NAMED[cfgname]
@@ -504,9 +504,10 @@ def _long_streams(cfg, n_streams, total, seed):
     (configs.DEFAULT_INI, "f64", 3, False),
     (configs.M_CLASS_INI, "f64", 2, False),
     (configs.CFG5_600, "f64", 4, True),
+    (configs.P_CLASS_INI, "f64", 3, False),
     (configs.DEFAULT_INI, "f32", 2, False),
     (dict(configs.DEFAULT_INI, fs=4750, n_cycles=3, n_bins=7), "f64", 2, False),   # odd hop: per-element loader
-], ids=["default_F1", "default_F3", "mclass_F2", "cfg5_F4", "float_F2", "oddhop_F2"])
+], ids=["default_F1", "default_F3", "mclass_F2", "cfg5_F4", "pclass_F3", "float_F2", "oddhop_F2"])
 def test_stream_push_equals_explicit_windows(cfg, dtype, F, given_mid):
     dt = DT[dtype]
     n_inst, C_ = 23, 6
@@ -532,6 +533,32 @@ def test_stream_push_equals_explicit_windows(cfg, dtype, F, given_mid):
         # differ by an ulp from the caller-side formula
         assert np.array_equal(got[..., [0, 2, 3]], want[..., [0, 2, 3]])
         assert np.max(np.abs(got[..., 1].astype(np.float64) - want[..., 1])) < (1e-11 if dtype == "f64" else 1e-5)
+
+
+@pytest.mark.parametrize("cfgname,dtype", [("cfg5_600", np.float64), ("p_class_config.ini", np.float64),
+                                           ("config.ini", np.float32), ("cfg5_600", np.float32)])
+def test_packed_short_windows_aligned_and_unaligned_sources_agree(cfgname, dtype):
+    """Plans that put several short windows into one warp pass: a source that is only element-aligned (per-element
+    loader, windows copied one by one into the pass's stage) must give the bits of the bulk-copy path, with a batch
+    size that leaves the last pass of some CTAs short."""
+    torch = pytest.importorskip("torch")
+    cfg = configs.NAMED[cfgname]
+    n_inst = 171                                        # 1026 windows: not a multiple of the pass size everywhere
+    win, mid = three_phase_batch(cfg, n_inst, 2, seed=5)
+    win, mid = win.astype(dtype), mid.astype(dtype)
+    with BatchEstimator(cfg, n_inst, 6, dtype=dtype) as a, BatchEstimator(cfg, n_inst, 6, dtype=dtype) as b:
+        assert a.info.load_mode == 0
+        for t in range(2):
+            dw = torch.from_numpy(win[t]).cuda()
+            dm = torch.from_numpy(mid[t]).cuda()
+            want = a.estimate(dw, dm).cpu().numpy()
+            pad = torch.empty(dw.numel() + 1, dtype=dw.dtype, device="cuda")
+            shifted = pad[1:]                           # element-aligned only
+            shifted.copy_(dw.reshape(-1))
+            got = b.estimate(shifted.reshape(dw.shape), dm).cpu().numpy()
+            assert np.array_equal(got, want, equal_nan=True), (cfgname, t)
+        want_cpu, _, _ = checker(dtype, 6).run(cfg, win[:, :20], mid[:, :20], n_threads=0)
+    assert_frames_close(got[:20], want_cpu[1], "f64" if dtype == np.float64 else "f32", cfgname)
 
 
 # ---------------------------------------------------------------------------------------
