@@ -187,10 +187,12 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
         encode_window_tensor(b, a.windows, (long long)(n_frames - 1) * b->n_windows + (w1 - w0), &a.tmap))
         a.use_tmap = 1;
     int grid = grid_for(b, a.n_windows);
-    if (b->plan.M == 0) {   // general kernel: one CTA per window, several resident per SM
+    if (b->plan.M == 0) {   // general kernel: one warp per window, plan.n_cons active warps per CTA
         a.warp_per_window = 0;
-        const long long cap = (long long)b->num_sms * 8;
-        grid = (int)(a.n_windows < cap ? a.n_windows : cap);
+        static const int no_fft = getenv("PMU_WIDE_DIRECT") ? atoi(getenv("PMU_WIDE_DIRECT")) : 0;
+        a.wide_fft = (!no_fft && b->d.N % 16 == 0 && b->d.N / 16 >= 32) ? 1 : 0;
+        const long long want = (a.n_windows + b->plan.n_cons - 1) / b->plan.n_cons, cap = (long long)b->num_sms * 2;
+        grid = (int)(want < cap ? want : cap);
     }
     if (a.warp_per_window && !getenv("PMU_GRID")) grid = (int)(a.n_windows < b->num_sms ? a.n_windows : b->num_sms);
     const int block = PMU_WARP * (1 + b->plan.n_cons);
@@ -466,7 +468,7 @@ int pmub_get_info(const pmub_batch* b, pmub_info* o)
     o->dft_radix = b->plan.M; o->dft_bins = b->plan.KC; o->n_stages = b->plan.n_stage;
     o->stage_bytes = b->plan.stage_bytes; o->slabs_per_window = b->plan.nslab;
     o->load_mode = b->plan.M == 0 ? 2 : (b->plan.aligned16 ? PMU_LOAD_BULK : PMU_LOAD_ELEM);
-    o->grid = grid_for(b, b->n_windows); o->block = PMU_WARP * (1 + b->plan.n_cons);
+    o->grid = grid_for(b, b->n_windows); o->block = b->plan.M == 0 ? 256 : PMU_WARP * (1 + b->plan.n_cons);
     o->smem_bytes = b->plan.smem_bytes;
     o->bytes_per_estimate = pmu::bytes_per_estimate(b->d.N, b->dtype, b->C);
     return 0;

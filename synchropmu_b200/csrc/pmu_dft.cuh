@@ -173,7 +173,9 @@ PMU_HD void ysel(const R* re, const R* im, R* yr, R* yi, bool* is_real)
 // Accumulate one residue: acc[k] (+)= U[k] * Y[k mod M], k < KC.
 //   FIRST : U == 1 for every k (i == 0), acc is initialised instead of accumulated.
 //   u     : lane-uniform twiddles W_N^{32 i k} (broadcast loads), ignored when FIRST.
-template <int M, int KC, bool FIRST, typename R>
+//   BIN0  : the first of the KC bins is bin 0 of the spectrum (twiddle 1, real codelet output: one add).  The general
+//           kernel accumulates later chunks of 16 bins (bins 16 c ... 16 c + 15, same k mod M) with BIN0 = false.
+template <int M, int KC, bool FIRST, typename R, bool BIN0 = true>
 PMU_HD void accumulate_residue(const R* x, const typename CplxOf<R>::type* u, R* ar, R* ai)
 {
     R re[M / 2 + 1], im[M / 2 + 1];
@@ -188,7 +190,7 @@ PMU_HD void accumulate_residue(const R* x, const typename CplxOf<R>::type* u, R*
         if constexpr (FIRST) {
             ar[k] = yr;
             ai[k] = is_real ? (R)0 : yi;
-        } else if constexpr (k == 0) {
+        } else if constexpr (k == 0 && BIN0) {
             ar[0] += yr;  // W^0 = 1, Y[0] real
         } else {
             const typename CplxOf<R>::type w = u[k];

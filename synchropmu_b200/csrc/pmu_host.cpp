@@ -241,8 +241,8 @@ static int env_int(const char* name, int dflt)
     return (s && *s) ? atoi(s) : dflt;
 }
 
-// Plan of the general kernel (pmu_wide.cuh, M == 0): one CTA per window, direct summation of the K+1 lowest bins
-// with a full table of W_N^m, estimator scratch in shared memory.  Takes every configuration the fused kernel
+// Plan of the general kernel (pmu_wide.cuh, M == 0): one warp per window, the K+1 lowest bins by chunks of 16 (pruned
+// FFT) or by direct summation with a full table of W_N^m, estimator scratch per warp in shared memory.  Takes every configuration the fused kernel
 // cannot (n_bins > 23), as long as the per-window scratch fits.
 static int make_wide_plan(const pmub_config& c, int max_smem, Plan* out)
 {
@@ -258,19 +258,23 @@ static int make_wide_plan(const pmub_config& c, int max_smem, Plan* out)
     p.jlo = K + 2;
     p.jhi = 2 * K + 1;
     p.raw_stride = 2 * p.Kp;
-    p.n_cons = 7;               // block = 32 * (1 + n_cons) = 256 threads
+    // shared memory: the trig table, then one scratch region per active warp (rectangular bins, X, W)
+    const int per_warp = align_up(align_up(2 * p.Kp * 8, 16) + 2 * K * 16, 128);
     int off = 0;
     p.off_ctrl = off;
     p.off_U = off; p.off_V = off;
     p.off_trig = off; off += align_up((p.jlo + p.jhi + 1) * 16, 128);
-    p.off_raw = off;  off += align_up(2 * p.Kp * 8, 128);
-    p.off_post = off; off += align_up(2 * K * 16, 128);
-    p.off_red = off; p.off_stage = off;
-    p.smem_bytes = off;
-    if (off > max_smem) {
+    p.off_raw = off;
+    p.off_post = off; p.off_red = off; p.off_stage = off;
+    int warps = (max_smem - off) / per_warp;
+    if (warps > 8) warps = 8;
+    if (warps < 1) {
         set_error("[pmu_init] ERROR: number of dft bins too large for the CUDA estimator's per-window scratch (about 2300 bins)");
         return -1;
     }
+    p.n_cons = warps;           // active warps per 256-thread CTA, one window each
+    p.stage_bytes = per_warp;
+    p.smem_bytes = off + warps * per_warp;
     *out = p;
     return 0;
 }

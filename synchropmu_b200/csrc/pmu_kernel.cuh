@@ -95,6 +95,7 @@ struct KernelArgs {
     // small launches (a few windows, e.g. the single-instance pmu_estimate): each warp runs the estimator of
     // the window it has just transformed, lane = bin (peak search = warp-shuffle argmax), no batching
     int warp_per_window;
+    int wide_fft;                // general kernel: 16 | N, bins by the pruned FFT instead of direct summation
     // profiling aid: [gridDim.x][warps][4] globaltimer stamps (setup done, first window ready,
     // tickets exhausted, warp exit); null in normal operation
     unsigned long long* timeline;
