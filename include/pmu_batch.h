@@ -63,7 +63,7 @@ typedef struct {
     double norm_factor;    /* sequential Hann sum, src/pmu_estimator.c:549-560           */
     /* how the kernel was specialised for this configuration */
     int dft_radix;         /* M: in-register real-FFT codelet size; 0 = the general kernel
-                              (n_bins > 23: direct summation, one CTA per window)        */
+                              (n_bins > 23: one warp per window, chunked pruned FFT)      */
     int dft_bins;          /* KC: rectangular bins accumulated per lane                  */
     int n_stages;          /* shared-memory ring depth                                   */
     int stage_bytes;

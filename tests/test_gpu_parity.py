@@ -171,7 +171,7 @@ def test_odd_window_length_and_wide_bins():
     (dict(n_bins=64, Q=2), np.float32),
 ])
 def test_many_bins_run_on_the_general_kernel(over, dtype):
-    """n_bins > 23 (legal per check_config_validity :386-449) is served by the one-CTA-per-window kernel: same parity bar,
+    """n_bins > 23 (legal per check_config_validity :386-449) is served by the one-warp-per-window kernel: same parity bar,
     explicit windows, a multi-frame call and the streaming front end."""
     cfg = dict(configs.DEFAULT_INI, **over)
     N, hop = configs.win_len(cfg), configs.hop(cfg)
