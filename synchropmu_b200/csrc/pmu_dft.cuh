@@ -131,28 +131,17 @@ struct RFFT {
             R er[H / 2 + 1], ei[H / 2 + 1], qr[H / 2 + 1], qi[H / 2 + 1];
             RFFT<H, R>::run(ev, er, ei);
             RFFT<H, R>::run(od, qr, qi);
-            static_for<0, H + 1>([&](auto kc) {
+            // X[k] = E[k] + W^k O[k] and X[H-k] = conj(E[k] - W^k O[k]) share the twiddle product; E[0], E[H/2],
+            // O[0], O[H/2] are real by symmetry
+            re[0] = er[0] + qr[0]; im[0] = 0;
+            re[H] = er[0] - qr[0]; im[H] = 0;
+            re[H / 2] = er[H / 2]; im[H / 2] = -qr[H / 2];          // W^(H/2) = -i
+            static_for<1, H / 2>([&](auto kc) {
                 constexpr int k = kc.value;
-                constexpr int kk = (k <= H / 2) ? k : H - k;
-                constexpr bool cj = (k > H / 2);
-                // E[0], E[H/2], O[0], O[H/2] are real by symmetry: drop their zero parts
-                constexpr bool real_in = (kk == 0) || (2 * kk == H);
-                R Er = er[kk], Ei = real_in ? (R)0 : (cj ? -ei[kk] : ei[kk]);
-                R Or = qr[kk], Oi = real_in ? (R)0 : (cj ? -qi[kk] : qi[kk]);
-                if constexpr (real_in) {
-                    constexpr int k16 = (k * (16 / M)) & 15;
-                    if constexpr (k16 == 0) { re[k] = Er + Or; im[k] = 0; }
-                    else if constexpr (k16 == 8) { re[k] = Er - Or; im[k] = 0; }
-                    else if constexpr (k16 == 4) { re[k] = Er; im[k] = -Or; }
-                    else {
-                        const R wr = cosv16<k16, R>(), wi = -sinv16<k16, R>();
-                        re[k] = Er + wr * Or; im[k] = wi * Or;
-                    }
-                } else {
-                    R tr, ti;
-                    tw_mul<k, M, R>(Or, Oi, &tr, &ti);
-                    re[k] = Er + tr; im[k] = Ei + ti;
-                }
+                R tr, ti;
+                tw_mul<k, M, R>(qr[k], qi[k], &tr, &ti);
+                re[k] = er[k] + tr;     im[k] = ei[k] + ti;
+                re[H - k] = er[k] - tr; im[H - k] = ti - ei[k];
             });
         }
     }
