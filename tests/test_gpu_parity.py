@@ -561,6 +561,62 @@ def test_packed_short_windows_aligned_and_unaligned_sources_agree(cfgname, dtype
     assert_frames_close(got[:20], want_cpu[1], "f64" if dtype == np.float64 else "f32", cfgname)
 
 
+def _random_valid_configs(n, seed):
+    """Configurations check_config_validity (:386-449) accepts, drawn to hit every kernel plan: 16/8/4/1-point codelets,
+    single- and multi-slab windows, packed short windows, 96-wide slabs, the general kernel (n_bins > 23)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        f0 = int(rng.choice([50, 60]))
+        fs = f0 * int(rng.choice([20, 25, 32, 37, 48, 64, 75, 96, 100, 128, 171, 200, 256, 320, 512, 1024]))
+        n_cycles = int(rng.integers(1, 13))
+        N = n_cycles * fs // f0
+        if N < 16 or N > 20000:
+            continue
+        hi = min(N // 2, n_cycles + 2 + int(rng.choice([0, 1, 3, 8, 20])))
+        if hi < n_cycles + 2:
+            continue
+        cfg = dict(n_cycles=n_cycles, f0=f0, frame_rate=int(rng.choice([f0, f0 // 2, 10])), fs=fs,
+                   n_bins=int(rng.integers(n_cycles + 2, hi + 1)), P=int(rng.integers(1, 4)), Q=int(rng.integers(1, 4)),
+                   interf_trig=float(rng.choice([0.0033, 0.02])), rocof_thresh=[3.0, 25.0, 0.035],
+                   rocof_low_pass_coeffs=[0.5913, 0.2043, 0.2043], iter_eipdft=int(rng.integers(0, 2)))
+        if api.validate(cfg):
+            out.append(cfg)
+    return out
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_valid_configurations_match_oracle(seed):
+    plans = set()
+    for cfg in _random_valid_configs(14, seed):
+        N = configs.win_len(cfg)
+        S, T = 77, 3                                  # 77 windows: > 64 (batched path), not a multiple of any pass size
+        rng = np.random.default_rng(N + seed)
+        f = cfg["f0"] + rng.uniform(-1.5, 1.5, S)
+        win = np.zeros((T, S, 1, N))
+        mid = np.zeros((T, S))
+        for t in range(T):
+            harm = [(0.1, 1.5 * cfg["f0"], 0.0)] if t == 1 else [(0.003, 3.0 * cfg["f0"], 0.5)]
+            win[t, :, 0, :] = signals.steady(cfg, t, 1 + rng.uniform(0, 1, S), f, rng.uniform(-3, 3, S), harmonics=harm)
+            mid[t] = signals.mid_fracsec(cfg, t)
+        win += 1e-4 * rng.standard_normal(win.shape)
+        want, km_want, _ = checker(np.float64, 1).run(cfg, win, mid, n_threads=0)
+        with BatchEstimator(cfg, S, 1) as est, BatchEstimator(cfg, S, 1) as multi:
+            i = est.info
+            plans.add((i.dft_radix, i.slabs_per_window > 1, i.load_mode))
+            est.set_debug(True)
+            seq = np.zeros_like(want)
+            for t in range(T):
+                seq[t] = est.estimate(win[t], mid[t])
+                km, _, _ = est.get_debug()
+                ok = ~np.isnan(want[t]).any(axis=-1)
+                assert np.array_equal(km[ok], km_want[t][ok]), (cfg, t)
+                assert_frames_close(seq[t], want[t], "f64", f"{cfg} frame {t}")
+            # the same frames in one call (one launch where the plan allows it): bit-identical
+            assert np.array_equal(multi.estimate_frames(win, mid), seq, equal_nan=True), cfg
+    assert len(plans) >= 4, plans                     # the draw really covered several kernel plans
+
+
 # ---------------------------------------------------------------------------------------
 # long runs and hostile inputs
 # ---------------------------------------------------------------------------------------
