@@ -333,7 +333,7 @@ __device__ __forceinline__ void finish_window(const KernelArgs& a, const Tone& f
     rs.dl0 = __ldcg(&a.st_dl0[w]);
     rs.dl1 = __ldcg(&a.st_dl1[w]);
     rs.st = __ldcg(&a.st_state[w]);
-    const double y = rocof_step(pp, f.freq, &rs);
+    const double y = sizeof(InT) == 4 ? rocof_step_f32(pp, f.freq, &rs) : rocof_step(pp, f.freq, &rs);
     a.st_fold[w] = rs.f_old;
     a.st_dl0[w] = rs.dl0;
     a.st_dl1[w] = rs.dl1;
@@ -442,7 +442,7 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, int po
         rs.dl0 = __ldcg(&a.st_dl0[w]);
         rs.dl1 = __ldcg(&a.st_dl1[w]);
         rs.st = __ldcg(&a.st_state[w]);
-        double y = rocof_step(pp, t.freq, &rs);
+        double y = sizeof(InT) == 4 ? rocof_step_f32(pp, t.freq, &rs) : rocof_step(pp, t.freq, &rs);
         a.st_fold[w] = rs.f_old;
         a.st_dl0[w] = rs.dl0;
         a.st_dl1[w] = rs.dl1;

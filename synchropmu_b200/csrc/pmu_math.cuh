@@ -440,6 +440,38 @@ PMU_HD double rocof_step(const PostParams& p, double freq, RocofState* s)
     return y;
 }
 
+// The same stage as the reference's float_p = float build executes it: every operand there is a float (phasor.freq,
+// freq_old, delay_line, thresholds, coefficients, (float)frame_rate), so each operation rounds to float and the state
+// it keeps is float.  The strict threshold tests of :240-241 sit on those rounded values - computing them in double
+// flips the state for a stream whose |ROCOF| lands within a float ulp of a threshold.  The state arrays stay double
+// in memory (floats are exact in them).
+#if defined(__CUDA_ARCH__)
+#define PMU_FMUL(a, b) __fmul_rn((a), (b))
+#define PMU_FADD(a, b) __fadd_rn((a), (b))
+#define PMU_FSUB(a, b) __fsub_rn((a), (b))
+#else
+PMU_HD float pmu_fround(float v) { volatile float t = v; return t; }   // host emulation: no contraction, no excess precision
+#define PMU_FMUL(a, b) pmu_fround((a) * (b))
+#define PMU_FADD(a, b) pmu_fround((a) + (b))
+#define PMU_FSUB(a, b) pmu_fround((a) - (b))
+#endif
+PMU_HD double rocof_step_f32(const PostParams& p, double freq, RocofState* s)
+{
+    const float f = (float)freq, f_old = (float)s->f_old, dl0 = (float)s->dl0, dl1 = (float)s->dl1;
+    const float fr = (float)p.frame_rate;
+    const float r = PMU_FMUL(PMU_FSUB(f, f_old), fr);                                        // :236
+    const float rd = PMU_FMUL(PMU_FSUB(r, dl0), fr);                                         // :237
+    if (!s->st && (fabsf(r) > (float)p.thr0 || fabsf(rd) > (float)p.thr1)) s->st = 1;        // :240
+    if (s->st && fabsf(r) < (float)p.thr2) s->st = 0;                                        // :241
+    float y = r;
+    if (!s->st)                                                                              // :246-248, left to right
+        y = PMU_FSUB(PMU_FADD(PMU_FMUL((float)p.lp1, r), PMU_FMUL((float)p.lp2, dl0)), PMU_FMUL((float)p.lp0, dl1));
+    s->f_old = (double)f;                                                                    // :256-260
+    s->dl0 = (double)r;
+    s->dl1 = (double)y;
+    return (double)y;
+}
+
 // wrap_angle (src/pmu_estimator.c:58): ties-to-even rint, range [-pi, pi].
 PMU_HD double wrap_angle_pi(double rad)
 {

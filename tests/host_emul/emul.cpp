@@ -154,7 +154,7 @@ int emul_run(const pmub_config* cfg, int dtype, int n_channels, long n_streams, 
             }
             Tone tone;
             int dbg = estimate_tone(pp, cx, cw, &tone);
-            double y = rocof_step(pp, tone.freq, &st[(size_t)s]);
+            double y = dtype == PMUB_F32 ? rocof_step_f32(pp, tone.freq, &st[(size_t)s]) : rocof_step(pp, tone.freq, &st[(size_t)s]);
             double m = mid[(size_t)t * (n_streams / n_channels) + s / n_channels];
             if (dtype == PMUB_F32) m = (double)(float)m;
             fill_frame(pp, tone, y, m, frames + u * 4);

@@ -60,3 +60,27 @@ def assert_frames_close(got, want, tol="f64", what=""):
     bad = {k: (e[k], t[k]) for k in t if e[k] > t[k]}
     assert not bad, f"{what}: parity gate exceeded {bad} (all errors {e})"
     return e
+
+
+def rocof_ambiguous(want, cfg, margin=2e-3):
+    """The ROCOF stage (src/pmu_estimator.c:236-260) is a two-state machine with strict threshold tests on
+    r = (f - f_old) frame_rate and on its difference.  In the float build a one-ulp difference in the frequency estimate
+    (3.8e-6 Hz at 60 Hz -> 2.3e-4 Hz/s in r) legitimately flips a decision that lies that close to a threshold, and the
+    stream's ROCOF then differs until the states meet again.  want [T, S, C, 4] (oracle frames) -> bool [T, S, C]: True
+    from the first frame on at which one of the oracle's own decisions is closer than `margin` to a threshold."""
+    w = np.asarray(want, dtype=np.float64)
+    fr = float(cfg["frame_rate"])
+    thr = [float(v) for v in cfg["rocof_thresh"]]
+    f_prev = np.full(w.shape[1:3], float(cfg["f0"]))
+    r_prev = np.zeros(w.shape[1:3])
+    amb = np.zeros(w.shape[:3], dtype=bool)
+    seen = np.zeros(w.shape[1:3], dtype=bool)
+    for t in range(w.shape[0]):
+        r = (w[t, ..., 2] - f_prev) * fr
+        rd = (r - r_prev) * fr
+        near = (np.abs(np.abs(r) - thr[0]) < margin) | (np.abs(np.abs(rd) - thr[1]) < margin * fr) | \
+               (np.abs(np.abs(r) - thr[2]) < margin)
+        seen |= near
+        amb[t] = seen
+        f_prev, r_prev = w[t, ..., 2], r
+    return amb

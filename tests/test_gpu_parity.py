@@ -16,7 +16,7 @@ import pytest
 
 import oracle_lib
 from oracle_lib import CpuChecker
-from parity import assert_frames_close, golden_floats
+from parity import assert_frames_close, golden_floats, rocof_ambiguous
 from stream_cases import STREAM_CASES, stream_case_windows
 from synchropmu_b200 import BatchEstimator, EstimatorConfig, PMUEstimator, api, configs, signals
 
@@ -585,9 +585,11 @@ def _random_valid_configs(n, seed):
     return out
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
-def test_random_valid_configurations_match_oracle(seed):
+@pytest.mark.parametrize("seed,dtype", [(1, np.float64), (2, np.float64), (3, np.float64), (4, np.float64), (5, np.float64),
+                                        (6, np.float64), (7, np.float32), (8, np.float32)])
+def test_random_valid_configurations_match_oracle(seed, dtype):
     plans = set()
+    tol = "f64" if dtype == np.float64 else "f32"
     for cfg in _random_valid_configs(14, seed):
         N = configs.win_len(cfg)
         S, T = 77, 3                                  # 77 windows: > 64 (batched path), not a multiple of any pass size
@@ -600,8 +602,10 @@ def test_random_valid_configurations_match_oracle(seed):
             win[t, :, 0, :] = signals.steady(cfg, t, 1 + rng.uniform(0, 1, S), f, rng.uniform(-3, 3, S), harmonics=harm)
             mid[t] = signals.mid_fracsec(cfg, t)
         win += 1e-4 * rng.standard_normal(win.shape)
-        want, km_want, _ = checker(np.float64, 1).run(cfg, win, mid, n_threads=0)
-        with BatchEstimator(cfg, S, 1) as est, BatchEstimator(cfg, S, 1) as multi:
+        win, mid = win.astype(dtype), mid.astype(dtype)
+        want, km_want, _ = checker(dtype, 1).run(cfg, win, mid, n_threads=0)
+        amb = rocof_ambiguous(want, cfg)
+        with BatchEstimator(cfg, S, 1, dtype=dtype) as est, BatchEstimator(cfg, S, 1, dtype=dtype) as multi:
             i = est.info
             plans.add((i.dft_radix, i.slabs_per_window > 1, i.load_mode))
             est.set_debug(True)
@@ -610,8 +614,18 @@ def test_random_valid_configurations_match_oracle(seed):
                 seq[t] = est.estimate(win[t], mid[t])
                 km, _, _ = est.get_debug()
                 ok = ~np.isnan(want[t]).any(axis=-1)
-                assert np.array_equal(km[ok], km_want[t][ok]), (cfg, t)
-                assert_frames_close(seq[t], want[t], "f64", f"{cfg} frame {t}")
+                if dtype == np.float64:
+                    assert np.array_equal(km[ok], km_want[t][ok]), (cfg, t)
+                    assert_frames_close(seq[t], want[t], tol, f"{cfg} frame {t}")
+                else:
+                    # float build: a one-ulp frequency difference may flip a ROCOF threshold decision that the oracle
+                    # itself takes within 2e-3 Hz/s of the threshold; those streams are compared without ROCOF
+                    clear = ~amb[t]
+                    assert clear.mean() > 0.8, cfg
+                    assert_frames_close(seq[t][clear], want[t][clear], tol, f"{cfg} frame {t}")
+                    g3, w3 = seq[t].copy(), want[t].copy()
+                    g3[..., 3] = w3[..., 3] = 0
+                    assert_frames_close(g3, w3, tol, f"{cfg} frame {t} (amp, phase, frequency of every stream)")
             # the same frames in one call (one launch where the plan allows it): bit-identical
             assert np.array_equal(multi.estimate_frames(win, mid), seq, equal_nan=True), cfg
     assert len(plans) >= 4, plans                     # the draw really covered several kernel plans
