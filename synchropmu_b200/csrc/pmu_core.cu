@@ -182,6 +182,8 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     a.load_mode = ok16 ? PMU_LOAD_BULK : PMU_LOAD_ELEM;
     static const int force_elem = getenv("PMU_FORCE_ELEM_LOAD") ? atoi(getenv("PMU_FORCE_ELEM_LOAD")) : 0;
     if (force_elem) a.load_mode = PMU_LOAD_ELEM;
+    static const int no_pdl = getenv("PMU_NO_PDL") ? atoi(getenv("PMU_NO_PDL")) : 0;
+    a.pdl = no_pdl ? 0 : 1;
     a.use_tmap = 0;
     if (!ring && a.load_mode == PMU_LOAD_BULK &&
         encode_window_tensor(b, a.windows, (long long)(n_frames - 1) * b->n_windows + (w1 - w0), &a.tmap))

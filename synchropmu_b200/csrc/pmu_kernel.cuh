@@ -96,6 +96,7 @@ struct KernelArgs {
     // the window it has just transformed, lane = bin (peak search = warp-shuffle argmax), no batching
     int warp_per_window;
     int wide_fft;                // general kernel: 16 | N, bins by the pruned FFT instead of direct summation
+    int pdl;                     // launched with programmatic stream serialization (see pmu_launch.cuh)
     // profiling aid: [gridDim.x][warps][4] globaltimer stamps (setup done, first window ready,
     // tickets exhausted, warp exit); null in normal operation
     unsigned long long* timeline;
@@ -524,6 +525,8 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     const int warp = tid / PMU_WARP;
     const int lane = tid % PMU_WARP;
     const int nthreads = blockDim.x;
+    // let the next launch in the stream be scheduled as soon as SMs free up (it waits for this grid to finish, above)
+    asm volatile("griddepcontrol.launch_dependents;");
 
     // contiguous, balanced range of streams for this CTA
     const long long w_begin = (a.n_windows * (long long)blockIdx.x) / gridDim.x;
@@ -558,6 +561,9 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         sV[i] = c;
     }
     for (int i = tid; i < a.post.jlo + a.post.jhi + 1; i += nthreads) sT[i] = a.trig[i];
+    // Everything above reads only this estimator's own tables.  From here on the kernel touches the caller's windows,
+    // the frames and the ROCOF state: wait for whatever precedes this launch in the stream (a no-op without PDL).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     if (n_local <= 0) return;
 

@@ -23,8 +23,21 @@ int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t
         if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev] = smem;
     }
     if (e == cudaSuccess) {
-        pmu_fused_kernel<T, T, M, KC, PITCH, WP><<<grid, block, smem, s>>>(a);
-        e = cudaGetLastError();
+        // Programmatic dependent launch: when the previous operation in the stream is a kernel, this grid's CTAs may be
+        // scheduled (and run their prologue: tables to shared memory, barrier set-up) before that kernel has drained;
+        // the kernel itself waits (griddepcontrol.wait) for its complete predecessor before it touches any input,
+        // output or state, so ordering is exactly stream order.
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)block);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = a.pdl ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, pmu_fused_kernel<T, T, M, KC, PITCH, WP>, a);
     }
     if (e != cudaSuccess) {
         pmu::set_error(std::string("[pmu_estimate] CUDA ERROR launching the estimator kernel: ") + cudaGetErrorString(e));
