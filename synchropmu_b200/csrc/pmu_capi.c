@@ -15,6 +15,10 @@
 #include "../../include/pmu_estimator.h"
 #include "../../include/pmu_batch.h"
 
+#ifndef M_PI /* strict ISO C modes do not define it */
+#define M_PI 3.14159265358979323846
+#endif
+
 /* internal entry points of pmu_core.cu (not part of the public headers) */
 int pmub_set_mirror(pmub_batch *b, int enable);
 const double *pmub_mirror(const pmub_batch *b);
