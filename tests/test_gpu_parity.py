@@ -631,6 +631,35 @@ def test_random_valid_configurations_match_oracle(seed, dtype):
     assert len(plans) >= 4, plans                     # the draw really covered several kernel plans
 
 
+def test_launch_ordering_with_producer_kernels_on_the_same_stream():
+    """Kernels are launched with programmatic stream serialization and wait on the device for their predecessor before
+    touching caller data.  Alternate a producer kernel that overwrites the ONE input buffer with our launch, many times
+    without synchronising: every frame set must belong to the input that was in the buffer in stream order."""
+    torch = pytest.importorskip("torch")
+    cfg = configs.DEFAULT_INI
+    n_inst, reps = 600, 24
+    win, mid = three_phase_batch(cfg, n_inst, 3, seed=13)
+    src = [torch.from_numpy(win[t]).cuda() for t in range(3)]
+    dm = torch.from_numpy(mid[0]).cuda()
+    with BatchEstimator(cfg, n_inst, 6) as ref:
+        want = []
+        for t in range(3):
+            ref.reset()
+            want.append(ref.estimate(src[t], dm).clone())          # torch tensor in -> torch tensor out
+    buf = torch.empty_like(src[0])
+    outs = [torch.empty((n_inst, 6, 4), dtype=torch.float64, device="cuda") for _ in range(reps)]
+    s = torch.cuda.Stream()
+    with BatchEstimator(cfg, n_inst, 6) as est, torch.cuda.stream(s):
+        est.set_stream(s.cuda_stream)
+        for i in range(reps):
+            torch.mul(src[i % 3], 1.0, out=buf)      # producer KERNEL (not a DMA copy) on the same stream, same buffer
+            est.estimate_async(buf, dm, outs[i])
+        s.synchronize()
+    # ROCOF carries state from launch to launch, so compare amplitude, phase and frequency (state-free)
+    for i in range(reps):
+        assert torch.equal(outs[i][..., :3], want[i % 3][..., :3]), i
+
+
 # ---------------------------------------------------------------------------------------
 # long runs and hostile inputs
 # ---------------------------------------------------------------------------------------
