@@ -647,13 +647,15 @@ def test_launch_ordering_with_producer_kernels_on_the_same_stream():
             ref.reset()
             want.append(ref.estimate(src[t], dm).clone())          # torch tensor in -> torch tensor out
     buf = torch.empty_like(src[0])
-    outs = [torch.empty((n_inst, 6, 4), dtype=torch.float64, device="cuda") for _ in range(reps)]
+    out = torch.empty((n_inst, 6, 4), dtype=torch.float64, device="cuda")
+    outs = [torch.empty_like(out) for _ in range(reps)]
     s = torch.cuda.Stream()
     with BatchEstimator(cfg, n_inst, 6) as est, torch.cuda.stream(s):
         est.set_stream(s.cuda_stream)
         for i in range(reps):
             torch.mul(src[i % 3], 1.0, out=buf)      # producer KERNEL (not a DMA copy) on the same stream, same buffer
-            est.estimate_async(buf, dm, outs[i])
+            est.estimate_async(buf, dm, out)         # ... and ONE frame buffer
+            torch.mul(out, 1.0, out=outs[i])         # consumer kernel reads it before the next launch may overwrite it
         s.synchronize()
     # ROCOF carries state from launch to launch, so compare amplitude, phase and frequency (state-free)
     for i in range(reps):
