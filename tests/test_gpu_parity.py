@@ -392,6 +392,32 @@ def test_config5_sharded_slice_600_samples():
     assert_frames_close(np.stack(got), want, "f64", "config5 sample")
 
 
+def test_config5_all_million_channels_on_one_gpu():
+    """BASELINE config 5 at its full size on ONE GPU: 174 763 instances x 6 = 1 048 578 channels of 600-sample windows
+    (5 GB of samples), two frames in one launch.  Sampled channels from the first, middle and last CTA ranges are
+    checked against the oracle; every output must be finite; the multi-frame launch equals frame-by-frame launches."""
+    torch = pytest.importorskip("torch")
+    cfg = configs.CFG5_600
+    n_inst, T = 174763, 2
+    dev = torch.device("cuda")
+    prm = signals.three_phase_params(n_inst, seed=5)
+    pt = {k: torch.as_tensor(v, device=dev) for k, v in prm.items()}
+    sample = np.unique(np.concatenate([np.arange(4), n_inst // 2 + np.arange(4), n_inst - 4 + np.arange(4),
+                                       np.random.default_rng(4).choice(n_inst, 12, replace=False)]))
+    idx = torch.as_tensor(sample, device=dev)
+    x = torch.stack([signals.steady(cfg, t, pt["amp"], pt["freq"], pt["phase"], xp=torch, ramp=pt["ramp"],
+                                    like=pt["amp"]).reshape(n_inst, 6, -1) for t in range(T)]).contiguous()
+    m = torch.stack([torch.full((n_inst,), signals.mid_fracsec(cfg, t), dtype=torch.float64, device=dev) for t in range(T)])
+    with BatchEstimator(cfg, n_inst, 6) as multi, BatchEstimator(cfg, n_inst, 6) as seq:
+        out = multi.estimate_frames(x, m)
+        assert multi.launches == 1
+        assert bool(torch.isfinite(out).all())
+        for t in range(T):
+            assert torch.equal(seq.estimate(x[t], m[t]), out[t])
+    want, _, _ = checker(np.float64, 6).run(cfg, x[:, idx].cpu().numpy(), m[:, idx].cpu().numpy(), n_threads=0)
+    assert_frames_close(out[:, idx].cpu().numpy(), want, "f64", "config5, 1M channels")
+
+
 # ---------------------------------------------------------------------------------------
 # several consecutive frames in one launch == the same frames one call at a time
 # ---------------------------------------------------------------------------------------
