@@ -435,7 +435,7 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     pp.lp0 = d.lp[0]; pp.lp1 = d.lp[1]; pp.lp2 = d.lp[2];
     pp.trig = b->dT;
     pp.trig_off = (unsigned)b->plan.off_trig;
-    a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.pitch = b->plan.pitch; a.wp = b->plan.wp; a.red_in_stage = b->plan.red_in_stage ? 1 : 0; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
+    a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.pitch = b->plan.pitch; a.wp = b->plan.wp; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
     a.n_stage = b->plan.n_stage; a.stage_bytes = b->plan.stage_bytes; a.n_cons = b->plan.n_cons;
     a.n_raw = b->plan.n_raw; a.raw_stride = b->plan.raw_stride; a.n_post = b->plan.n_post;
     a.n_u = b->plan.n_u;

@@ -354,14 +354,6 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
     // 128-bit stores of a quarter warp hit distinct banks
     p.red_stride = 2 * p.KC + 2;  // compile-time in the kernel (immediate LDS offsets)
 
-    // The 32 x (2 KC + 2) scratch of the lane reduction fits the stage whose samples the warp has just consumed: reusing
-    // it (the stage is released a fraction of a microsecond later) turns 47 KB into more ring stages.  Measured
-    // (profiles/r1_ab_red_in_stage.txt): worth 4 % for multi-slab windows (M-class: 11 -> 15 stages), a loss of 2-6 % for
-    // single-slab windows, whose 8-10 stages already cover the latency - so only the former use it.
-    // PMU_RED_IN_STAGE = 1 / 0 forces it on (where it fits) / off.
-    const int red_env = env_int("PMU_RED_IN_STAGE", -1);
-    p.red_in_stage = (red_env < 0 ? p.nslab > 1 : red_env != 0) && p.stage_bytes >= 32 * p.red_stride * 8;
-
     int want_cons = env_int("PMU_CONSUMER_WARPS", PMU_MAX_CONSUMERS);
     if (want_cons < 1) want_cons = 1;
     if (want_cons > PMU_MAX_CONSUMERS) want_cons = PMU_MAX_CONSUMERS;
@@ -386,7 +378,7 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
         p.off_trig = off; off += align_up((p.jlo + p.jhi + 1) * 16, 128);
         p.off_raw = off;  off += align_up(p.n_raw * 32 * p.raw_stride * 8, 128);
         p.off_post = off; off += align_up(p.n_post * 2 * K * 32 * 16, 128);
-        p.off_red = off;  off += p.red_in_stage ? 0 : align_up(p.n_cons * 32 * p.red_stride * 8, 128);
+        p.off_red = off;  off += align_up(p.n_cons * 32 * p.red_stride * 8, 128);
         p.off_stage = off;
         int ns = (max_smem - off) / p.stage_bytes;
         if (ns > ns_cap) ns = ns_cap;

@@ -37,7 +37,6 @@ struct Plan {
     int M, KC;          // codelet size, bins per lane
     int L, W, nslab;    // residues, slab width, slabs per window
     int pitch;          // stage row pitch in elements (PMU_PITCH16 for the 16-point codelet, else W)
-    bool red_in_stage;  // the lane-reduction scratch is the stage a warp has just consumed: no region of its own
     int wp;             // windows per warp pass: 4 for short single-slab windows (8 lanes per window), else 1
     int Kp;             // n_bins + 1
     int n_stage, stage_bytes;

@@ -97,7 +97,6 @@ struct KernelArgs {
     int warp_per_window;
     int wide_fft;                // general kernel: 16 | N, bins by the pruned FFT instead of direct summation
     int pdl;                     // launched with programmatic stream serialization (see pmu_launch.cuh)
-    int red_in_stage;            // the lane-reduction scratch is the stage the warp has just consumed (no own region)
     // profiling aid: [gridDim.x][warps][4] globaltimer stamps (setup done, first window ready,
     // tickets exhausted, warp exit); null in normal operation
     unsigned long long* timeline;
@@ -710,7 +709,6 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         CT* ar = acc;
         CT* ai = acc + KC;
         bool first = true;
-        int held_st = 0, held_use = 0;
         for (int sl = 0; sl < a.nslab; ++sl) {
             const int idx = item * a.nslab + sl;
             unsigned st_u;
@@ -743,11 +741,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 }
             }
             __syncwarp();
-            if (a.red_in_stage && sl + 1 == a.nslab) {
-                // keep the last stage: its samples are consumed, the lane reduction below uses it as scratch
-                held_st = st;
-                held_use = use;
-            } else if (lane == 0) {
+            if (lane == 0) {
                 *reinterpret_cast<volatile int*>(&ctrl->stage_seq[st]) = use + 1;
                 mbar_arrive(&ctrl->empty[st]);
             }
@@ -758,8 +752,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         //      partials into its row of the warp's scratch (128-bit stores, conflict-free row
         //      stride), then lane c adds up column c of the 32 rows and deposits the total ----
         constexpr int RS = 2 * KC + 2;  // row stride in CT elements: an odd number of complex slots
-        CT* red = a.red_in_stage ? reinterpret_cast<CT*>(stages + (size_t)held_st * a.stage_bytes)
-                                 : reinterpret_cast<CT*>(smem + a.off_red) + (size_t)(warp - 1) * PMU_WARP * RS;
+        CT* red = reinterpret_cast<CT*>(smem + a.off_red) + (size_t)(warp - 1) * PMU_WARP * RS;
         {
             ccplx* my = reinterpret_cast<ccplx*>(red + (size_t)lane * RS);
 #pragma unroll
@@ -769,45 +762,21 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                     my[k] = c;
                 }
         }
-        // column sums into registers (lane c <- column c of each stream's G rows; always double)
-        constexpr int NCOL = (2 * KC + PMU_WARP - 1) / PMU_WARP;
-        double colsum[WP][NCOL];
-        __syncwarp();
-#pragma unroll
-        for (int s2 = 0; s2 < WP; ++s2) {          // stream s2 of the pass: rows s2*G ... s2*G + G-1 of the scratch
-#pragma unroll
-            for (int q = 0; q < NCOL; ++q) {
-                const int c = lane + PMU_WARP * q;
-                double s0 = 0.0, s1 = 0.0, s2_ = 0.0, s3 = 0.0;
-                if (c < 2 * a.Kp) {
-                    const CT* col = red + (size_t)s2 * G * RS + c;
-#pragma unroll
-                    for (int l = 0; l < G; l += 4) {
-                        s0 += (double)col[(l + 0) * RS];
-                        s1 += (double)col[(l + 1) * RS];
-                        s2_ += (double)col[(l + 2) * RS];
-                        s3 += (double)col[(l + 3) * RS];
-                    }
-                }
-                colsum[s2][q] = (s0 + s1) + (s2_ + s3);
-            }
-        }
-        if (a.red_in_stage) {
-            // scratch done: hand the stage back to the producer (generic-proxy writes before the next TMA write)
-            __syncwarp();
-            if (lane == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                *reinterpret_cast<volatile int*>(&ctrl->stage_seq[held_st]) = held_use + 1;
-                mbar_arrive(&ctrl->empty[held_st]);
-            }
-        }
         if (WP == 1 && a.warp_per_window) {
             // small launch: this warp finishes its own window right away, lane = bin
             double* myrow = reinterpret_cast<double*>(smem + a.off_raw) + (size_t)(warp - 1) * a.raw_stride;
+            __syncwarp();
+            for (int c = lane; c < 2 * a.Kp; c += PMU_WARP) {
+                const CT* col = red + c;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-            for (int q = 0; q < NCOL; ++q) {
-                const int c = lane + PMU_WARP * q;
-                if (c < 2 * a.Kp) myrow[c] = colsum[0][q];
+                for (int l = 0; l < PMU_WARP; l += 4) {
+                    s0 += (double)col[(l + 0) * RS];
+                    s1 += (double)col[(l + 1) * RS];
+                    s2 += (double)col[(l + 2) * RS];
+                    s3 += (double)col[(l + 3) * RS];
+                }
+                myrow[c] = (s0 + s1) + (s2 + s3);
             }
             __syncwarp();
             // frames of one stream are claimed by tickets in frame order, but by different warps: frame f waits
@@ -839,12 +808,19 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         __threadfence_block();
         double* row = reinterpret_cast<double*>(smem + a.off_raw) + ((size_t)rb * PMU_WARP + slot * WP) * a.raw_stride;
 #pragma unroll
-        for (int s2 = 0; s2 < WP; ++s2) {
+        for (int s2 = 0; s2 < WP; ++s2) {          // stream s2 of the pass: rows s2*G ... s2*G + G-1 of the scratch
             if (WP > 1 && t * WP + s2 >= n_local) break;   // the CTA's last pass may be short
+            for (int c = lane; c < 2 * a.Kp; c += PMU_WARP) {
+                const CT* col = red + (size_t)s2 * G * RS + c;
+                double s0 = 0.0, s1 = 0.0, s2_ = 0.0, s3 = 0.0;   // the column sums are always double
 #pragma unroll
-            for (int q = 0; q < NCOL; ++q) {
-                const int c = lane + PMU_WARP * q;
-                if (c < 2 * a.Kp) row[(size_t)s2 * a.raw_stride + c] = colsum[s2][q];
+                for (int l = 0; l < G; l += 4) {
+                    s0 += (double)col[(l + 0) * RS];
+                    s1 += (double)col[(l + 1) * RS];
+                    s2_ += (double)col[(l + 2) * RS];
+                    s3 += (double)col[(l + 3) * RS];
+                }
+                row[(size_t)s2 * a.raw_stride + c] = (s0 + s1) + (s2_ + s3);
             }
         }
         __syncwarp();

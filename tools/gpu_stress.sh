@@ -7,4 +7,3 @@ echo "== 3 consumer warps, 3 stages"; PMU_STAGES=3 PMU_CONSUMER_WARPS=3 PMU_POST
 echo "== per-element loader everywhere"; PMU_FORCE_ELEM_LOAD=1 timeout 900 python -m pytest tests -x -q -m gpu -k "not latency" > gpurun_out/pytest_stress3.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/pytest_stress3.log
 echo "== row bulk copies instead of tensor-map slabs, batched estimator for small launches too, no programmatic dependent launch"; PMU_NO_TENSOR_MAP=1 PMU_WARP_PER_WINDOW_MAX=0 PMU_ZERO_COPY_MAX=0 PMU_NO_PDL=1 timeout 900 python -m pytest tests -x -q -m gpu -k "not latency and not warp_per_window" > gpurun_out/pytest_stress4.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/pytest_stress4.log
 echo "== no window packing (one window per warp pass everywhere)"; PMU_PACK=1 timeout 900 python -m pytest tests -x -q -m gpu -k "not latency" > gpurun_out/pytest_stress5.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/pytest_stress5.log
-echo "== lane-reduction scratch inside the consumed stage, everywhere it fits"; PMU_RED_IN_STAGE=1 timeout 900 python -m pytest tests -x -q -m gpu -k "not latency" > gpurun_out/pytest_stress6.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/pytest_stress6.log
