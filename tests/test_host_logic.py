@@ -4,6 +4,7 @@ layouts match the reference's ABI, .ini parsing / validation behave like the ref
 kernel's lane arithmetic — compiled for the CPU by tests/host_emul — matches the oracle."""
 import ctypes as C
 import json
+import math
 import re
 import subprocess
 from pathlib import Path
@@ -191,3 +192,89 @@ def test_plan_and_arithmetic_for_other_window_lengths(cfg, expect):
         assert plan[k] == v, (plan, expect)
     assert_frames_close(got, want[:, :, 0, :], "f64", f"N={N}")
     assert np.array_equal(flags & 0xFFFF, km[:, :, 0])
+
+
+# ---------------------------------------------------------------------------------------
+# .ini parsing against the reference's own iniparser, on randomly mangled files
+# ---------------------------------------------------------------------------------------
+_INI_BASE = [("signal","n_cycles","4"),("signal","sample_rate","25600"),("signal","nominal_freq","50"),
+        ("synchrophasor","frame_rate","50"),("synchrophasor","number_of_dft_bins","11"),("synchrophasor","ipdft_iterations","3"),
+        ("synchrophasor","iter_e_ipdft_enable","1"),("synchrophasor","iter_e_ipdft_iterations","3"),("synchrophasor","interference_threshold","0.0033"),
+        ("rocof","threshold_1","3"),("rocof","threshold_2","25"),("rocof","threshold_3","0.035"),
+        ("rocof","low_pass_filter_1","0.5913"),("rocof","low_pass_filter_2","0.2043"),("rocof","low_pass_filter_3","0.2043")]
+
+def _ini_variant(rng):
+    vals = dict(((s,k),v) for s,k,v in _INI_BASE)
+    # value mutations
+    def setv(s,k,choices): vals[(s,k)] = rng.choice(choices)
+    setv("signal","n_cycles",["4","2","6","04","0x4","4.0","4 ","+4"])
+    setv("signal","sample_rate",["25600","12800","25600.0","0x6400","2.56e4","25600;c"])
+    setv("signal","nominal_freq",["50","60","50.0"])
+    setv("synchrophasor","frame_rate",["50","25","100","50.5"])
+    setv("synchrophasor","number_of_dft_bins",["11","8","9","13","011"])
+    setv("synchrophasor","ipdft_iterations",["3","1","2"])
+    setv("synchrophasor","iter_e_ipdft_enable",["1","0","true","false","TRUE","yes","no","Y","n","T","F","2","on"])
+    setv("synchrophasor","iter_e_ipdft_iterations",["3","1","5"])
+    setv("synchrophasor","interference_threshold",["0.0033","3.3e-3",".0033","0.02","1","0.0033f"])
+    setv("rocof","threshold_3",["0.035","3.5e-2","0.05"])
+    lines=[]
+    secs=["signal","synchrophasor","rocof"]
+    if rng.random()<0.3: rng.shuffle(secs)
+    for s in secs:
+        sname = s.upper() if rng.random()<0.3 else (s.capitalize() if rng.random()<0.3 else s)
+        lines.append(rng.choice(["[%s]","  [%s]","[%s]   ","[ %s ]","[%s] ; comment"]) % sname)
+        keys=[(ss,k) for (ss,k) in vals if ss==s]
+        if rng.random()<0.3: rng.shuffle(keys)
+        for (ss,k) in keys:
+            if rng.random()<0.03 and k != "nominal_freq": continue   # missing key (a missing nominal_freq makes the reference divide by zero)
+            kn = k.upper() if rng.random()<0.2 else k
+            v = vals[(ss,k)]
+            if rng.random()<0.15: v = rng.choice(['"%s"',"'%s'"]) % v
+            sep = rng.choice([" = ","=","  =  ","\t=\t"," =","= "])
+            tail = rng.choice(["",""," ; note"," # note","   ",";x","#x"])
+            lead = rng.choice([""," ","\t","    "])
+            lines.append(f"{lead}{kn}{sep}{v}{tail}")
+            if rng.random()<0.1: lines.append(rng.choice(["","; full comment","# another","   "]))
+            if rng.random()<0.04: lines.append(f"{k} = {vals[(ss,k)]}")  # duplicate
+    if rng.random()<0.05: lines.insert(rng.randrange(len(lines)), "this is not valid")
+    return "\n".join(lines)+"\n"
+
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_ini_parser_agrees_with_the_reference_on_mangled_files(tmp_path, seed):
+    """250 .ini files per seed with the quirks iniparser tolerates (case, spacing, quotes, inline comments, duplicate
+    and missing keys, hexadecimal / octal / exponent numbers, every spelling of a boolean, stray lines): the unmodified
+    reference (oracle/_ref) and pmub_parse_ini + pmub_validate must accept the same files, and for the accepted ones
+    a probe estimate through the oracle port configured with OUR parse must equal, bit for bit, the reference's
+    estimate configured from ITS parse - so every parameter was read identically."""
+    import random
+    from oracle_lib import have
+    if not have("ref", np.float64, 1):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    rng = random.Random(seed)
+    ref, port = CpuChecker("ref", np.float64, 1), CpuChecker("port", np.float64, 1)
+    accepted = 0
+    for i in range(250):
+        path = tmp_path / f"f{i}.ini"
+        path.write_text(_ini_variant(rng))
+        h = ref.open_ini(str(path))
+        cfg = api.parse_ini(str(path))
+        ours_ok = cfg is not None and api.validate(cfg)
+        assert bool(h) == bool(ours_ok), (i, path.read_text(), cfg)
+        if not h:
+            continue
+        accepted += 1
+        n = ref.win_len(h)
+        assert n == configs.win_len(cfg) and ref.n_bins(h) == cfg["n_bins"], (i, cfg)
+        t = np.arange(n) / float(cfg["fs"])
+        x = (2.0 * np.cos(2 * math.pi * 51.0 * t) + 0.2 * np.cos(2 * math.pi * 75.0 * t)).reshape(1, -1)
+        want = [ref.estimate(h, x, m)[0] for m in (0.0, 0.02)]
+        ref.close(h)
+        hp = port.open(cfg)
+        assert hp, (i, cfg)
+        got = [port.estimate(hp, x, m)[0] for m in (0.0, 0.02)]
+        port.close(hp)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w, equal_nan=True), (i, cfg, path.read_text())
+    assert accepted > 40        # the rest were rejected by both, for the same files
