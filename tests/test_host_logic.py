@@ -278,3 +278,43 @@ def test_ini_parser_agrees_with_the_reference_on_mangled_files(tmp_path, seed):
         for g, w in zip(got, want):
             assert np.array_equal(g, w, equal_nan=True), (i, cfg, path.read_text())
     assert accepted > 40        # the rest were rejected by both, for the same files
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_config_validation_agrees_with_the_reference_on_random_structs(seed):
+    """check_config_validity (:386-449) against pmub_validate on 400 random estimator_config structs per seed, most of
+    them near a boundary of some rule (f0 = 0 is left out: the reference divides by it before validating)."""
+    import random
+    from oracle_lib import have
+    if not have("ref", np.float64, 1):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    rng = random.Random(seed)
+    ref = CpuChecker("ref", np.float64, 1)
+    n_ok = 0
+    for i in range(400):
+        f0 = rng.choice([50, 60])
+        n_cycles = rng.choice([1, 2, 4, 6, 10, 50])
+        fs = f0 * rng.choice([20, 64, 128, 256, 512])
+        N = n_cycles * fs // f0
+        cfg = dict(n_cycles=n_cycles, f0=f0, frame_rate=rng.choice([1, 25, 50, 60]), fs=fs,
+                   n_bins=rng.choice([n_cycles + 2, n_cycles + 3, N // 2]), P=rng.choice([1, 3]), Q=rng.choice([0, 1, 3]),
+                   interf_trig=rng.choice([1e-9, 0.0033, 1.0]), rocof_thresh=[3.0, 25.0, 0.035],
+                   rocof_low_pass_coeffs=[rng.choice([0.5913, 0.0, -2.0]), 0.2043, rng.choice([0.2043, 1e9])],
+                   iter_eipdft=rng.choice([0, 1]))
+        for _ in range(rng.choice([0, 1, 1, 2])):      # push up to two fields onto / across a boundary of their rule
+            k = rng.choice(["f0", "fs", "n_cycles", "n_bins", "frame_rate", "P", "interf_trig", "thr"])
+            if k == "f0": cfg["f0"] = rng.choice([49, 55, 1, 61])
+            elif k == "fs": cfg["fs"] = rng.choice([0, cfg["fs"] + 1, 4799, cfg["f0"]])
+            elif k == "n_cycles": cfg["n_cycles"] = rng.choice([0, 51, 50, 1])
+            elif k == "n_bins": cfg["n_bins"] = rng.choice([cfg["n_cycles"] + 1, N // 2 + 1, 0, N // 2])
+            elif k == "frame_rate": cfg["frame_rate"] = 0
+            elif k == "P": cfg["P"] = 0
+            elif k == "interf_trig": cfg["interf_trig"] = rng.choice([-0.1, 0.0, 1.0001])
+            else: cfg["rocof_thresh"][rng.randrange(3)] = rng.choice([0.0, -1.0])
+        h = ref.open(cfg)
+        ours = api.validate(cfg)
+        assert bool(h) == bool(ours), (i, cfg)
+        if h:
+            n_ok += 1
+            ref.close(h)
+    assert 50 < n_ok < 350
