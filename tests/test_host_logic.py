@@ -318,3 +318,31 @@ def test_config_validation_agrees_with_the_reference_on_random_structs(seed):
             n_ok += 1
             ref.close(h)
     assert 50 < n_ok < 350
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_valid_configurations_on_the_host_emulation(seed):
+    """The kernel's own arithmetic headers compiled for the CPU (tests/host_emul), on randomly drawn valid
+    configurations: every launch plan (16/8/4/1-point codelets, slabs, packed short windows, the general kernel's
+    chunks) against the oracle, peak bin exact - the GPU-less twin of the randomized GPU test."""
+    from random_configs import random_valid_configs
+    plans = set()
+    for cfg in random_valid_configs(10, seed):
+        N = configs.win_len(cfg)
+        S, T = 6, 3
+        rng = np.random.default_rng(N + seed)
+        f = cfg["f0"] + rng.uniform(-1.5, 1.5, S)
+        win = np.zeros((T, S, 1, N))
+        mid = np.zeros((T, S))
+        for t in range(T):
+            harm = [(0.1, 1.5 * cfg["f0"], 0.0)] if t == 1 else [(0.003, 3.0 * cfg["f0"], 0.5)]
+            win[t, :, 0, :] = signals.steady(cfg, t, 1 + rng.uniform(0, 1, S), f, rng.uniform(-3, 3, S), harmonics=harm)
+            mid[t] = signals.mid_fracsec(cfg, t)
+        win += 1e-4 * rng.standard_normal(win.shape)
+        want, km, _ = CpuChecker("port", np.float64, 1).run(cfg, win, mid)
+        got, flags, _spec, plan = emul_lib.run(cfg, win[:, :, 0, :], mid)
+        plans.add((plan["M"], plan["nslab"] > 1, plan["wp"]))
+        assert_frames_close(got, want[:, :, 0, :], "f64", str(cfg))
+        ok = ~np.isnan(want[:, :, 0, :]).any(axis=-1)
+        assert np.array_equal((flags & 0xFFFF)[ok], km[:, :, 0][ok]), cfg
+    assert len(plans) >= 3, plans
