@@ -419,6 +419,32 @@ def test_config5_all_million_channels_on_one_gpu():
     assert_frames_close(out[:, idx].cpu().numpy(), want, "f64", "config5, 1M channels")
 
 
+def test_config2_mclass_one_instance_six_channels_50_frames():
+    """BASELINE config 2 as SURVEY.md 8(d) words it: m_class_config.ini (N = 3072, Q = 10), one instance of 3 voltages
+    (325.27 V) + 3 currents (14.14 A, -0.3 rad), 50.2 Hz, +10 % interharmonic at 75 Hz on every channel (the Q loop runs
+    on every frame), 50 consecutive frames at a hop of 512 samples - through the drop-in pmu_estimate of the
+    NUM_CHANLS = 6 library, against the unmodified reference / oracle frame by frame."""
+    cfg = configs.M_CLASS_INI
+    N, hop, T = configs.win_len(cfg), configs.hop(cfg), 50
+    fs = cfg["fs"]
+    n = np.arange(N + (T - 1) * hop)
+    amp = np.array([325.27] * 3 + [14.14] * 3)
+    ph = np.array([0.0, -2 * math.pi / 3, 2 * math.pi / 3] * 2) + np.array([0.0] * 3 + [-0.3] * 3)
+    x = amp[:, None] * (np.cos(2 * math.pi * 50.2 * n / fs + ph[:, None]) + 0.1 * np.cos(2 * math.pi * 75.0 * n / fs + ph[:, None]))
+    win = np.stack([x[:, t * hop:t * hop + N] for t in range(T)])[:, None]            # [T, 1, 6, N]
+    mid = np.array([[((t * hop + N // 2) % fs) / fs] for t in range(T)])                 # [T, 1]
+    want, _, _ = checker(np.float64, 6).run(cfg, win, mid, n_threads=0)
+    pmu = PMUEstimator(n_channels=6)
+    assert pmu.configure_from_class(EstimatorConfig.from_dict(cfg)) == 0
+    got = np.zeros((T, 6, 4))
+    for t in range(T):
+        frames = pmu.estimate(win[t, 0], float(mid[t, 0]))
+        got[t] = [[f["amp"], f["ph"], f["freq"], f["rocof"]] for f in frames]
+    pmu.deinit()
+    assert_frames_close(got, want[:, 0], "f64", "config 2")
+    assert abs(got[-1, 0, 2] - 50.2) < 1e-3 and abs(got[-1, 0, 0] - 325.27) < 0.05     # and the answer is the right one
+
+
 # ---------------------------------------------------------------------------------------
 # several consecutive frames in one launch == the same frames one call at a time
 # ---------------------------------------------------------------------------------------
