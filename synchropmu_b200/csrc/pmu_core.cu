@@ -437,10 +437,10 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     pp.trig_off = (unsigned)b->plan.off_trig;
     a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.pitch = b->plan.pitch; a.wp = b->plan.wp; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
     a.n_stage = b->plan.n_stage; a.stage_bytes = b->plan.stage_bytes; a.n_cons = b->plan.n_cons;
-    a.n_raw = b->plan.n_raw; a.raw_stride = b->plan.raw_stride; a.n_post = b->plan.n_post;
+    a.n_raw = b->plan.n_raw; a.raw_stride = b->plan.raw_stride; a.red_bytes = b->plan.red_bytes;
     a.n_u = b->plan.n_u;
     a.off_ctrl = b->plan.off_ctrl; a.off_U = b->plan.off_U; a.off_V = b->plan.off_V; a.off_trig = b->plan.off_trig;
-    a.off_raw = b->plan.off_raw; a.off_post = b->plan.off_post; a.off_red = b->plan.off_red; a.off_stage = b->plan.off_stage;
+    a.off_raw = b->plan.off_raw; a.off_red = b->plan.off_red; a.off_stage = b->plan.off_stage;
     a.U = b->dU; a.V = b->dV; a.trig = b->dT;
 
     if (pmub_reset(b)) { free_batch(b); return -1; }
@@ -666,11 +666,17 @@ int pmub_stream_push(pmub_batch* b, int n_frames, const void* new_samples, const
         // ingest: frame f's hop samples of every stream go to ring position (wpos + f*hop) mod cap
         if ((size_t)hop * sz >= 2048) {
             // wide rows: 2-D DMA straight from the caller's buffer into the rings
+            // (two when the block crosses the end of the ring: the write position is a multiple of the hop only
+            //  if the hop divides win_len)
             for (int f = 0; f < n_frames; ++f) {
                 const long long p = (b->ring_wpos + (long long)f * hop) % cap;
-                CUDA_OK(cudaMemcpy2DAsync(b->d_ring + ((size_t)w0 * (size_t)cap + (size_t)p) * sz, (size_t)cap * sz,
-                                          (const unsigned char*)new_samples + ((size_t)f * n + (size_t)w0) * (size_t)hop * sz,
-                                          (size_t)hop * sz, (size_t)hop * sz, (size_t)(w1 - w0), cudaMemcpyDefault, s));
+                const long long n1 = (cap - p < hop) ? cap - p : hop;
+                const unsigned char* src = (const unsigned char*)new_samples + ((size_t)f * n + (size_t)w0) * (size_t)hop * sz;
+                CUDA_OK(cudaMemcpy2DAsync(b->d_ring + ((size_t)w0 * (size_t)cap + (size_t)p) * sz, (size_t)cap * sz, src,
+                                          (size_t)hop * sz, (size_t)n1 * sz, (size_t)(w1 - w0), cudaMemcpyDefault, s));
+                if (n1 < hop)
+                    CUDA_OK(cudaMemcpy2DAsync(b->d_ring + (size_t)w0 * (size_t)cap * sz, (size_t)cap * sz, src + (size_t)n1 * sz,
+                                              (size_t)hop * sz, (size_t)(hop - n1) * sz, (size_t)(w1 - w0), cudaMemcpyDefault, s));
             }
         } else {
             // narrow rows: contiguous copies into a staging area (host input), then a scatter kernel
@@ -684,7 +690,7 @@ int pmub_stream_push(pmub_batch* b, int n_frames, const void* new_samples, const
             }
             const long long total = (w1 - w0) * hop * n_frames;
             int blocks = (int)((total + 255) / 256);
-            if (blocks > 148 * 16) blocks = 148 * 16;
+            if (blocks > b->num_sms * 16) blocks = b->num_sms * 16;
             if (sz == 8)
                 ring_scatter_kernel<double><<<blocks, 256, 0, s>>>((double*)b->d_ring, (const double*)src, (long long)n, w0, w1, n_frames,
                                                                     (int)hop, cap, b->ring_wpos);

@@ -220,3 +220,19 @@ PMU_HD pmu_c hann_combine(const double* raw, int k)
     o.y = 0.5 * raw[2 * k + 1] - 0.25 * (li + raw[2 * (k + 1) + 1]);
     return o;
 }
+
+// The same combination over a whole lane-private row, in place: X holds the K+1 rectangular bins on entry and the K
+// Hann-windowed bins on return (entry K keeps its rectangular value).  Same operations, in the same order, as K calls
+// of hann_combine.
+PMU_HD void hann_combine_inplace(const Col& X, int K)
+{
+    pmu_c cur = X.get(0);
+    pmu_c left = X.get(1);
+    left.y = -left.y;   // rect[-1] = conj rect[1]
+    for (int k = 0; k < K; ++k) {
+        const pmu_c nxt = X.get(k + 1);
+        X.put(k, 0.5 * cur.x - 0.25 * (left.x + nxt.x), 0.5 * cur.y - 0.25 * (left.y + nxt.y));
+        left = cur;
+        cur = nxt;
+    }
+}

@@ -265,7 +265,7 @@ static int make_wide_plan(const pmub_config& c, int max_smem, Plan* out)
     p.off_U = off; p.off_V = off;
     p.off_trig = off; off += align_up((p.jlo + p.jhi + 1) * 16, 128);
     p.off_raw = off;
-    p.off_post = off; p.off_red = off; p.off_stage = off;
+    p.off_red = off; p.off_stage = off;
     int warps = (max_smem - off) / per_warp;
     if (warps > 8) warps = 8;
     if (warps < 1) {
@@ -349,36 +349,32 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
     p.n_u = n_groups * p.KC;
     p.jlo = K + 2;
     p.jhi = 2 * K + 1;
-    p.raw_stride = 2 * p.Kp + 1;  // odd number of doubles: lane-per-window reads stay conflict-free
-    // per-lane row of the reduction scratch: >= 2*Kp doubles, an odd number of 16-byte units so that the
+    // one window's K+1 rectangular bins as 16-byte complex entries, rows an odd number of entries apart: the lane-per-
+    // window 128-bit reads of the estimator (which Hann-combines the row in place and uses it as X) stay conflict-free
+    p.raw_stride = 2 * (p.Kp | 1);
+    // per-lane row of the reduction scratch: >= 2*Kp elements, an odd number of 16-byte units so that the
     // 128-bit stores of a quarter warp hit distinct banks
     p.red_stride = 2 * p.KC + 2;  // compile-time in the kernel (immediate LDS offsets)
+    // ... and the same region holds the estimator's residual spectrum W[K][32] while the warp posts a batch
+    const int dft_elem = (s == 4) ? 4 : 8;   // the float build reduces float partials
+    p.red_bytes = align_up(32 * p.red_stride * dft_elem, 128);
+    if (p.red_bytes < K * 32 * 16) p.red_bytes = K * 32 * 16;
 
     int want_cons = env_int("PMU_CONSUMER_WARPS", PMU_MAX_CONSUMERS);
     if (want_cons < 1) want_cons = 1;
     if (want_cons > PMU_MAX_CONSUMERS) want_cons = PMU_MAX_CONSUMERS;
-    // Measured (profiles/r1_sweep_smem.jsonl): ring depth is worth more than spare estimator scratch - two raw-bin
-    // buffers and two estimator slots keep the seven consumer warps busy and leave room for two more stages.
-    int want_raw = env_int("PMU_RAW_BUFFERS", 2);   // powers of two only (the kernel masks)
-    want_raw = want_raw >= 8 ? 8 : (want_raw >= 4 ? 4 : 2);
-    int want_post = env_int("PMU_POST_SLOTS", 2);
-    if (want_post < 1) want_post = 1;
-    if (want_post > PMU_MAX_POST) want_post = PMU_MAX_POST;
     int ns_cap = env_int("PMU_STAGES", PMU_MAX_STAGES);
     if (ns_cap > PMU_MAX_STAGES) ns_cap = PMU_MAX_STAGES;
 
-    // Shared-memory budget: prefer the full complement of scratch; when bins/windows are large,
-    // give up scratch slots (then consumer warps) until at least `min_stages` ring stages fit.
-    auto layout = [&](int n_cons, int n_raw, int n_post) {
-        p.n_cons = n_cons; p.n_raw = n_raw; p.n_post = n_post;
+    auto layout = [&](int n_cons, int n_raw) {
+        p.n_cons = n_cons; p.n_raw = n_raw;
         int off = 0;
         p.off_ctrl = off; off += align_up((int)sizeof(CtrlBlock), 128);
         p.off_U = off;    off += align_up(p.n_u * 16, 128);
         p.off_V = off;    off += align_up(p.KC * 32 * 16, 128);
         p.off_trig = off; off += align_up((p.jlo + p.jhi + 1) * 16, 128);
         p.off_raw = off;  off += align_up(p.n_raw * 32 * p.raw_stride * 8, 128);
-        p.off_post = off; off += align_up(p.n_post * 2 * K * 32 * 16, 128);
-        p.off_red = off;  off += align_up(p.n_cons * 32 * p.red_stride * 8, 128);
+        p.off_red = off;  off += p.n_cons * p.red_bytes;
         p.off_stage = off;
         int ns = (max_smem - off) / p.stage_bytes;
         if (ns > ns_cap) ns = ns_cap;
@@ -386,15 +382,40 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
         p.smem_bytes = off + (ns > 0 ? ns : 0) * p.stage_bytes;
         return ns;
     };
-    const int tries[][3] = {{want_cons, want_raw, want_post}, {want_cons, 2, 3}, {want_cons, 2, 2}, {want_cons, 2, 1},
-                            {5, 2, 2}, {5, 2, 1}, {3, 2, 1}, {2, 2, 1}, {1, 2, 1}};
+    // Shared-memory budget.  A raw-bin buffer is held by its batch until the estimator has finished with it, so the
+    // ring of raw buffers bounds how many batches can be in the estimator at once (plus the one or two being filled).
+    // Ring depth is still worth more than anything else (profiles/r1_sweep_smem.jsonl): take as many raw buffers as fit
+    // WITHOUT costing a stage relative to the minimum of 4; only the interference iterations (iter_e_ipDFT, :666-703)
+    // make a batch stay long enough for more than 4 to matter.  When bins/windows are large, give up raw buffers,
+    // then consumer warps, until at least `min_stages` ring stages fit.
+    const int forced_raw = env_int("PMU_RAW_BUFFERS", 0);
+    const int cons_tries[] = {want_cons, 5, 3, 2, 1};
     bool ok = false;
     for (int pass = 0; pass < 2 && !ok; ++pass) {
         const int min_stages = pass == 0 ? 4 : 2;
-        for (const auto& t : tries) {
-            const int nc = t[0] < want_cons ? t[0] : want_cons, nr = t[1] < want_raw ? t[1] : want_raw,
-                      np = t[2] < want_post ? t[2] : want_post;
-            if (layout(nc, nr < 2 ? 2 : nr, np < 1 ? 1 : np) >= min_stages) { ok = true; break; }
+        for (int nc0 : cons_tries) {
+            const int nc = nc0 < want_cons ? nc0 : want_cons;
+            if (forced_raw >= 2) {
+                if (layout(nc, forced_raw > PMU_MAX_RAW ? PMU_MAX_RAW : forced_raw) >= min_stages) { ok = true; break; }
+                continue;
+            }
+            const int base_raw = nc >= 3 ? 4 : 3;
+            const int ns_ref = layout(nc, base_raw);
+            if (ns_ref < min_stages) {
+                if (layout(nc, 2) >= min_stages) { ok = true; break; }
+                continue;
+            }
+            int nr = base_raw;
+            const int nr_max = c.iter_eipdft ? (nc + 1 < PMU_MAX_RAW ? nc + 1 : PMU_MAX_RAW) : base_raw;
+            // with the interference iterations enabled, one stage beyond the eighth is worth less than the extra
+            // batches in flight (the ninth stage adds < 1 % to the streaming rate)
+            int ns_keep = ns_ref;
+            if (c.iter_eipdft && ns_ref > 8 && env_int("PMU_TRADE_STAGE", 1)) ns_keep = ns_ref - 1;
+            for (int cand_raw = nr_max; cand_raw > base_raw; --cand_raw)
+                if (layout(nc, cand_raw) >= ns_keep) { nr = cand_raw; break; }
+            layout(nc, nr);
+            ok = true;
+            break;
         }
     }
     if (!ok) return make_wide_plan(c, max_smem, out);   // e.g. very long windows with many bins

@@ -40,10 +40,11 @@ struct Plan {
     int wp;             // windows per warp pass: 4 for short single-slab windows (8 lanes per window), else 1
     int Kp;             // n_bins + 1
     int n_stage, stage_bytes;
-    int n_cons, n_raw, raw_stride, n_post;
+    int n_cons, n_raw, raw_stride;
+    int red_bytes;      // per consumer warp: lane-reduction scratch = the estimator's W columns while the warp posts a batch
     int n_u;
     int jlo, jhi;
-    int off_ctrl, off_U, off_V, off_trig, off_raw, off_post, off_red, off_stage;
+    int off_ctrl, off_U, off_V, off_trig, off_raw, off_red, off_stage;
     int red_stride;     // doubles per lane row of the per-warp reduction scratch
     int smem_bytes;
     bool aligned16;     // window pitch and row pitch allow TMA bulk copies

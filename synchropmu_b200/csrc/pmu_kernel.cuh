@@ -33,7 +33,6 @@
 #define PMU_PITCH16_SHORT 64  // ... for 1024-sample windows, stored at their natural pitch, two per warp pass
 #define PMU_PITCH16_96 96     // ... for windows of a multiple of 96 (not 128) residues: M-class 3072 = 2 x 96 x 16
 #define PMU_MAX_RAW 8
-#define PMU_MAX_POST 8
 #define PMU_MAX_GROUPS 256  // groups of <= 32 streams per CTA when a launch carries several frames
 
 enum { PMU_LOAD_BULK = 0, PMU_LOAD_ELEM = 1 };
@@ -56,11 +55,11 @@ struct KernelArgs {
     int load_mode;               // PMU_LOAD_BULK / PMU_LOAD_ELEM
     int n_stage, stage_bytes;
     int n_cons;                  // consumer warps
-    int n_raw, raw_stride;       // raw-bin buffers in the ring, doubles per window slot
-    int n_post;                  // post-processing scratch slots
+    int n_raw, raw_stride;       // raw-bin buffers in the ring, doubles per window slot (an odd number of 16-byte units)
+    int red_bytes;               // per consumer warp: lane-reduction scratch, reused as the estimator's W columns
     int n_u;                     // entries of U (complex)
     // shared-memory layout (byte offsets from the dynamic smem base)
-    int off_ctrl, off_U, off_V, off_trig, off_raw, off_post, off_red, off_stage;
+    int off_ctrl, off_U, off_V, off_trig, off_raw, off_red, off_stage;
     // tables (global memory; copied to smem by the kernel)
     const pmu_c* U;              // [ceil(L/32)][KC]   W_N^{32 i k}
     const pmu_c* V;              // [KC][32]           W_N^{lane k}
@@ -109,7 +108,6 @@ struct CtrlBlock {
     int ticket;
     int batch_cnt[PMU_MAX_RAW];
     int raw_owner[PMU_MAX_RAW];
-    int post_lock[PMU_MAX_POST];
     int grp_done[PMU_MAX_GROUPS];   // per group of <= 32 streams: frames fully post-processed
 };
 
@@ -398,33 +396,38 @@ __device__ __noinline__ void post_window_warp(const KernelArgs& a, const double*
 
 // ---- post-processing of one batch (lane = window) --------------------------------------
 // Batch = <= 32 consecutive streams of this CTA at frame f.  w_first = index (within this
-// launch) of the batch's first stream.
+// launch) of the batch's first stream.  The estimator's two bin arrays need no scratch of their own:
+// X is the batch's raw-bin buffer, Hann-combined in place (a lane-private row of 16-byte entries), and the
+// residual spectrum W lives in the posting warp's lane-reduction scratch, which is idle until the warp
+// transforms its next window.  Every consumer warp can therefore post a batch at the same time; the raw
+// buffer goes back to the ring when the estimator is done with X.
 template <typename InT>
-__device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, int post_slot, long long w_first, int frame,
+__device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, unsigned w_off, long long w_first, int frame,
                                         int bsz, int batch_id, int lane)
 {
     unsigned char* smem = pmu_smem;
     const PostParams& pp = a.post;   // stays in the kernel-parameter constant bank
     CtrlBlock* ctrl = reinterpret_cast<CtrlBlock*>(smem + a.off_ctrl);
     const int K = pp.K;
-    pmu_c* scratch = reinterpret_cast<pmu_c*>(smem + a.off_post) + (size_t)post_slot * (2 * K * PMU_WARP);
-    const Col X = Col::make(scratch + lane, PMU_WARP);
-    const Col Wk = Col::make(scratch + K * PMU_WARP + lane, PMU_WARP);
+    double* row = reinterpret_cast<double*>(smem + a.off_raw) + ((size_t)raw_buf * PMU_WARP + lane) * a.raw_stride;
+    const Col X = Col::make(reinterpret_cast<pmu_c*>(row), 1);
+    const Col Wk = Col::make(reinterpret_cast<pmu_c*>(smem + w_off) + lane, PMU_WARP);
     const bool active = lane < bsz;
     const long long w = w_first + lane;                         // stream index within the launch
     const long long wf = (long long)frame * a.frame_stride + w; // row in the frame-major arrays
 
+    Tone t;
+    int dbg = 0;
     if (active) {
-        const double* row = reinterpret_cast<const double*>(smem + a.off_raw) +
-                            ((size_t)raw_buf * PMU_WARP + lane) * a.raw_stride;
-        for (int k = 0; k < K; ++k) {
-            pmu_c xw = hann_combine(row, k);
-            X.put(k, xw.x, xw.y);
-            if (a.spec_out) {
+        hann_combine_inplace(X, K);
+        if (a.spec_out) {
+            for (int k = 0; k < K; ++k) {
+                const pmu_c xw = X.get(k);
                 a.spec_out[((size_t)wf * K + k) * 2] = xw.x;
                 a.spec_out[((size_t)wf * K + k) * 2 + 1] = xw.y;
             }
         }
+        dbg = estimate_tone(pp, X, Wk, &t);
     }
     // hand the raw buffer to batch (batch_id + n_raw)
     __syncwarp();
@@ -435,8 +438,6 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, int po
     }
 
     if (active) {
-        Tone t;
-        int dbg = estimate_tone(pp, X, Wk, &t);
         RocofState rs;
         // the previous frame's state may have been written by another warp of this CTA
         rs.f_old = __ldcg(&a.st_fold[w]);
@@ -474,10 +475,6 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, int po
         }
     }
     __syncwarp();
-    if (lane == 0) {
-        __threadfence_block();
-        atomicExch(&ctrl->post_lock[post_slot], 0);
-    }
 }
 
 // Load the M samples of one residue from a stage (row pitch in elements).  FULL: every lane of
@@ -546,7 +543,6 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             ctrl->batch_cnt[i] = 0;
             ctrl->raw_owner[i] = i;
         }
-        for (int i = 0; i < PMU_MAX_POST; ++i) ctrl->post_lock[i] = 0;
         mbar_fence_init();
     }
     for (int i = tid; i < PMU_MAX_GROUPS; i += nthreads) ctrl->grp_done[i] = 0;
@@ -687,7 +683,9 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     const int gl = lane % G;              // its lane index within that stream's group
     by_nstage.init((unsigned)a.n_stage);
     const int w_per_it = a.W / PMU_WARP;  // full-slab residue groups (W % 32 == 0 when nslab > 1)
-    const int raw_mask = a.n_raw - 1;     // n_raw is a power of two
+    FastDiv by_nraw;
+    by_nraw.init((unsigned)a.n_raw);
+    const unsigned red_off = (unsigned)a.off_red + (unsigned)(warp - 1) * (unsigned)a.red_bytes;
 
     for (;;) {
         int item = 0;
@@ -752,7 +750,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         //      partials into its row of the warp's scratch (128-bit stores, conflict-free row
         //      stride), then lane c adds up column c of the 32 rows and deposits the total ----
         constexpr int RS = 2 * KC + 2;  // row stride in CT elements: an odd number of complex slots
-        CT* red = reinterpret_cast<CT*>(smem + a.off_red) + (size_t)(warp - 1) * PMU_WARP * RS;
+        CT* red = reinterpret_cast<CT*>(smem + red_off);
         {
             ccplx* my = reinterpret_cast<ccplx*>(red + (size_t)lane * RS);
 #pragma unroll
@@ -800,7 +798,9 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         int g, slot, bsz, first_t;                 // in passes; converted to streams below when WP > 1
         bm.locate(t, &g, &slot, &bsz, &first_t);
         const int gb = f * bm.nb + g;              // batch id over the whole launch, in ticket order
-        const int rb = gb & raw_mask;
+        unsigned rb_u;
+        by_nraw.div((unsigned)gb, &rb_u);
+        const int rb = (int)rb_u;
         if (lane == 0) {
             while (ld_volatile_s32(&ctrl->raw_owner[rb]) != gb) __nanosleep(64);
         }
@@ -837,22 +837,14 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             }
             // ---- this warp post-processes batch (f, g) ----
             __threadfence_block();
-            int ps = 0;
-            if (lane == 0) {
-                // frame f of these streams needs the ROCOF state left by frame f-1
-                if (a.n_frames > 1)
+            // frame f of these streams needs the ROCOF state left by frame f-1
+            if (a.n_frames > 1) {
+                if (lane == 0)
                     while (ld_volatile_s32(&ctrl->grp_done[g]) != f) __nanosleep(64);
-                for (;;) {
-                    bool got = false;
-                    for (int s = 0; s < a.n_post; ++s)
-                        if (atomicCAS(&ctrl->post_lock[s], 0, 1) == 0) { ps = s; got = true; break; }
-                    if (got) break;
-                    __nanosleep(128);
-                }
+                __syncwarp();
+                __threadfence_block();
             }
-            ps = __shfl_sync(0xffffffffu, ps, 0);
-            __threadfence_block();
-            post_batch<InT>(a, rb, ps, w_begin + first_t, f, bsz, gb, lane);
+            post_batch<InT>(a, rb, red_off, w_begin + first_t, f, bsz, gb, lane);
             if (a.n_frames > 1 && lane == 0) {
                 __threadfence_block();
                 *reinterpret_cast<volatile int*>(&ctrl->grp_done[g]) = f + 1;

@@ -204,23 +204,51 @@ struct Sweep {
         zi = (z_re * ei + z_im * er) * g;
     }
 
-    // 1 / sin(pi (r + j)/N)
-    PMU_HD double inv_den(const PostParams& p, int j) const
-    {
-        pmu_c t = pmu_trig(p, j + p.jlo);
-        return pmu_rcp(sr * t.x + cr * t.y);
-    }
+    // 1 / sin(pi (r + j)/N), t = trig[j] = (cos(j pi/N), sin(j pi/N))
+    PMU_HD double inv_den_t(const pmu_c& t) const { return pmu_rcp(sr * t.x + cr * t.y); }
+    PMU_HD double inv_den(const PostParams& p, int j) const { return inv_den_t(pmu_trig(p, j + p.jlo)); }
 
-    // value at bin k given I[m-1], I[m], I[m+1]
-    PMU_HD void eval(const PostParams& p, int k, double im1, double i0, double ip1, double* wr, double* wi) const
+    // value at bin k = kstar + m given e = trig[m] and I[m-1], I[m], I[m+1]
+    PMU_HD void eval_e(const PostParams& p, const pmu_c& e, double im1, double i0, double ip1, double* wr, double* wi) const
     {
-        pmu_c e = pmu_trig(p, (k - kstar) + p.jlo);
         double br = p.c3q * (im1 + ip1) + 0.5 * i0;
         double bi = p.s3q * (im1 - ip1);
         double tr = e.x * br - e.y * bi;
         double ti = e.x * bi + e.y * br;
         *wr = zr * tr - zi * ti;
         *wi = zr * ti + zi * tr;
+    }
+    PMU_HD void eval(const PostParams& p, int k, double im1, double i0, double ip1, double* wr, double* wi) const
+    {
+        eval_e(p, pmu_trig(p, (k - kstar) + p.jlo), im1, i0, ip1, wr, wi);
+    }
+};
+
+// A sweep walked bin by bin from bin 0: keeps the sliding window of the three reciprocals and the table entry of the
+// current bin (the entry loaded for I[m+1] is the e of the next bin), so every bin costs one table read and one
+// reciprocal.
+struct SweepWalk {
+    double im1, i0;
+    pmu_c e;      // trig[m] of the bin about to be evaluated
+    int idx;      // table index of trig[m + 1]
+
+    PMU_HD void start(const PostParams& p, const Sweep& sw)
+    {
+        idx = -sw.kstar + p.jlo;          // trig[m] for bin 0
+        im1 = sw.inv_den_t(pmu_trig(p, idx - 1));
+        e = pmu_trig(p, idx);
+        i0 = sw.inv_den_t(e);
+        ++idx;
+    }
+    PMU_HD void step(const PostParams& p, const Sweep& sw, double* wr, double* wi)
+    {
+        const pmu_c tn = pmu_trig(p, idx);
+        const double ip1 = sw.inv_den_t(tn);
+        sw.eval_e(p, e, im1, i0, ip1, wr, wi);
+        im1 = i0;
+        i0 = ip1;
+        e = tn;
+        ++idx;
     }
 };
 
@@ -313,31 +341,41 @@ struct Col {
 
 // One ipDFT over Y[j] (COMP=false) or over Y[j] - wf(j, -f, amp e^{-i ph}) (COMP=true,
 // the e_ipDFT inner loop :646-654).  km_out receives the chosen peak bin.
+//
+// The peak search (find3LargestIndx, :705-720: first strict maximum, a NaN only wins at bin 0) is a running scan
+// written so that every bin costs one compare and a handful of predicated moves: `up` is forced at bin 0 (so a NaN
+// there sticks, as every later compare against it is false), the right neighbour is whatever follows the bin that
+// took the lead last, the left neighbour is the bin before it.
 template <bool COMP>
 PMU_HD int ipdft_pass(const PostParams& p, const Col& Y, const Tone& prev, Tone* out, int* km_out)
 {
     Sweep sw;
-    double im1 = 0, i0 = 0, ip1 = 0;
+    SweepWalk wk;
     if (COMP) {
         sw.init(p, -prev.freq, prev.amp * prev.cr, -prev.amp * prev.ci);  // amp e^{-i ph}, :646
-        im1 = sw.inv_den(p, -sw.kstar - 1);
-        i0 = sw.inv_den(p, -sw.kstar);
+        wk.start(p, sw);
     }
     Peak pk;
+    pk.best = 0; pk.left = 0; pk.right = 0; pk.prev = 0; pk.yr = 0; pk.yi = 0; pk.km = 0;
+    bool was_up = false;
     for (int j = 0; j < p.K; ++j) {
         pmu_c y = Y.get(j);
         if (COMP) {
             double wr, wi;
-            ip1 = sw.inv_den(p, j - sw.kstar + 1);
-            sw.eval(p, j, im1, i0, ip1, &wr, &wi);
+            wk.step(p, sw, &wr, &wi);
             y.x -= wr;
             y.y -= wi;
-            im1 = i0;
-            i0 = ip1;
         }
-        double v = y.x * y.x + y.y * y.y;
-        if (j == 0) pk.first(v, y.x, y.y);
-        else pk.next(j, v, y.x, y.y);
+        const double v = y.x * y.x + y.y * y.y;
+        pk.right = was_up ? v : pk.right;
+        const bool up = (v > pk.best) || (j == 0);
+        pk.left = up ? pk.prev : pk.left;
+        pk.best = up ? v : pk.best;
+        pk.km = up ? j : pk.km;
+        pk.yr = up ? y.x : pk.yr;
+        pk.yi = up ? y.y : pk.yi;
+        pk.prev = v;
+        was_up = up;
     }
     if (km_out) *km_out = pk.km;
     return ipdft_finish(p, pk, out);
@@ -366,17 +404,15 @@ PMU_HD void residual(const PostParams& p, const Col& X, const Tone& t, const Col
     Sweep sp, sn;
     sp.init(p, t.freq, t.amp * t.cr, t.amp * t.ci);    // phsr_0 = amp e^{+i ph}
     sn.init(p, -t.freq, t.amp * t.cr, -t.amp * t.ci);  // phsr_1 = amp e^{-i ph}
-    double pm1 = sp.inv_den(p, -sp.kstar - 1), p0 = sp.inv_den(p, -sp.kstar);
-    double nm1 = sn.inv_den(p, -sn.kstar - 1), n0 = sn.inv_den(p, -sn.kstar);
+    SweepWalk wp, wn;
+    wp.start(p, sp);
+    wn.start(p, sn);
     double ed = 0, e = 0;
+#pragma unroll 2
     for (int j = 0; j < p.K; ++j) {
-        double pp1 = sp.inv_den(p, j - sp.kstar + 1);
-        double np1 = sn.inv_den(p, j - sn.kstar + 1);
         double ar, ai, br, bi;
-        sp.eval(p, j, pm1, p0, pp1, &ar, &ai);
-        sn.eval(p, j, nm1, n0, np1, &br, &bi);
-        pm1 = p0; p0 = pp1;
-        nm1 = n0; n0 = np1;
+        wp.step(p, sp, &ar, &ai);
+        wn.step(p, sn, &br, &bi);
         pmu_c x = X.get(j);
         double wr = x.x - (ar + br);
         double wi = x.y - (ai + bi);
