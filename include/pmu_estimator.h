@@ -4,7 +4,7 @@
  * Source- and binary-compatible with SynchroPMU's public header
  * (reference src/pmu_estimator.h:27-128 and the type macros of src/func_stubs.h:33-47):
  * the same four functions, the same caller-owned `pmu_context`, the same struct
- * layouts byte for byte (checked by tests/test_abi.py against the reference build),
+ * layouts byte for byte (checked by tests/test_host_logic.py against the reference's own header),
  * so existing C callers (test/test.c, examples/simple_example*.c) and the reference's
  * ctypes wrapper (python/pmu_estimator.py) link unchanged.  Behind it every estimate
  * runs the hand-written sm_100a kernel; there is no CPU implementation in this library.
@@ -16,6 +16,13 @@
  * and the matching library:  libpmu_estimator.so (double, 1 channel — the one the
  * reference's Python wrapper needs), libpmu_estimator_c6.so, libpmu_estimator_f32.so,
  * libpmu_estimator_f32_c6.so.  See INTEGRATION.md.
+ *
+ * NOTE - default width.  The reference's func_stubs.h:38 defines float_p as `float` (and has to be edited to get a
+ * double build); THIS header defaults to `double`, the width the reference's own Python wrapper hard-codes
+ * (python/pmu_estimator.py:7-14).  A caller compiled against the reference's unmodified headers (float) must link
+ * libpmu_estimator_f32*.so - or be recompiled with -DPMU_FLOAT_P=float against this header.  Linking it to the
+ * double library would hand float windows to a double ABI; pmu_abi_float_bytes() (4 or 8) lets a caller check the
+ * width of the library it actually loaded.
  */
 #ifndef PMU_ESTIMATOR_H
 #define PMU_ESTIMATOR_H
@@ -173,6 +180,10 @@ int pmu_estimate(pmu_context *ctx, float_p *in_signal_windows, float_p mid_fracs
 int pmu_deinit(pmu_context *ctx);
 
 int pmu_dump_frame(pmu_frame *frame, FILE *stream);
+
+/* sizeof(float_p) of the library that was actually loaded (4 or 8): lets a caller built against the reference's
+ * float headers detect that it was linked to the double library (see the NOTE at the top).  Not in the reference. */
+int pmu_abi_float_bytes(void);
 
 /* ---- batched entry (new; same layouts repeated per instance) ----------------------- */
 /* pmu_estimate == a batch of one instance.  Typed wrappers over pmu_batch.h. */

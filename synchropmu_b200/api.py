@@ -188,9 +188,11 @@ class BatchEstimator:
         h = C.c_void_p()
         code = PMUB_F64 if self.dtype == np.float64 else PMUB_F32
         if isinstance(cfg, (str, os.PathLike)):
+            self.cfg = parse_ini(os.fspath(cfg)) or {}
             rc = self.lib.pmub_create_ini(C.byref(h), os.fsencode(cfg), code, self.n_instances,
                                           self.n_channels, device)
         else:
+            self.cfg = dict(cfg)
             rc = self.lib.pmub_create(C.byref(h), C.byref(CoreConfig.from_dict(cfg)), code,
                                       self.n_instances, self.n_channels, device)
         if rc != 0 or not h.value:
@@ -282,26 +284,37 @@ class BatchEstimator:
         self._check(self.lib.pmub_stream_begin(self._h, int(hop), int(max_frames_per_push),
                                                _ptr(history) if history is not None else None,
                                                int(first_sample_index)), "pmub_stream_begin")
-        self.hop = int(hop) if hop else None
+        # hop = 0 lets the library take one frame per reporting interval: fs / frame_rate samples
+        self.hop = int(hop) if hop else int(self.cfg["fs"]) // int(self.cfg["frame_rate"])
+        self.max_frames_per_push = max(1, int(max_frames_per_push))
         return self.hop
 
     def stream_push(self, new_samples, mid_fracsec=None, out=None):
         """``new_samples [F, n_instances, n_channels, hop]`` -> frames ``[F, n_instances, n_channels, 4]``;
         ``mid_fracsec [F, n_instances]`` or None (computed on the device from the sample counter)."""
         n, c = self.n_instances, self.n_channels
+        if getattr(self, "hop", None) is None:
+            raise RuntimeError("stream_push before stream_begin")
         is_torch = hasattr(new_samples, "data_ptr")
         F = int(new_samples.shape[0])
+        if not 1 <= F <= self.max_frames_per_push:
+            raise ValueError(f"{F} frames in one push; stream_begin allowed 1..{self.max_frames_per_push}")
         if is_torch:
             import torch
 
             tdt = torch.float64 if self.dtype == np.float64 else torch.float32
             assert new_samples.dtype == tdt and new_samples.is_contiguous()
+            assert new_samples.numel() == F * n * c * self.hop, "new_samples must be [F, n_instances, n_channels, hop]"
+            if mid_fracsec is not None:
+                assert mid_fracsec.dtype == tdt and mid_fracsec.is_contiguous() and mid_fracsec.numel() == F * n
             if out is None:
                 out = torch.empty((F, n, c, 4), dtype=tdt, device=new_samples.device)
         else:
             new_samples = np.ascontiguousarray(new_samples, dtype=self.dtype)
+            assert new_samples.size == F * n * c * self.hop, "new_samples must be [F, n_instances, n_channels, hop]"
             if mid_fracsec is not None:
                 mid_fracsec = np.ascontiguousarray(mid_fracsec, dtype=self.dtype)
+                assert mid_fracsec.size == F * n
             if out is None:
                 out = np.empty((F, n, c, 4), dtype=self.dtype)
         self._check(self.lib.pmub_stream_push(self._h, F, _ptr(new_samples),

@@ -161,6 +161,8 @@ int pmu_deinit(pmu_context *ctx)
 }
 
 /* reference src/pmu_estimator.c:306-324 (same text format) */
+int pmu_abi_float_bytes(void) { return (int)sizeof(float_p); }
+
 int pmu_dump_frame(pmu_frame *frame, FILE *stream)
 {
     if (frame == NULL || stream == NULL) {

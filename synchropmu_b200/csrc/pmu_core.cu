@@ -518,8 +518,10 @@ int pmub_estimate_frames(pmub_batch* b, int n_frames, const void* windows, const
     const bool win_dev = is_device_ptr(windows), mid_dev = is_device_ptr(mid), fr_dev = is_device_ptr(frames);
     double* d_export = reinterpret_cast<double*>(b->d_out + fr_bytes);
 
-    if (win_dev && mid_dev && fr_dev && !b->mirror) {
-        if (launch_frames(b, 0, b->n_windows, n_frames, windows, mid, frames, nullptr, main_stream(b))) return -1;
+    if (win_dev && mid_dev && fr_dev) {
+        if (launch_frames(b, 0, b->n_windows, n_frames, windows, mid, frames, b->mirror ? d_export : nullptr, main_stream(b))) return -1;
+        if (b->mirror)   // keep the drop-in API's view of the ROCOF state fresh whatever kind of pointers came in
+            CUDA_OK(cudaMemcpyAsync(b->h_out + fr_bytes, d_export, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, main_stream(b)));
         CUDA_OK(cudaStreamSynchronize(main_stream(b)));
         return 0;
     }
@@ -585,7 +587,9 @@ int pmub_estimate_frames(pmub_batch* b, int n_frames, const void* windows, const
             CUDA_OK(cudaMemcpy2DAsync((unsigned char*)frames + (size_t)w0 * 4 * sz, fr_bytes, dF + (size_t)w0 * 4 * sz, fr_bytes,
                                       (size_t)(w1 - w0) * 4 * sz, (size_t)n_frames, cudaMemcpyDeviceToHost, s));
     }
-    return pmub_sync(b);
+    if (pmub_sync(b)) return -1;
+    if (b->mirror) CUDA_OK(cudaMemcpy(b->h_out + fr_bytes, d_export, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int pmub_estimate(pmub_batch* b, const void* windows, const void* mid, void* frames)

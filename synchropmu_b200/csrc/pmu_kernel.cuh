@@ -290,22 +290,29 @@ __device__ __forceinline__ void sweep_bin(const PostParams& p, const Sweep& sw, 
     sw.eval(p, j, sw.inv_den(p, m - 1), sw.inv_den(p, m), sw.inv_den(p, m + 1), wr, wi);
 }
 
-__device__ __forceinline__ void e_ipdft_warp(const PostParams& p, double yr, double yi, int j, bool valid, Tone* t, int* km_first)
+// e_ipDFT (:626-664) with lane = bin; one copy of the pass for the plain and the compensated iterations (see
+// ipdft_pass in pmu_math.cuh for why).  Returns the peak bin of the first pass.
+__device__ __forceinline__ int e_ipdft_warp(const PostParams& p, double yr, double yi, int j, bool valid, Tone* t)
 {
-    Tone cur = *t;
-    if (!ipdft_warp(p, yr, yi, j, valid, &cur, km_first)) {
-        for (int it = 0; it < p.P; ++it) {
+    Tone cur;
+    cur.amp = 0; cur.cr = 1; cur.ci = 0; cur.freq = 0;
+    int km_first = 0;
+    for (int it = 0; it <= p.P; ++it) {
+        double wr = 0.0, wi = 0.0;
+        if (it > 0) {
             Sweep sw;
             sw.init(p, -cur.freq, cur.amp * cur.cr, -cur.amp * cur.ci);
-            double wr, wi;
             sweep_bin(p, sw, j, &wr, &wi);
-            Tone nxt;
-            const int done = ipdft_warp(p, yr - wr, yi - wi, j, valid, &nxt, nullptr);
-            cur = nxt;
-            if (done) break;
         }
+        Tone nxt;
+        int km;
+        const int done = ipdft_warp(p, yr - wr, yi - wi, j, valid, &nxt, &km);
+        if (it == 0) km_first = km;
+        cur = nxt;
+        if (done) break;
     }
     *t = cur;
+    return km_first;
 }
 
 // X - pureTone(t) at this lane's bin
@@ -369,26 +376,24 @@ __device__ __noinline__ void post_window_warp(const KernelArgs& a, const double*
         a.spec_out[((size_t)wf * K + j) * 2] = xr;
         a.spec_out[((size_t)wf * K + j) * 2 + 1] = xi;
     }
+    // the same single loop as estimate_tone (pmu_math.cuh): "estimate a tone from Y, subtract it from X into W"
     Tone f;
     f.amp = 0; f.cr = 1; f.ci = 0; f.freq = 0;
-    int km = 0;
-    e_ipdft_warp(pp, xr, xi, j, valid, &f, &km);                       // :205
-    int dbg = km & PMU_DBG_KM_MASK;
-    if (pp.iter_en) {
-        double wr, wi;
-        residual_bin(pp, xr, xi, j, f, &wr, &wi);                      // :206-215  Xi
-        const double Ed = warp_sum(valid ? wr * wr + wi * wi : 0.0);   // :219
-        const double E = warp_sum(valid ? xr * xr + xi * xi : 0.0);    // :220
-        if (Ed > pp.eps * E) {                                         // :229
+    int dbg = 0;
+    double yr = xr, yi = xi;
+    const int last = pp.iter_en ? 2 * pp.Q : 0;
+    for (int s = 0; s <= last; ++s) {
+        Tone t;
+        const int km = e_ipdft_warp(pp, yr, yi, j, valid, &t);        // :205, :679, :685
+        if (s == 0) dbg = km & PMU_DBG_KM_MASK;
+        if (!(s & 1)) f = t;
+        if (s == last || !pp.iter_en) break;
+        residual_bin(pp, xr, xi, j, t, &yr, &yi);                     // :206-215, :680-684, :690-695
+        if (s == 0) {
+            const double Ed = warp_sum(valid ? yr * yr + yi * yi : 0.0);   // :219
+            const double E = warp_sum(valid ? xr * xr + xi * xi : 0.0);    // :220
+            if (!(Ed > pp.eps * E)) break;                            // :229
             dbg |= PMU_DBG_TRIGGERED;
-            Tone it;
-            it.amp = 0; it.cr = 1; it.ci = 0; it.freq = 0;
-            for (int i = 0; i < pp.Q; ++i) {                           // :675-696
-                e_ipdft_warp(pp, wr, wi, j, valid, &it, nullptr);
-                residual_bin(pp, xr, xi, j, it, &wr, &wi);
-                e_ipdft_warp(pp, wr, wi, j, valid, &f, nullptr);
-                if (i + 1 < pp.Q) residual_bin(pp, xr, xi, j, f, &wr, &wi);
-            }
         }
     }
     if (lane == 0) finish_window<InT>(a, f, dbg, w, frame);

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <string>
 
 #include "pmu_host.hpp"
@@ -15,12 +16,18 @@ namespace {
 template <typename T, int M, int KC, int PITCH, int WP = 1>
 int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
 {
-    static int configured[64];  // per device: dynamic smem already opted in for this instantiation
+    // per device: has this instantiation been opted in to the device's maximum dynamic shared memory?  The attribute
+    // is only ever set to that one value, so concurrent host threads (batches that share an instantiation but differ
+    // in smem_bytes) cannot lower it under each other's launches.
+    static std::atomic<int> configured[64];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess && (dev < 0 || dev >= 64 || configured[dev] != smem)) {
-        e = cudaFuncSetAttribute(pmu_fused_kernel<T, T, M, KC, PITCH, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev] = smem;
+    if (e == cudaSuccess && (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire))) {
+        int max_optin = smem;
+        e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(pmu_fused_kernel<T, T, M, KC, PITCH, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+        if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev].store(1, std::memory_order_release);
     }
     if (e == cudaSuccess) {
         // Programmatic dependent launch: when the previous operation in the stream is a kernel, this grid's CTAs may be
@@ -67,12 +74,14 @@ int launch_kc(int KC, const KernelArgs& a, int grid, int block, int smem, cudaSt
 template <typename T>
 int launch_wide(const KernelArgs& a, int grid, int smem, cudaStream_t s)
 {
-    static int configured[64];
+    static std::atomic<int> configured[64];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess && smem > 48 * 1024 && (dev < 0 || dev >= 64 || configured[dev] != smem)) {
-        e = cudaFuncSetAttribute(pmu_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev] = smem;
+    if (e == cudaSuccess && (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire))) {
+        int max_optin = smem;
+        e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pmu_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+        if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev].store(1, std::memory_order_release);
     }
     if (e == cudaSuccess) {
         pmu_wide_kernel<T><<<grid, PMU_WIDE_THREADS, smem, s>>>(a);

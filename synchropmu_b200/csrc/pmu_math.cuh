@@ -57,6 +57,19 @@ PMU_HD void pmu_sincospi(double x, double* s, double* c)
 #ifndef PMU_FAST_TRIG
 #define PMU_FAST_TRIG 1
 #endif
+// unroll factors of the estimator's bin loops (independent reciprocal / sweep chains per bin: the loops are latency-,
+// not issue-bound, so several bins in flight per lane pay)
+#ifndef PMU_UNROLL_COMP
+#define PMU_UNROLL_COMP 2
+#endif
+#ifndef PMU_UNROLL_RES
+#define PMU_UNROLL_RES 2
+#endif
+#ifndef PMU_FAST_SQRT
+#define PMU_FAST_SQRT 1
+#endif
+#define PMU_PRAGMA(x) _Pragma(#x)
+#define PMU_UNROLL(n) PMU_PRAGMA(unroll n)
 
 // sin(pi x), cos(pi x) for |x| <= 1/2 (the Dirichlet anchor r of a sweep): Taylor polynomials of the half angle
 // (|pi x / 2| <= pi/4: truncation < 5e-17) and one angle doubling, 21 FMAs in two independent chains instead of
@@ -125,6 +138,28 @@ PMU_HD double pmu_rcp(double x)
     return fma(r, e, r);
 #else
     return 1.0 / x;
+#endif
+}
+
+// sqrt(x) for x = |Y|^2 >= 0: hardware reciprocal-square-root seed + two coupled (Goldschmidt) iterations and a final
+// residual correction, within an ulp of the library routine without its slow-path branch.  0 -> 0; denormal or
+// infinite arguments (outside the documented |Y| range) give NaN.
+PMU_HD double pmu_sqrt(double x)
+{
+#if PMU_FAST_SQRT && defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    g = fma(fma(-g, g, x), h, g);
+    return x == 0.0 ? 0.0 : g;
+#else
+    return sqrt(x);
 #endif
 }
 
@@ -277,9 +312,9 @@ struct Peak {
 //   here     : exp(i ph) = (Y/|Y|) exp(-i pi d), sin(pi d) from the same sincospi.
 PMU_HD int ipdft_finish(const PostParams& p, const Peak& pk, Tone* t)
 {
-    double mk = sqrt(pk.best);
-    double ml = (pk.km == 0) ? mk : sqrt(pk.left);              // kl = km when km == 0 (:718)
-    double mr = (pk.km == p.K - 1) ? ml : sqrt(pk.right);       // kr = km-1 at the last bin (:719)
+    double mk = pmu_sqrt(pk.best);
+    double ml = (pk.km == 0) ? mk : pmu_sqrt(pk.left);          // kl = km when km == 0 (:718)
+    double mr = (pk.km == p.K - 1) ? ml : pmu_sqrt(pk.right);   // kr = km-1 at the last bin (:719)
     double d = 2 * (mr - ml) * pmu_rcp(ml + mr + 2 * mk);       // :598
     t->freq = (pk.km + d) * p.df;                               // :601
     double inv = pmu_rcp(mk);
@@ -339,28 +374,33 @@ struct Col {
 #endif
 };
 
-// One ipDFT over Y[j] (COMP=false) or over Y[j] - wf(j, -f, amp e^{-i ph}) (COMP=true,
+// One ipDFT over Y[j] (comp == false) or over Y[j] - wf(j, -f, amp e^{-i ph}) (comp == true,
 // the e_ipDFT inner loop :646-654).  km_out receives the chosen peak bin.
 //
 // The peak search (find3LargestIndx, :705-720: first strict maximum, a NaN only wins at bin 0) is a running scan
 // written so that every bin costs one compare and a handful of predicated moves: `up` is forced at bin 0 (so a NaN
 // there sticks, as every later compare against it is false), the right neighbour is whatever follows the bin that
 // took the lead last, the left neighbour is the bin before it.
-template <bool COMP>
-PMU_HD int ipdft_pass(const PostParams& p, const Col& Y, const Tone& prev, Tone* out, int* km_out)
+//
+// `comp` is a run-time flag on purpose: the plain and the compensated pass share ONE copy of the loop and of the
+// interpolation tail.  The estimator's working set of instructions is what bounds it when the interference
+// iterations run (ncu: `no_instruction` was the top stall with every call site inlined separately), so every routine
+// below exists exactly once in the kernel.
+PMU_HD int ipdft_pass(const PostParams& p, const Col& Y, bool comp, const Tone& prev, Tone* out, int* km_out)
 {
     Sweep sw;
     SweepWalk wk;
-    if (COMP) {
+    if (comp) {
         sw.init(p, -prev.freq, prev.amp * prev.cr, -prev.amp * prev.ci);  // amp e^{-i ph}, :646
         wk.start(p, sw);
     }
     Peak pk;
     pk.best = 0; pk.left = 0; pk.right = 0; pk.prev = 0; pk.yr = 0; pk.yi = 0; pk.km = 0;
     bool was_up = false;
+    PMU_UNROLL(PMU_UNROLL_COMP)
     for (int j = 0; j < p.K; ++j) {
         pmu_c y = Y.get(j);
-        if (COMP) {
+        if (comp) {
             double wr, wi;
             wk.step(p, sw, &wr, &wi);
             y.x -= wr;
@@ -381,24 +421,27 @@ PMU_HD int ipdft_pass(const PostParams& p, const Col& Y, const Tone& prev, Tone*
     return ipdft_finish(p, pk, out);
 }
 
-// e_ipDFT (src/pmu_estimator.c:626-664).
-PMU_HD void e_ipdft(const PostParams& p, const Col& Y, Tone* t, int* km_first)
+// e_ipDFT (src/pmu_estimator.c:626-664): the plain ipDFT, then up to P compensated ones; stops as soon as one of them
+// reports |delta| <= 1e-11.  Returns the peak bin of the first pass.
+PMU_HD int e_ipdft(const PostParams& p, const Col& Y, Tone* t)
 {
-    Tone cur = *t;
-    if (!ipdft_pass<false>(p, Y, cur, &cur, km_first)) {
-        for (int it = 0; it < p.P; ++it) {
-            Tone nxt;
-            int done = ipdft_pass<true>(p, Y, cur, &nxt, nullptr);
-            cur = nxt;
-            if (done) break;
-        }
+    Tone cur;
+    cur.amp = 0; cur.cr = 1; cur.ci = 0; cur.freq = 0;
+    int km_first = 0;
+    for (int it = 0; it <= p.P; ++it) {
+        Tone nxt;
+        int km;
+        const int done = ipdft_pass(p, Y, it > 0, cur, &nxt, &km);
+        if (it == 0) km_first = km;
+        cur = nxt;
+        if (done) break;
     }
     *t = cur;
+    return km_first;
 }
 
 // W[j] = X[j] - pureTone(t)[j]   (pureTone :563-577; Xi/Xf updates :215, :681-684, :692-695)
-// and, when ENERGY, Ed = sum |W[j]|^2, E = sum |X[j]|^2  (:219-220 compute cabs(z*z) = |z|^2).
-template <bool ENERGY>
+// and Ed = sum |W[j]|^2, E = sum |X[j]|^2  (:219-220 compute cabs(z*z) = |z|^2; only the first call's sums are used).
 PMU_HD void residual(const PostParams& p, const Col& X, const Tone& t, const Col& W, double* Ed, double* E)
 {
     Sweep sp, sn;
@@ -408,7 +451,7 @@ PMU_HD void residual(const PostParams& p, const Col& X, const Tone& t, const Col
     wp.start(p, sp);
     wn.start(p, sn);
     double ed = 0, e = 0;
-#pragma unroll 2
+    PMU_UNROLL(PMU_UNROLL_RES)
     for (int j = 0; j < p.K; ++j) {
         double ar, ai, br, bi;
         wp.step(p, sp, &ar, &ai);
@@ -417,12 +460,11 @@ PMU_HD void residual(const PostParams& p, const Col& X, const Tone& t, const Col
         double wr = x.x - (ar + br);
         double wi = x.y - (ai + bi);
         W.put(j, wr, wi);
-        if (ENERGY) {
-            ed += wr * wr + wi * wi;
-            e += x.x * x.x + x.y * x.y;
-        }
+        ed += wr * wr + wi * wi;
+        e += x.x * x.x + x.y * x.y;
     }
-    if (ENERGY) { *Ed = ed; *E = e; }
+    *Ed = ed;
+    *E = e;
 }
 
 // Bits of the per-window debug word (exported only through the debug entry point).
@@ -432,25 +474,29 @@ PMU_HD void residual(const PostParams& p, const Col& X, const Tone& t, const Col
 // Everything between the DFT and the ROCOF stage for one window:
 // src/pmu_estimator.c:205-233 (+ iter_e_ipDFT :666-703).  X holds the Hann-windowed
 // bins, W is scratch of the same shape.  Returns the debug word.
+//
+// The reference's sequence
+//     f  = e_ipDFT(X);  Xi = X - pure(f);  trigger test;
+//     Q x { it = e_ipDFT(Xi);  Xf = X - pure(it);  f = e_ipDFT(Xf);  [Xi = X - pure(f)] }
+// is one alternation  "estimate a tone from Y, subtract it from X into W"  with the roles of the two tones swapping, so
+// it runs here as a single loop of 2Q + 1 steps around one copy of e_ipdft and one copy of residual.
 PMU_HD int estimate_tone(const PostParams& p, const Col& X, const Col& W, Tone* out)
 {
     Tone f;
     f.amp = 0; f.cr = 1; f.ci = 0; f.freq = 0;
-    int km = 0;
-    e_ipdft(p, X, &f, &km);                                  // :205
-    int dbg = km & PMU_DBG_KM_MASK;
-    double Ed = 0, E = 0;
-    if (p.iter_en) residual<true>(p, X, f, W, &Ed, &E);      // :206-222  (W = Xi)
-    if (p.iter_en && Ed > p.eps * E) {                       // :227-229 (NaN compares false)
-        dbg |= PMU_DBG_TRIGGERED;
-        Tone it;
-        it.amp = 0; it.cr = 1; it.ci = 0; it.freq = 0;
-        for (int i = 0; i < p.Q; ++i) {                      // :675
-            e_ipdft(p, W, &it, nullptr);                     // :679   interference tone from Xi
-            residual<false>(p, X, it, W, nullptr, nullptr);  // :680-684  W = Xf = X - pure(it)
-            e_ipdft(p, W, &f, nullptr);                      // :685   fundamental from Xf
-            if (i + 1 < p.Q)
-                residual<false>(p, X, f, W, nullptr, nullptr);  // :690-695  W = Xi = X - pure(f)
+    int dbg = 0;
+    const int last = p.iter_en ? 2 * p.Q : 0;
+    for (int s = 0; s <= last; ++s) {
+        Tone t;
+        const int km = e_ipdft(p, s == 0 ? X : W, &t);       // :205 (s = 0), :679 (odd s: interference), :685 (even s)
+        if (s == 0) dbg = km & PMU_DBG_KM_MASK;
+        if (!(s & 1)) f = t;                                 // even steps estimate the fundamental
+        if (s == last || !p.iter_en) break;
+        double Ed, E;
+        residual(p, X, t, W, &Ed, &E);                       // :206-215, :680-684, :690-695
+        if (s == 0) {
+            if (!(Ed > p.eps * E)) break;                    // :227-229 (NaN compares false)
+            dbg |= PMU_DBG_TRIGGERED;
         }
     }
     *out = f;
