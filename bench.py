@@ -4,24 +4,33 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
 
-Workload (BASELINE.json config 3, the one the metric is quoted on): per GPU 4096 independent
-estimator instances x 6 channels, config/config.ini parameters (2048-sample window, 11 bins,
-P=3, Q=3, iterations enabled), streaming consecutive windows with ROCOF state carried in HBM.
-One step = one pmub_estimate_frames call = `--frames-per-step` (8) consecutive frames of every
-stream = 196608 estimates = one kernel launch; `single_frame_launch` in the output is the same
-kernel launched one frame (24576 estimates) at a time.  16 distinct consecutive frames (6.4 GB)
-are resident in HBM and cycled, so every step reads inputs far larger than the 126 MB L2.  Weak scaling: every rank owns its own 4096 instances, no collective on the hot
-path; the optional NCCL gather of frames to rank 0 is timed separately.
+Headline workload (BASELINE.json config 3, the one the metric is quoted on): per GPU 4096 independent
+estimator instances x 6 channels, config/config.ini parameters (2048-sample window, 11 bins, P=3, Q=3,
+iterations enabled), streaming consecutive windows with ROCOF state carried in HBM.  One step = one
+pmub_estimate_frames call = `--frames-per-step` (8) consecutive frames of every stream = 196608 estimates =
+one kernel launch.  16 distinct consecutive frames (6.4 GB) are resident in HBM and cycled, so every step
+reads inputs far larger than the 126 MB L2.  Weak scaling: every rank owns its own 4096 instances, no
+collective on the hot path; the optional NCCL gather of frames to rank 0 is timed separately.
 
-Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM;
-`e2e` = the same metric through the C ABI with pinned HOST buffers (H2D and D2H inside the
-timed region); `roofline` = algorithmic bytes / launch time against the measured HBM copy
-bandwidth; `cpu_baseline` = the reference CPU path on this box's host cores (a bounded sample).
+Prints ONE JSON line (rank 0):
+  value         device-timed throughput of the K timed steps, inputs resident in HBM
+  sustained     the same loop kept running for >= 1 s (CUDA-event timed; SM clock sampled over that second)
+  roofline      algorithmic bytes / launch time against the measured HBM copy bandwidth
+  workloads     the other configurations, each a short device-timed run with its own roofline fraction:
+                config 5 (600-sample windows, 1M/8 channels per GPU), M-class (3072 samples), the float build,
+                config 3 / M-class with EVERY stream triggering the interference iterations, the reference's
+                test2.c point (16 cycles @ 51.2 kHz = 16384 samples, 18 bins)
+  stream_device the streaming front end with its sample rings resident in HBM (device-timed)
+  e2e           the same metric through the synchronous C ABI call with pinned HOST buffers (H2D + D2H inside)
+  e2e_stream    ... through the streaming front end (only the new samples cross PCIe), double and int16 ingest
+  cpu_baseline  the reference CPU path on this box's host cores (a bounded sample)
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -45,6 +54,18 @@ WORKLOADS = {
     "config3": dict(cfg="config.ini", n_inst=4096, n_ch=6, desc="4096 instances x 6 ch, 2048-sample window (config.ini)"),
     "config5": dict(cfg="cfg5_600", n_inst=21846, n_ch=6, desc="131076 channels of 600-sample windows (1M/8 per GPU)"),
     "mclass": dict(cfg="m_class_config.ini", n_inst=4096, n_ch=6, desc="4096 instances x 6 ch, 3072-sample M-class window"),
+    "test2_n16384": dict(cfg="test2_16cyc", n_inst=1024, n_ch=6,
+                         desc="reference test2.c sweep point: 16 cycles @ 51.2 kHz = 16384-sample window, 18 bins"),
+}
+TRIG_TONE = [(0.1, 75.0, 0.0)]   # the 10 % interharmonic of test/test.c:60: every stream runs the Q loop
+# name -> (workload, dtype, every stream triggered, frames per launch)
+EXTRA_LEGS = {
+    "config5_f64": ("config5", "f64", False, 8),
+    "mclass_f64": ("mclass", "f64", False, 8),
+    "config3_f32": ("config3", "f32", False, 8),
+    "config3_f64_all_triggered": ("config3", "f64", True, 8),
+    "mclass_f64_all_triggered": ("mclass", "f64", True, 8),
+    "test2_n16384_f64": ("test2_n16384", "f64", False, 4),
 }
 
 
@@ -62,6 +83,9 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the `workloads` legs (other configurations)")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--extra-steps", type=int, default=50, help="timed launches per `workloads` leg")
     ap.add_argument("--interharmonic", action="store_true", help="add a 10 %% 75 Hz tone so the Q loop triggers")
     return ap.parse_args()
 
@@ -74,6 +98,29 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def kernel_source_hash() -> str:
+    """Hash of the CUDA sources the shipped library is built from: ncu-derived constants are only valid for it."""
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "synchropmu_b200" / "csrc").glob("*")):
+        if f.suffix in (".cu", ".cuh", ".cpp", ".hpp", ".c"):
+            h.update(f.name.encode())
+            h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(key: str):
+    """dram bytes per launch from the committed ncu capture - only if that capture was taken on THIS kernel source
+    (profiles/traffic_per_launch.json carries the source hash); otherwise None, never a stale constant."""
+    f = ROOT / "profiles" / "traffic_per_launch.json"
+    try:
+        d = json.loads(f.read_text())
+        if d.get("kernel_source_hash") == kernel_source_hash():
+            return d.get(key)
+    except Exception:
+        pass
+    return None
 
 
 # ------------------------------------------------------------------------------------------
@@ -99,7 +146,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -110,10 +157,12 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if (t0 is not None and ts < t0) or (t1 is not None and ts > t1):
+                continue
             parts = [p.strip() for p in r.split(",")]
             if len(parts) < 6:
                 continue
@@ -146,7 +195,7 @@ def cpu_reference_run(cfg, n_ch, dtype, sample_inst, sample_frames, steps, warmu
     N = configs.win_len(cfg)
     win = np.zeros((sample_frames, sample_inst, n_ch, N), dtype=npdt)
     mid = np.zeros((sample_frames, sample_inst))
-    harm = [(0.1, 75.0, 0.0)] if interharmonic else []
+    harm = TRIG_TONE if interharmonic else []
     for t in range(sample_frames):
         win[t] = signals.steady(cfg, t, prm["amp"], prm["freq"], prm["phase"], ramp=prm["ramp"],
                                 harmonics=harm).reshape(sample_inst, n_ch, N)
@@ -175,6 +224,250 @@ def cpu_reference_run(cfg, n_ch, dtype, sample_inst, sample_frames, steps, warmu
     return value, info, total / len(secs) * 1e3
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank's host threads (and so, by first touch, its pinned staging buffers) to the NUMA node the GPU
+    hangs off: with 8 ranks on one box the H2D copies otherwise cross the socket interconnect."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+class Bench:
+    def __init__(self, args):
+        import torch
+
+        self.torch = torch
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the estimator)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.numa_node = bind_to_gpu_numa_node(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.stream = torch.cuda.Stream(device=self.dev)   # a real (non-default) stream: the kernel and the timing
+        self.peak, self.peak_src = measured_peak()
+
+    # -- helpers ----------------------------------------------------------------------------
+    def max_over_ranks(self, v: float) -> float:
+        if self.dist is None:
+            return v
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def make_inputs(self, cfg, n_inst, n_ch, tdt, n_frames, harm):
+        """n_frames consecutive frames of this rank's shard of the (weak-scaled) population, built in HBM."""
+        torch = self.torch
+        prm = signals.three_phase_params(self.world * n_inst)
+        sl = slice(self.rank * n_inst * n_ch, (self.rank + 1) * n_inst * n_ch)
+        pt = {k: torch.as_tensor(v[sl], device=self.dev) for k, v in prm.items()}
+        N = configs.win_len(cfg)
+        win = torch.empty((n_frames, n_inst, n_ch, N), dtype=tdt, device=self.dev)
+        mid = torch.empty((n_frames, n_inst), dtype=tdt, device=self.dev)
+        for t in range(n_frames):
+            x = signals.steady(cfg, t, pt["amp"], pt["freq"], pt["phase"], xp=torch, ramp=pt["ramp"], harmonics=harm,
+                               like=pt["amp"])
+            win[t] = x.to(tdt).reshape(n_inst, n_ch, N)
+            mid[t] = signals.mid_fracsec(cfg, t)
+            del x
+        return win, mid
+
+    def timed_launches(self, fn, steps):
+        """CUDA-event time of `steps` calls of fn(i) on self.stream, max over ranks, in ms."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(self.stream)
+        torch.cuda.synchronize()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+    def device_leg(self, wl_name, dtype, triggered, F, steps, warmup=5):
+        """A short device-timed run of another configuration: {value, frac, ...}."""
+        from synchropmu_b200 import BatchEstimator
+
+        torch = self.torch
+        wl = WORKLOADS[wl_name]
+        cfg = configs.NAMED[wl["cfg"]]
+        n_inst, n_ch = wl["n_inst"], wl["n_ch"]
+        tdt = torch.float64 if dtype == "f64" else torch.float32
+        npdt = np.float64 if dtype == "f64" else np.float32
+        win, mid = self.make_inputs(cfg, n_inst, n_ch, tdt, F, TRIG_TONE if triggered else [])
+        out = torch.empty((F, n_inst, n_ch, 4), dtype=tdt, device=self.dev)
+        est = BatchEstimator(cfg, n_inst, n_ch, dtype=npdt, device=self.local_rank)
+        est.set_stream(self.stream.cuda_stream)
+        est.set_debug(True)                      # one untimed launch to count how many streams really trigger
+        est.estimate_frames_async(1, win[:1], mid[:1], out[:1])
+        torch.cuda.synchronize()
+        trig_frac = float(est.get_debug()[1].mean())
+        est.set_debug(False)
+        est.reset()
+
+        def go(i):
+            est.estimate_frames_async(F, win, mid, out)
+
+        for i in range(warmup):
+            go(i)
+        self.barrier()
+        ms = self.timed_launches(go, steps)
+        n_est = n_inst * n_ch * F
+        value = self.world * n_est * steps / (ms * 1e-3)
+        bpe = configs.bytes_per_estimate(cfg, 8 if dtype == "f64" else 4, n_ch)
+        finite = bool(torch.isfinite(out).all().item())
+        info = est.info
+        res = dict(value=value, unit=UNIT, frac=value / self.world * bpe / 1e9 / self.peak, ms_per_launch=ms / steps,
+                   launches=steps, estimates_per_launch=n_est, bytes_per_estimate=bpe, win_len=configs.win_len(cfg),
+                   n_bins=cfg["n_bins"], Q=cfg["Q"], dtype=dtype, triggered_fraction=trig_frac, outputs_finite=finite,
+                   workload=wl["desc"], ring_stages=int(info.n_stages))
+        est.close()
+        del win, mid, out
+        torch.cuda.empty_cache()
+        return res
+
+
+def stream_legs(B, est, cfg, n_inst, n_ch, tdt, npdt, win_all, args):
+    """The streaming front end (pmub_stream_*): sample rings resident in HBM, each push hands over the `hop` new samples
+    of every stream.  Three measurements:
+      stream_device   new samples already in HBM, F frames per push, CUDA-event timed (no host copy)
+      e2e_stream      pinned host samples in the batch dtype, one frame per synchronous push (as in round 1)
+      e2e_stream_i16  pinned host int16 ADC counts (promoted on the device, lossless), asynchronous pushes from two
+                      alternating buffers: the copy of push t+1 overlaps the kernels of push t; every push's frames are
+                      read on the host
+    """
+    torch = B.torch
+    world = B.world
+    N = configs.win_len(cfg)
+    hop = configs.hop(cfg)
+    itemsize = 8 if tdt == torch.float64 else 4
+    F = args.frames_per_step
+    n_est_frame = n_inst * n_ch
+    n_res = win_all.shape[0]
+
+    # ---- device-resident ------------------------------------------------------------------------------------------
+    torch.cuda.set_stream(B.stream)
+    est.set_stream(B.stream.cuda_stream)
+    est.reset()
+    est.stream_begin(hop=hop, max_frames_per_push=F, history=win_all[0][:, :, :N - hop].contiguous())
+    # frame t's new samples are the last `hop` samples of window t (t >= 1)
+    blocks = [torch.stack([win_all[(k * F + f + 1) % n_res][:, :, N - hop:] for f in range(F)]).contiguous() for k in range(2)]
+    d_out = torch.empty((F, n_inst, n_ch, 4), dtype=tdt, device=B.dev)
+    tickets = []
+    for i in range(3):
+        tickets.append(est.stream_push(blocks[i % 2], None, out=d_out, asynchronous=True)[1])
+    torch.cuda.synchronize()
+    n_push = max(10, min(args.steps, 100))
+    launches0 = est.launches
+    ms = B.timed_launches(lambda i: est.stream_push(blocks[i % 2], None, out=d_out, asynchronous=True), n_push)
+    est.sync()
+    v = world * n_est_frame * F * n_push / (ms * 1e-3)
+    s = itemsize
+    alg = hop * s + 4 * s + 2 * (3 * s + 1)                  # new samples in, frame out, ROCOF state in and out
+    moved = N * s + 2 * hop * s + 4 * s + 2 * (3 * s + 1)    # what this implementation moves: whole window from the ring + ingest
+    stream_device = dict(value=v, unit=UNIT, frames_per_push=F, pushes=n_push, ms_per_push=ms / n_push,
+                         gpu_launches=int(est.launches - launches0),
+                         roofline=dict(bound="hbm", algorithmic_bytes_per_estimate=alg, frac=v / world * alg / 1e9 / B.peak,
+                                       moved_bytes_per_estimate=moved, frac_of_bytes_moved=v / world * moved / 1e9 / B.peak,
+                                       peak=B.peak, unit="GB/s"),
+                         note="sample rings and the new samples resident in HBM; the estimator still reads each whole window "
+                              "from its ring (windows overlap by win_len - hop), so `frac` against the streaming-algorithmic bytes "
+                              "shows the reuse that is left on the table; the kernel itself is FP64-issue bound at this point")
+    del blocks, d_out
+
+    # ---- end to end, batch dtype, synchronous, one frame per push ---------------------------------------------------
+    torch.cuda.set_stream(torch.cuda.default_stream(B.dev))
+    est.set_stream(None)
+    est.reset()
+    est.stream_begin(hop=hop, max_frames_per_push=1, history=win_all[0][:, :, :N - hop].contiguous())
+    h_new = [torch.empty((1, n_inst, n_ch, hop), dtype=tdt).pin_memory() for _ in range(2)]
+    for i in range(2):
+        h_new[i][0].copy_(win_all[(i + 1) % n_res][:, :, N - hop:])
+    h_out = [torch.empty((1, n_inst, n_ch, 4), dtype=tdt).pin_memory() for _ in range(2)]
+    hn = [h.numpy() for h in h_new]
+    ho = [h.numpy() for h in h_out]
+    for i in range(2):
+        est.stream_push(hn[i % 2], None, out=ho[0])
+    B.barrier()
+    n_push = args.e2e_steps * 4
+    t0 = time.perf_counter()
+    for i in range(n_push):
+        est.stream_push(hn[i % 2], None, out=ho[0])
+        _ = float(ho[0][0, 0, 0, 2])
+    dt = B.max_over_ranks(time.perf_counter() - t0)
+    e2e_stream = dict(value=world * n_est_frame * n_push / dt, unit=UNIT,
+                      h2d_bytes_per_step=int(n_est_frame * hop * itemsize), d2h_bytes_per_step=int(n_est_frame * 4 * itemsize),
+                      steps=n_push, ms_per_step=dt / n_push * 1e3, host_memory="pinned", numa_node=B.numa_node,
+                      note="pmub_stream_push (synchronous): sample rings resident in HBM, one frame per call, only the "
+                           "%d new samples per stream are copied in, as %d-byte values" % (hop, itemsize))
+
+    # ---- end to end, int16 ADC counts, asynchronous double-buffered pushes --------------------------------------------
+    est.reset()
+    est.stream_begin(hop=hop, max_frames_per_push=1, history=win_all[0][:, :, :N - hop].contiguous())
+    amax = win_all[0].abs().amax(dim=2).clamp_min(1e-30)          # per stream
+    scale = (amax / 32000.0).double()
+    est.stream_set_scale(scale.reshape(-1).cpu().numpy())
+    q_new = [torch.empty((1, n_inst, n_ch, hop), dtype=torch.int16).pin_memory() for _ in range(2)]
+    for i in range(2):
+        q = torch.round(win_all[(i + 1) % n_res][:, :, N - hop:].double() / scale[:, :, None]).clamp_(-32768, 32767)
+        q_new[i][0].copy_(q.to(torch.int16))
+    qn = [h.numpy() for h in q_new]
+    prev = None
+    for i in range(3):
+        _, tk = est.stream_push(qn[i % 2], None, out=ho[i % 2], asynchronous=True)
+        est.stream_wait(tk)
+    B.barrier()
+    t0 = time.perf_counter()
+    for i in range(n_push):
+        _, tk = est.stream_push(qn[i % 2], None, out=ho[i % 2], asynchronous=True)
+        if prev is not None:
+            est.stream_wait(prev[0])
+            _ = float(ho[prev[1]][0, 0, 0, 2])     # the previous push's frames, read on the host while this one runs
+        prev = (tk, i % 2)
+    est.stream_wait(prev[0])
+    _ = float(ho[prev[1]][0, 0, 0, 2])
+    dt = B.max_over_ranks(time.perf_counter() - t0)
+    finite = bool(np.isfinite(ho[0]).all() and np.isfinite(ho[1]).all())
+    e2e_stream_i16 = dict(value=world * n_est_frame * n_push / dt, unit=UNIT,
+                          h2d_bytes_per_step=int(n_est_frame * hop * 2), d2h_bytes_per_step=int(n_est_frame * 4 * itemsize),
+                          steps=n_push, ms_per_step=dt / n_push * 1e3, host_memory="pinned", numa_node=B.numa_node,
+                          outputs_finite=finite,
+                          note="pmub_stream_push_ex(PMUB_SAMPLES_I16, PMUB_PUSH_ASYNC): int16 ADC counts x per-stream scale, promoted "
+                               "to the batch dtype on the device (exact), two alternating pinned buffers; every push's frames are read "
+                               "on the host one push later")
+    est.stream_set_scale(None)
+    return stream_device, e2e_stream, e2e_stream_i16
+
+
 def main():
     args = parse_args()
     wl = WORKLOADS[args.workload]
@@ -182,7 +475,6 @@ def main():
     n_inst, n_ch = wl["n_inst"], wl["n_ch"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     itemsize = 8 if args.dtype == "f64" else 4
     N = configs.win_len(cfg)
     bpe = configs.bytes_per_estimate(cfg, itemsize, n_ch)
@@ -211,40 +503,19 @@ def main():
         return
 
     # ---------------- our arm ----------------------------------------------------------------
-    import torch
-
+    B = Bench(args)
+    torch, dist, dev, local_rank = B.torch, B.dist, B.dev, B.local_rank
     from synchropmu_b200 import BatchEstimator
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the estimator)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
     tdt = torch.float64 if args.dtype == "f64" else torch.float32
     npdt = np.float64 if args.dtype == "f64" else np.float32
-
-    # this rank's shard of the (weak-scaled) population: world * n_inst instances in total
-    prm = signals.three_phase_params(world * n_inst)
-    sl = slice(rank * n_inst * n_ch, (rank + 1) * n_inst * n_ch)
-    pt = {k: torch.as_tensor(v[sl], device=dev) for k, v in prm.items()}
-    harm = [(0.1, 75.0, 0.0)] if args.interharmonic else []
+    harm = TRIG_TONE if args.interharmonic else []
     F = args.frames_per_step
     n_frames_res = F * args.sets
-    win_all = torch.empty((n_frames_res, n_inst, n_ch, N), dtype=tdt, device=dev)
-    mid_all = torch.empty((n_frames_res, n_inst), dtype=tdt, device=dev)
-    for t in range(n_frames_res):
-        x = signals.steady(cfg, t, pt["amp"], pt["freq"], pt["phase"], xp=torch, ramp=pt["ramp"], harmonics=harm,
-                           like=pt["amp"])
-        win_all[t] = x.to(tdt).reshape(n_inst, n_ch, N)
-        mid_all[t] = signals.mid_fracsec(cfg, t)
-        del x
+    win_all, mid_all = B.make_inputs(cfg, n_inst, n_ch, tdt, n_frames_res, harm)
     out = torch.empty((F, n_inst, n_ch, 4), dtype=tdt, device=dev)
     est = BatchEstimator(cfg, n_inst, n_ch, dtype=npdt, device=local_rank)
-    stream = torch.cuda.Stream(device=dev)   # a real (non-default) stream: the kernel and the timing
+    stream = B.stream
     torch.cuda.synchronize()
     torch.cuda.set_stream(stream)            # events below are recorded on the same stream
     est.set_stream(stream.cuda_stream)
@@ -254,46 +525,49 @@ def main():
         s0 = (i % args.sets) * F
         est.estimate_frames_async(F, win_all[s0:s0 + F], mid_all[s0:s0 + F], out)
 
-    for i in range(max(3, args.warmup)):
+    warm = max(3, args.warmup)
+    for i in range(warm):
         step(i)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-        torch.cuda.synchronize()
+    B.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.05)
     launches0 = est.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    ms_total = ev0.elapsed_time(ev1)
+    t_timed0 = time.perf_counter()
+    ms_total = B.timed_launches(step, args.steps)
     launches = est.launches - launches0
-    if dist is not None:
-        tmax = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.barrier()
-        ms_total = float(tmax.item())
-    clocks = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
-    if rank == 0:
-        if ms_total < 400.0:
-            # the timed region is too short for nvidia-smi's sampling period: keep the same kernel
-            # running (untimed) for ~1 s so that the clocks are sampled under the same load
-            t_end = time.time() + 1.0
-            i = 0
-            while time.time() < t_end:
-                for _ in range(200):
-                    step(i)
-                    i += 1
-                torch.cuda.synchronize()
-        sampler.stop()
-        clocks = sampler.summary()
     ms_per_step = ms_total / args.steps
     value = world * n_est_step * args.steps / (ms_total * 1e-3)
+
+    # ---------------- the same loop kept running for >= 1 s: what the part sustains once the power cap bites ------
+    sustained = None
+    t_sus0 = t_sus1 = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(math.ceil(1200.0 / ms_per_step)))
+        t_sus0 = time.perf_counter()
+        ms_sus = B.timed_launches(step, n_sus)
+        t_sus1 = time.perf_counter()
+        v_sus = world * n_est_step * n_sus / (ms_sus * 1e-3)
+        sustained = dict(value=v_sus, unit=UNIT, frac=v_sus / world * bpe / 1e9 / B.peak, steps=n_sus, seconds=ms_sus * 1e-3,
+                         ms_per_step=ms_sus / n_sus)
+    elif rank == 0 and ms_total < 400.0:
+        # no sustained leg: still keep the kernel running long enough for nvidia-smi's sampling period
+        t_end = time.time() + 1.0
+        i = 0
+        while time.time() < t_end:
+            for _ in range(200):
+                step(i)
+                i += 1
+            torch.cuda.synchronize()
+    clocks = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+    if rank == 0:
+        sampler.stop()
+        clocks = sampler.summary(t_timed0, None)
+        clocks["interval"] = "the K timed steps and the sustained loop that follows them without a gap (same kernel, same inputs)"
+        if sustained is not None:
+            cs = sampler.summary(t_sus0 + 0.1, t_sus1)
+            sustained.update(sm_mhz=cs["sm_mhz"], reasons=cs["reasons"], clock_samples=cs["samples"])
     finite = bool(torch.isfinite(out).all().item())
 
     # optional gather of the frames to rank 0 over NCCL/NVLink (off the hot path, timed separately)
@@ -318,14 +592,9 @@ def main():
         n1 = max(20, min(args.steps * F, 400))
         for i in range(5):
             est.estimate_async(win_all[i % n_frames_res], mid_all[i % n_frames_res], out1)
-        s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0e.record(stream)
-        for i in range(n1):
-            est.estimate_async(win_all[i % n_frames_res], mid_all[i % n_frames_res], out1)
-        s1e.record(stream)
-        torch.cuda.synchronize()
-        ms1 = s0e.elapsed_time(s1e) / n1
-        single = dict(value=world * n_inst * n_ch / (ms1 * 1e-3), unit=UNIT, ms_per_launch=ms1,
+        ms1 = B.timed_launches(lambda i: est.estimate_async(win_all[i % n_frames_res], mid_all[i % n_frames_res], out1), n1) / n1
+        v1 = world * n_inst * n_ch / (ms1 * 1e-3)
+        single = dict(value=v1, unit=UNIT, frac=v1 / world * bpe / 1e9 / B.peak, ms_per_launch=ms1,
                       note="one frame (%d estimates) per kernel launch" % (n_inst * n_ch))
 
     # ---------------- frames written straight into rank 0's HBM by the kernel (P2P stores over NVLink,
@@ -349,15 +618,12 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
         n2 = max(10, args.steps // 4)
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record(stream)
-        for i in range(n2):
+
+        def step_remote(i):
             s0 = (i % args.sets) * F
             est.estimate_frames_async(F, win_all[s0:s0 + F], mid_all[s0:s0 + F], remote)
-        p1.record(stream)
-        torch.cuda.synchronize()
-        tp = torch.tensor([p0.elapsed_time(p1)], device=dev)
-        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+
+        tp = B.timed_launches(step_remote, n2)
         # one more pass on a known set, into rank 0 and locally, to check that the remote copy is the same data
         est.reset()
         est.estimate_frames_async(F, win_all[0:F], mid_all[0:F], remote)
@@ -372,7 +638,7 @@ def main():
         if rank == 0:
             got = _api.peer_read(base, (world, F, n_inst, n_ch, 4), npdt).astype(np.float64).sum(axis=(1, 2, 3))
             ok = bool(np.allclose(got, np.array(all_sums), rtol=1e-12, atol=0))
-        p2p = dict(value=world * n_est_step * n2 / (float(tp.item()) * 1e-3), unit=UNIT, steps=n2, verified=ok,
+        p2p = dict(value=world * n_est_step * n2 / (tp * 1e-3), unit=UNIT, steps=n2, verified=ok,
                    note="same launches with `frames` pointing into rank 0's HBM (CUDA IPC): frame stores cross NVLink, no collective")
         dist.barrier()
         if rank != 0:
@@ -394,82 +660,61 @@ def main():
         hout = host_out.numpy()
         for i in range(2):
             est.estimate(hin[i % 2], hmid[i % 2], out=hout)
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
+        B.barrier()
         t0 = time.perf_counter()
         for i in range(args.e2e_steps):
             est.estimate(hin[i % 2], hmid[i % 2], out=hout)
             _ = float(hout[0, 0, 2])                      # the step's result is read on the host
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            tm = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dt = float(tm.item())
+        dt = B.max_over_ranks(time.perf_counter() - t0)
         e2e = dict(value=world * n_inst * n_ch * args.e2e_steps / dt, unit=UNIT,
                    h2d_bytes_per_step=int(n_inst * n_ch * N * itemsize + n_inst * itemsize),
                    d2h_bytes_per_step=int(n_inst * n_ch * 4 * itemsize), steps=args.e2e_steps,
-                   ms_per_step=dt / args.e2e_steps * 1e3, host_memory="pinned",
+                   ms_per_step=dt / args.e2e_steps * 1e3, host_memory="pinned", numa_node=B.numa_node,
                    note="one frame per synchronous pmub_estimate call, H2D of the windows and D2H of the frames inside")
+        del host_in, hin
 
-    # ---------------- e2e through the streaming front end: only the hop new samples cross PCIe ----
+    # ---------------- the streaming front end: device-resident, then end to end ----------------------------------
+    stream_device = None
     e2e_stream = None
+    e2e_stream_i16 = None
     if not args.no_e2e:
-        hop = configs.hop(cfg)
-        est.stream_begin(hop=hop, max_frames_per_push=1, history=win_all[0][:, :, :N - hop].contiguous())
-        h_new = [torch.empty((1, n_inst, n_ch, hop), dtype=tdt).pin_memory() for _ in range(2)]
-        for i in range(2):
-            h_new[i][0].copy_(win_all[(i + 1) % n_frames_res][:, :, N - hop:])
-        h_out = torch.empty((1, n_inst, n_ch, 4), dtype=tdt).pin_memory()
-        hn = [h.numpy() for h in h_new]
-        ho = h_out.numpy()
-        for i in range(2):
-            est.stream_push(hn[i % 2], None, out=ho)
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        t0 = time.perf_counter()
-        n_push = args.e2e_steps * 4
-        for i in range(n_push):
-            est.stream_push(hn[i % 2], None, out=ho)
-            _ = float(ho[0, 0, 0, 2])
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            tm = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dt = float(tm.item())
-        e2e_stream = dict(value=world * n_inst * n_ch * n_push / dt, unit=UNIT,
-                          h2d_bytes_per_step=int(n_inst * n_ch * hop * itemsize),
-                          d2h_bytes_per_step=int(n_inst * n_ch * 4 * itemsize), steps=n_push,
-                          ms_per_step=dt / n_push * 1e3, host_memory="pinned",
-                          note="pmub_stream_push: sample rings resident in HBM, one frame per call, only the "
-                               "%d new samples per stream are copied in" % hop)
+        stream_device, e2e_stream, e2e_stream_i16 = stream_legs(B, est, cfg, n_inst, n_ch, tdt, npdt, win_all, args)
+
+    est.close()
+    del win_all, mid_all, out
+    torch.cuda.empty_cache()
+
+    # ---------------- the other configurations (short runs) ---------------------------------------------------------
+    workloads = None
+    if not args.no_workloads:
+        workloads = {}
+        torch.cuda.set_stream(stream)
+        for name, (wl_name, dt_name, trig, f_leg) in EXTRA_LEGS.items():
+            try:
+                workloads[name] = B.device_leg(wl_name, dt_name, trig, f_leg, args.extra_steps)
+            except Exception as e:   # a leg that cannot run is reported, it does not take the headline down
+                workloads[name] = dict(error=str(e)[:300])
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peak()
     achieved = bpe * n_est_step / (ms_per_step * 1e-3) / 1e9
-    traffic = None
-    tr_file = ROOT / "profiles" / "traffic_per_launch.json"
-    if tr_file.exists():
-        try:
-            traffic = json.loads(tr_file.read_text()).get(f"{args.workload}_{args.dtype}")
-        except Exception:
-            traffic = None
-    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                    peak_source=peak_src, kernel="pmu_fused_kernel", bytes_per_estimate=bpe,
-                    estimates_per_launch=n_est_step, launch_ms=ms_per_step)
+    roofline = dict(bound="hbm", achieved=achieved, peak=B.peak, unit="GB/s", frac=achieved / B.peak,
+                    traffic=measured_traffic(f"{args.workload}_{args.dtype}"), traffic_source="profiles/traffic_per_launch.json "
+                    "(ncu dram__bytes_read+write of one launch; used only when its kernel_source_hash matches the tree)",
+                    peak_source=B.peak_src, kernel="pmu_fused_kernel", bytes_per_estimate=bpe,
+                    estimates_per_launch=n_est_step, launch_ms=ms_per_step, kernel_source_hash=kernel_source_hash())
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         _, cpu_baseline, _ = cpu_reference_run(cfg, n_ch, args.dtype, 256, 4, 3, 1, args.interharmonic)
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm,
                 ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype,
                 data="synthetic", config=config, roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, clocks=clocks,
-                gpu_launches=int(launches), outputs_finite=finite, impl="ours", single_frame_launch=single,
-                e2e_stream=e2e_stream)
+                gpu_launches=int(launches), outputs_finite=finite, impl="ours", sustained=sustained,
+                single_frame_launch=single, stream_device=stream_device, e2e_stream=e2e_stream,
+                e2e_stream_i16=e2e_stream_i16, workloads=workloads)
     if gather_ms is not None:
         line["frame_gather_ms"] = gather_ms
         line["frames_p2p_to_rank0"] = p2p

@@ -134,6 +134,26 @@ int pmub_stream_begin(pmub_batch *b, unsigned hop, unsigned max_frames_per_push,
                       unsigned long long first_sample_index);
 int pmub_stream_push(pmub_batch *b, int n_frames, const void *new_samples, const void *mid_fracsec,
                      void *frames);
+/* The general push: narrow sample formats and/or asynchronous operation.
+ *   sample_format  PMUB_SAMPLES_NATIVE  float_p samples (what pmub_stream_push takes)
+ *                  PMUB_SAMPLES_F32     float samples promoted on the device (for the double estimator)
+ *                  PMUB_SAMPLES_I16     int16 ADC counts; sample = scale[stream] * count with the factors given to
+ *                                       pmub_stream_set_scale (host double [n_instances * n_channels], NULL = 1).
+ *                  Promotion is exact, so the frames equal what pmub_estimate returns for windows holding the same
+ *                  promoted values; only 4 or 2 bytes per sample cross PCIe.
+ *   flags          PMUB_PUSH_ASYNC: return as soon as the work is queued.  `samples`, `mid_fracsec` and `frames` must
+ *                  stay valid until pmub_stream_wait(ticket) (or pmub_sync) returns; with two alternating pinned
+ *                  sample buffers the host-to-device copy of push t+1 overlaps the kernels of push t.  At most four
+ *                  pushes are kept in flight (a fifth waits for the oldest).
+ *   ticket         (may be NULL) receives the push's sequence number for pmub_stream_wait. */
+#define PMUB_SAMPLES_NATIVE 0
+#define PMUB_SAMPLES_F32 1
+#define PMUB_SAMPLES_I16 2
+#define PMUB_PUSH_ASYNC 1u
+int pmub_stream_set_scale(pmub_batch *b, const double *scale);
+int pmub_stream_push_ex(pmub_batch *b, int n_frames, const void *samples, int sample_format,
+                        const void *mid_fracsec, void *frames, unsigned flags, unsigned long long *ticket);
+int pmub_stream_wait(pmub_batch *b, unsigned long long ticket);
 int pmub_sync(pmub_batch *b);
 /* Run on the caller's CUDA stream (cudaStream_t passed as void*); NULL = own stream. */
 int pmub_set_stream(pmub_batch *b, void *cuda_stream);

@@ -22,6 +22,8 @@ LIB_DIR = PKG / "lib"
 CSRC = PKG / "csrc"
 
 PMUB_F32, PMUB_F64 = 4, 8
+SAMPLES_NATIVE, SAMPLES_F32, SAMPLES_I16 = 0, 1, 2   # pmub_stream_push_ex sample formats
+PUSH_ASYNC = 1
 
 
 class CoreConfig(C.Structure):
@@ -111,6 +113,9 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.pmub_estimate_frames_async.argtypes = [vp, ip, vp, vp, vp]
     lib.pmub_stream_begin.argtypes = [vp, C.c_uint, C.c_uint, vp, C.c_ulonglong]
     lib.pmub_stream_push.argtypes = [vp, ip, vp, vp, vp]
+    lib.pmub_stream_push_ex.argtypes = [vp, ip, vp, ip, vp, vp, C.c_uint, C.POINTER(C.c_ulonglong)]
+    lib.pmub_stream_set_scale.argtypes = [vp, vp]
+    lib.pmub_stream_wait.argtypes = [vp, C.c_ulonglong]
     lib.pmub_sync.argtypes = [vp]
     lib.pmub_set_stream.argtypes = [vp, vp]
     lib.pmub_launch_count.argtypes = [vp]
@@ -133,7 +138,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
         getattr(lib, fn).restype = ip
     for fn in ("pmub_validate", "pmub_parse_ini", "pmub_create", "pmub_create_ini", "pmub_destroy",
                "pmub_get_info", "pmub_estimate", "pmub_estimate_async", "pmub_estimate_frames",
-               "pmub_estimate_frames_async", "pmub_stream_begin", "pmub_stream_push", "pmub_sync", "pmub_set_stream",
+               "pmub_estimate_frames_async", "pmub_stream_begin", "pmub_stream_push", "pmub_stream_push_ex",
+               "pmub_stream_set_scale", "pmub_stream_wait", "pmub_sync", "pmub_set_stream",
                "pmub_reset", "pmub_get_state", "pmub_set_state", "pmub_set_debug", "pmub_get_debug"):
         getattr(lib, fn).restype = ip
     if path is None:
@@ -289,9 +295,23 @@ class BatchEstimator:
         self.max_frames_per_push = max(1, int(max_frames_per_push))
         return self.hop
 
-    def stream_push(self, new_samples, mid_fracsec=None, out=None):
+    def stream_set_scale(self, scale) -> None:
+        """Per-stream factors of the int16 sample format: sample = scale[stream] * count (None = 1)."""
+        if scale is None:
+            self._check(self.lib.pmub_stream_set_scale(self._h, None), "pmub_stream_set_scale")
+            return
+        sc = np.ascontiguousarray(scale, dtype=np.float64).reshape(-1)
+        assert sc.size == self.n_instances * self.n_channels
+        self._check(self.lib.pmub_stream_set_scale(self._h, sc.ctypes.data), "pmub_stream_set_scale")
+
+    def stream_push(self, new_samples, mid_fracsec=None, out=None, asynchronous: bool = False):
         """``new_samples [F, n_instances, n_channels, hop]`` -> frames ``[F, n_instances, n_channels, 4]``;
-        ``mid_fracsec [F, n_instances]`` or None (computed on the device from the sample counter)."""
+        ``mid_fracsec [F, n_instances]`` or None (computed on the device from the sample counter).
+
+        The sample format follows the dtype of ``new_samples``: the batch dtype (native), float32 into a double
+        batch (promoted on the device) or int16 ADC counts (times the factors of :meth:`stream_set_scale`).
+        ``asynchronous=True`` queues the push and returns ``(out, ticket)``: ``out`` (and the inputs) must stay alive
+        until :meth:`stream_wait` has returned for that ticket."""
         n, c = self.n_instances, self.n_channels
         if getattr(self, "hop", None) is None:
             raise RuntimeError("stream_push before stream_begin")
@@ -303,24 +323,45 @@ class BatchEstimator:
             import torch
 
             tdt = torch.float64 if self.dtype == np.float64 else torch.float32
-            assert new_samples.dtype == tdt and new_samples.is_contiguous()
+            fmt = {tdt: SAMPLES_NATIVE, torch.float32: SAMPLES_F32, torch.int16: SAMPLES_I16}.get(new_samples.dtype)
+            assert fmt is not None and new_samples.is_contiguous(), "samples must be the batch dtype, float32 or int16"
             assert new_samples.numel() == F * n * c * self.hop, "new_samples must be [F, n_instances, n_channels, hop]"
             if mid_fracsec is not None:
                 assert mid_fracsec.dtype == tdt and mid_fracsec.is_contiguous() and mid_fracsec.numel() == F * n
             if out is None:
                 out = torch.empty((F, n, c, 4), dtype=tdt, device=new_samples.device)
         else:
-            new_samples = np.ascontiguousarray(new_samples, dtype=self.dtype)
+            new_samples = np.asarray(new_samples)
+            if new_samples.dtype == np.int16:
+                fmt = SAMPLES_I16
+            elif new_samples.dtype == np.float32 and self.dtype == np.float64:
+                fmt = SAMPLES_F32
+            else:
+                fmt = SAMPLES_NATIVE
+                new_samples = new_samples.astype(self.dtype, copy=False)
+            new_samples = np.ascontiguousarray(new_samples)
             assert new_samples.size == F * n * c * self.hop, "new_samples must be [F, n_instances, n_channels, hop]"
             if mid_fracsec is not None:
                 mid_fracsec = np.ascontiguousarray(mid_fracsec, dtype=self.dtype)
                 assert mid_fracsec.size == F * n
             if out is None:
                 out = np.empty((F, n, c, 4), dtype=self.dtype)
-        self._check(self.lib.pmub_stream_push(self._h, F, _ptr(new_samples),
-                                              _ptr(mid_fracsec) if mid_fracsec is not None else None, _ptr(out)),
-                    "pmub_stream_push")
+        mid_p = _ptr(mid_fracsec) if mid_fracsec is not None else None
+        if fmt == SAMPLES_NATIVE and not asynchronous:
+            self._check(self.lib.pmub_stream_push(self._h, F, _ptr(new_samples), mid_p, _ptr(out)), "pmub_stream_push")
+            return out
+        ticket = C.c_ulonglong(0)
+        self._check(self.lib.pmub_stream_push_ex(self._h, F, _ptr(new_samples), fmt, mid_p, _ptr(out),
+                                                 PUSH_ASYNC if asynchronous else 0, C.byref(ticket)), "pmub_stream_push_ex")
+        if asynchronous:
+            # the library keeps at most four pushes in flight: hold on to the buffers of the last four
+            self._keepalive = (getattr(self, "_keepalive", None) or [])[-3:] + [(new_samples, mid_fracsec, out)]
+            return out, int(ticket.value)
         return out
+
+    def stream_wait(self, ticket: int) -> None:
+        """Block until the asynchronous push that returned ``ticket`` has delivered its frames."""
+        self._check(self.lib.pmub_stream_wait(self._h, int(ticket)), "pmub_stream_wait")
 
     def estimate_frames_async(self, n_frames: int, d_windows, d_mid_fracsec, d_out) -> None:
         self._check(self.lib.pmub_estimate_frames_async(self._h, int(n_frames), _ptr(d_windows), _ptr(d_mid_fracsec),

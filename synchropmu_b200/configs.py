@@ -20,6 +20,10 @@ CFG5_600 = dict(n_cycles=3, f0=50, frame_rate=50, fs=10000, n_bins=8, P=3, Q=3,
                 iter_eipdft=1, interf_trig=0.0033, **_ROCOF)
 TEST_C_Q22 = dict(n_cycles=4, f0=50, frame_rate=50, fs=25600, n_bins=11, P=3, Q=22,
                   iter_eipdft=1, interf_trig=0.0033, **_ROCOF)
+# one point of the reference's wall-time sweep (test/test2.c:62-76: fs = 51.2 kHz, n_cycles = 16 -> 16384 samples,
+# n_bins = n_cycles + 2 = 18, first Q of the sweep)
+TEST2_16CYC = dict(n_cycles=16, f0=50, frame_rate=50, fs=51200, n_bins=18, P=3, Q=3,
+                   iter_eipdft=1, interf_trig=0.0033, **_ROCOF)
 
 NAMED = {
     "config.ini": DEFAULT_INI,
@@ -27,6 +31,7 @@ NAMED = {
     "m_class_config.ini": M_CLASS_INI,
     "cfg5_600": CFG5_600,
     "test_c_q22": TEST_C_Q22,
+    "test2_16cyc": TEST2_16CYC,
 }
 
 

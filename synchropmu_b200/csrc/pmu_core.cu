@@ -57,6 +57,14 @@ struct pmub_batch {
     unsigned long long stream_origin, stream_pushed;  // absolute index of sample 0; samples pushed so far
     unsigned char* d_push;      // staging of a push's new samples when they are scattered by a kernel (lazy)
     size_t d_push_cap;
+    // asynchronous / narrow-format ingest (pmub_stream_push_ex): two staging slots so that the host->device copy of
+    // push t+1 overlaps the kernel of push t, per-stream scale factors for integer samples
+    unsigned char* d_stage[2];
+    size_t d_stage_cap[2];
+    cudaEvent_t ev_h2d[2], ev_ingested[2], ev_done[4];
+    bool ev_ingested_valid[2], ev_done_valid[4];
+    double* d_scale;
+    unsigned long long push_no;
     int* d_dbg;
     double* d_spec;
     unsigned long long* d_timeline;   // profiling aid (pmub_debug_timeline)
@@ -253,12 +261,14 @@ static int ensure_cap(unsigned char** p, size_t* cap, size_t need)
     return 0;
 }
 
-// Ingest of the streaming front end when the per-stream block is too narrow for an efficient 2-D DMA:
-// the new samples arrive as one contiguous copy and this kernel scatters them into the rings.
-//   src [n_frames][n_streams][hop] -> ring[w][(wpos + f*hop + j) mod cap]   (elements of `esz` bytes)
-template <typename T>
-__global__ void ring_scatter_kernel(T* __restrict__ ring, const T* __restrict__ src, long long n_streams, long long w0,
-                                    long long w1, int n_frames, int hop, long long cap, long long wpos)
+// Ingest of the streaming front end: the new samples arrive as one contiguous block (host copy or device buffer) and
+// this kernel scatters them into the per-stream rings, promoting narrow sample formats on the way:
+//   src [n_frames][n_streams][hop] -> ring[w][(wpos + f*hop + j) mod cap] = (RingT)(scale[w] * src)   (scale == nullptr: 1)
+// HBM-bound, trivially: reads hop * sizeof(SrcT) and writes hop * sizeof(RingT) per stream and frame.
+template <typename RingT, typename SrcT>
+__global__ void ring_scatter_kernel(RingT* __restrict__ ring, const SrcT* __restrict__ src, const double* __restrict__ scale,
+                                    long long n_streams, long long w0, long long w1, int n_frames, int hop, long long cap,
+                                    long long wpos)
 {
     const long long per_frame = (w1 - w0) * hop;
     const long long total = per_frame * n_frames;
@@ -269,8 +279,26 @@ __global__ void ring_scatter_kernel(T* __restrict__ ring, const T* __restrict__ 
         const int j = (int)(r % hop);
         long long p = wpos + (long long)f * hop + j;
         p %= cap;
-        ring[w * cap + p] = src[((long long)f * n_streams + w) * hop + j];
+        const SrcT v = src[((long long)f * n_streams + w) * hop + j];
+        ring[w * cap + p] = scale ? (RingT)(scale[w] * (double)v) : (RingT)v;
     }
+}
+
+template <typename SrcT>
+static cudaError_t launch_scatter(pmub_batch* b, const void* src, const double* scale, long long w0, long long w1, int n_frames,
+                                  cudaStream_t s)
+{
+    const long long total = (w1 - w0) * b->hop * n_frames;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > b->num_sms * 16) blocks = b->num_sms * 16;
+    if (blocks < 1) blocks = 1;
+    if (b->dtype == PMUB_F64)
+        ring_scatter_kernel<double, SrcT><<<blocks, 256, 0, s>>>((double*)b->d_ring, (const SrcT*)src, scale, b->n_windows, w0, w1,
+                                                                  n_frames, b->hop, b->ring_cap, b->ring_wpos);
+    else
+        ring_scatter_kernel<float, SrcT><<<blocks, 256, 0, s>>>((float*)b->d_ring, (const SrcT*)src, scale, b->n_windows, w0, w1,
+                                                                 n_frames, b->hop, b->ring_cap, b->ring_wpos);
+    return cudaGetLastError();
 }
 
 static bool is_device_ptr(const void* p)
@@ -297,6 +325,13 @@ static int free_batch(pmub_batch* b)
     cudaFree(b->st_fold); cudaFree(b->st_dl0); cudaFree(b->st_dl1); cudaFree(b->st_state);
     cudaFree(b->d_windows); cudaFree(b->d_mid); cudaFree(b->d_out); cudaFree(b->d_frames); cudaFree(b->d_ring); cudaFree(b->d_push);
     cudaFree(b->d_dbg); cudaFree(b->d_spec); cudaFree(b->d_timeline);
+    cudaFree(b->d_stage[0]); cudaFree(b->d_stage[1]); cudaFree(b->d_scale);
+    for (int i = 0; i < 2; ++i) {
+        if (b->ev_h2d[i]) cudaEventDestroy(b->ev_h2d[i]);
+        if (b->ev_ingested[i]) cudaEventDestroy(b->ev_ingested[i]);
+    }
+    for (int i = 0; i < 4; ++i)
+        if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
     if (b->h_in) cudaFreeHost(b->h_in);
     if (b->h_out) cudaFreeHost(b->h_out);
     for (int i = 0; i < 2; ++i)
@@ -405,6 +440,11 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     CK(cudaStreamCreateWithFlags(&b->stream[0], cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&b->stream[1], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&b->ev_order, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&b->ev_h2d[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b->ev_ingested[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming));
     // small batches (the single-instance pmu_estimate path) go through pinned staging
     const size_t in_bytes = n * b->d.N * (size_t)dtype + (size_t)n_instances * dtype;
     if (in_bytes <= (size_t)(4 << 20)) {
@@ -692,15 +732,8 @@ int pmub_stream_push(pmub_batch* b, int n_frames, const void* new_samples, const
                                             (size_t)(w1 - w0) * (size_t)hop * sz, cudaMemcpyHostToDevice, s));
                 src = b->d_push;
             }
-            const long long total = (w1 - w0) * hop * n_frames;
-            int blocks = (int)((total + 255) / 256);
-            if (blocks > b->num_sms * 16) blocks = b->num_sms * 16;
-            if (sz == 8)
-                ring_scatter_kernel<double><<<blocks, 256, 0, s>>>((double*)b->d_ring, (const double*)src, (long long)n, w0, w1, n_frames,
-                                                                    (int)hop, cap, b->ring_wpos);
-            else
-                ring_scatter_kernel<float><<<blocks, 256, 0, s>>>((float*)b->d_ring, (const float*)src, (long long)n, w0, w1, n_frames,
-                                                                   (int)hop, cap, b->ring_wpos);
+            if (sz == 8) CUDA_OK(launch_scatter<double>(b, src, nullptr, w0, w1, n_frames, s));
+            else CUDA_OK(launch_scatter<float>(b, src, nullptr, w0, w1, n_frames, s));
             CUDA_OK(cudaGetLastError());
         }
         if (launch_frames(b, w0, w1, n_frames, nullptr, dM, dF, nullptr, s, &ring)) return -1;
@@ -711,6 +744,132 @@ int pmub_stream_push(pmub_batch* b, int n_frames, const void* new_samples, const
     b->ring_wpos = (b->ring_wpos + (long long)n_frames * hop) % cap;
     b->stream_pushed += (unsigned long long)n_frames * (unsigned long long)hop;
     return pmub_sync(b);
+}
+
+// Per-stream scale factors of integer sample formats (sample = scale[stream] * count); NULL = 1.
+int pmub_stream_set_scale(pmub_batch* b, const double* scale)
+{
+    if (!b) { set_error("[pmu_stream] ERROR: NULL batch"); return -1; }
+    CUDA_OK(cudaSetDevice(b->device));
+    if (pmub_sync(b)) return -1;
+    if (!scale) {
+        cudaFree(b->d_scale);
+        b->d_scale = nullptr;
+        return 0;
+    }
+    if (!b->d_scale) CUDA_OK(cudaMalloc(&b->d_scale, (size_t)b->n_windows * sizeof(double)));
+    CUDA_OK(cudaMemcpy(b->d_scale, scale, (size_t)b->n_windows * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static size_t sample_bytes(const pmub_batch* b, int fmt)
+{
+    switch (fmt) {
+        case PMUB_SAMPLES_NATIVE: return (size_t)b->dtype;
+        case PMUB_SAMPLES_F32: return 4;
+        case PMUB_SAMPLES_I16: return 2;
+    }
+    return 0;
+}
+
+// The general push: any sample format, optionally asynchronous.  Host samples are copied into one of two staging
+// slots on a copy stream (the copy of push t+1 overlaps the kernels of push t), scattered / promoted into the rings and
+// estimated on the compute stream; the frames go back with an asynchronous copy and an event marks the push complete.
+int pmub_stream_push_ex(pmub_batch* b, int n_frames, const void* samples, int sample_format, const void* mid, void* frames,
+                        unsigned flags, unsigned long long* ticket)
+{
+    if (!b || !b->d_ring) { set_error("[pmu_stream] ERROR: call pmub_stream_begin first"); return -1; }
+    const size_t esz = b ? sample_bytes(b, sample_format) : 0;
+    if (!samples || !frames || n_frames < 1 || n_frames > b->stream_max_frames || esz == 0) {
+        set_error("[pmu_stream] ERROR: bad argument (n_frames must be 1..max_frames_per_push, sample_format one of PMUB_SAMPLES_*)");
+        return -1;
+    }
+    if (sample_format == PMUB_SAMPLES_NATIVE && !(flags & PMUB_PUSH_ASYNC)) {
+        if (ticket) *ticket = b->push_no;
+        return pmub_stream_push(b, n_frames, samples, mid, frames);
+    }
+    CUDA_OK(cudaSetDevice(b->device));
+    const size_t sz = (size_t)b->dtype;
+    const size_t n = (size_t)b->n_windows;
+    const long long cap = b->ring_cap, hop = b->hop, N = b->d.N;
+    const size_t mid_bytes = (size_t)b->n_inst * sz, fr_bytes = n * 4 * sz;   // per frame
+    const size_t in_bytes = n * (size_t)hop * esz * n_frames;
+    const bool in_dev = is_device_ptr(samples), mid_dev = mid ? is_device_ptr(mid) : true, fr_dev = is_device_ptr(frames);
+    if (mid && !mid_dev && ensure_cap(&b->d_mid, &b->d_mid_cap, mid_bytes * n_frames)) return -1;
+    if (!fr_dev && ensure_cap(&b->d_frames, &b->d_frames_cap, fr_bytes * n_frames)) return -1;
+    const int slot = (int)(b->push_no & 1);
+    const int dslot = (int)(b->push_no & 3);
+    cudaStream_t s_copy = b->has_user_stream ? b->user_stream : b->stream[0];
+    cudaStream_t s_comp = b->has_user_stream ? b->user_stream : b->stream[1];
+    if (!b->has_user_stream) {
+        // start after whatever the caller already queued on the (legacy) default stream, e.g. the producer of device samples
+        CUDA_OK(cudaEventRecord(b->ev_order, main_stream(b)));
+        CUDA_OK(cudaStreamWaitEvent(s_copy, b->ev_order, 0));
+        CUDA_OK(cudaStreamWaitEvent(s_comp, b->ev_order, 0));
+    }
+    // at most four pushes in flight: the completion event about to be reused must have fired
+    if (b->ev_done_valid[dslot]) CUDA_OK(cudaEventSynchronize(b->ev_done[dslot]));
+    const void* src = samples;
+    if (!in_dev) {
+        if (b->d_stage_cap[slot] < in_bytes) {
+            // growing a slot: nothing may still be reading the old allocation
+            if (pmub_sync(b)) return -1;
+            if (ensure_cap(&b->d_stage[slot], &b->d_stage_cap[slot], in_bytes)) return -1;
+        }
+        if (!b->has_user_stream && b->ev_ingested_valid[slot]) CUDA_OK(cudaStreamWaitEvent(s_copy, b->ev_ingested[slot], 0));
+        CUDA_OK(cudaMemcpyAsync(b->d_stage[slot], samples, in_bytes, cudaMemcpyHostToDevice, s_copy));
+        if (!b->has_user_stream) {
+            CUDA_OK(cudaEventRecord(b->ev_h2d[slot], s_copy));
+            CUDA_OK(cudaStreamWaitEvent(s_comp, b->ev_h2d[slot], 0));
+        }
+        src = b->d_stage[slot];
+    }
+    const unsigned char* dM = nullptr;
+    if (mid) {
+        if (mid_dev) dM = (const unsigned char*)mid;
+        else {
+            CUDA_OK(cudaMemcpyAsync(b->d_mid, mid, mid_bytes * n_frames, cudaMemcpyHostToDevice, s_comp));
+            dM = b->d_mid;
+        }
+    }
+    unsigned char* dF = fr_dev ? (unsigned char*)frames : b->d_frames;
+    switch (sample_format) {
+        case PMUB_SAMPLES_NATIVE:
+            if (sz == 8) CUDA_OK(launch_scatter<double>(b, src, nullptr, 0, (long long)n, n_frames, s_comp));
+            else CUDA_OK(launch_scatter<float>(b, src, nullptr, 0, (long long)n, n_frames, s_comp));
+            break;
+        case PMUB_SAMPLES_F32: CUDA_OK(launch_scatter<float>(b, src, nullptr, 0, (long long)n, n_frames, s_comp)); break;
+        case PMUB_SAMPLES_I16: CUDA_OK(launch_scatter<short>(b, src, b->d_scale, 0, (long long)n, n_frames, s_comp)); break;
+    }
+    if (!in_dev && !b->has_user_stream) {
+        CUDA_OK(cudaEventRecord(b->ev_ingested[slot], s_comp));
+        b->ev_ingested_valid[slot] = true;
+    }
+    RingSrc ring;
+    ring.start = ((b->ring_wpos + hop - N) % cap + cap) % cap;
+    ring.t0 = (b->stream_origin + b->stream_pushed + (unsigned long long)hop - (unsigned long long)N) % b->cfg.fs;
+    if (launch_frames(b, 0, (long long)n, n_frames, nullptr, dM, dF, nullptr, s_comp, &ring)) return -1;
+    if (!fr_dev) CUDA_OK(cudaMemcpyAsync(frames, dF, fr_bytes * n_frames, cudaMemcpyDeviceToHost, s_comp));
+    CUDA_OK(cudaEventRecord(b->ev_done[dslot], s_comp));
+    b->ev_done_valid[dslot] = true;
+    if (ticket) *ticket = b->push_no;
+    b->push_no++;
+    b->ring_wpos = (b->ring_wpos + (long long)n_frames * hop) % cap;
+    b->stream_pushed += (unsigned long long)n_frames * (unsigned long long)hop;
+    if (!(flags & PMUB_PUSH_ASYNC)) CUDA_OK(cudaEventSynchronize(b->ev_done[dslot]));
+    return 0;
+}
+
+// Block until the push that returned `ticket` has delivered its frames.
+int pmub_stream_wait(pmub_batch* b, unsigned long long ticket)
+{
+    if (!b) { set_error("[pmu_stream] ERROR: NULL batch"); return -1; }
+    if (ticket >= b->push_no) { set_error("[pmu_stream] ERROR: no such push"); return -1; }
+    if (ticket + 4 < b->push_no) return 0;   // its event slot has been reused, which required it to have completed
+    CUDA_OK(cudaSetDevice(b->device));
+    const int dslot = (int)(ticket & 3);
+    if (b->ev_done_valid[dslot]) CUDA_OK(cudaEventSynchronize(b->ev_done[dslot]));
+    return 0;
 }
 
 int pmub_get_state(pmub_batch* b, double* freq_old, double* dl0, double* dl1, unsigned char* state)

@@ -564,7 +564,12 @@ def _long_streams(cfg, n_streams, total, seed):
     (configs.P_CLASS_INI, "f64", 3, False),
     (configs.DEFAULT_INI, "f32", 2, False),
     (dict(configs.DEFAULT_INI, fs=4750, n_cycles=3, n_bins=7), "f64", 2, False),   # odd hop: per-element loader
-], ids=["default_F1", "default_F3", "mclass_F2", "cfg5_F4", "pclass_F3", "float_F2", "oddhop_F2"])
+    # hop does not divide win_len (768 samples, hop 512): pushed blocks cross the end of the ring - wide rows go in
+    # as two 2-D copies (f64, 4 KB per row), narrow ones through the scatter kernel (f32)
+    (dict(configs.DEFAULT_INI, f0=60, fs=15360, n_cycles=3, frame_rate=30, n_bins=8), "f64", 8, True),
+    (dict(configs.DEFAULT_INI, f0=60, fs=15360, n_cycles=3, frame_rate=30, n_bins=8), "f32", 3, False),
+], ids=["default_F1", "default_F3", "mclass_F2", "cfg5_F4", "pclass_F3", "float_F2", "oddhop_F2", "hop_not_dividing_N_F8",
+        "hop_not_dividing_N_f32"])
 def test_stream_push_equals_explicit_windows(cfg, dtype, F, given_mid):
     dt = DT[dtype]
     n_inst, C_ = 23, 6
@@ -583,6 +588,7 @@ def test_stream_push_equals_explicit_windows(cfg, dtype, F, given_mid):
         for p in range(pushes):
             blk = np.stack([x[:, N - hop + t * hop:N + t * hop].reshape(n_inst, C_, hop) for t in range(p * F, (p + 1) * F)])
             got[p * F:(p + 1) * F] = stream.stream_push(blk, mids[p * F:(p + 1) * F] if given_mid else None)
+    assert np.isfinite(want).all()
     if given_mid:
         assert np.array_equal(got, want)
     else:
@@ -590,6 +596,74 @@ def test_stream_push_equals_explicit_windows(cfg, dtype, F, given_mid):
         # differ by an ulp from the caller-side formula
         assert np.array_equal(got[..., [0, 2, 3]], want[..., [0, 2, 3]])
         assert np.max(np.abs(got[..., 1].astype(np.float64) - want[..., 1])) < (1e-11 if dtype == "f64" else 1e-5)
+
+
+def test_stream_push_explicit_odd_hop_that_does_not_divide_the_window():
+    """An explicit hop (not fs / frame_rate) that divides neither win_len nor the ring length."""
+    cfg = configs.DEFAULT_INI
+    n_inst, C_, hop, F = 11, 6, 600, 3
+    N = configs.win_len(cfg)
+    pushes = 6
+    T = pushes * F
+    x = _long_streams(cfg, n_inst * C_, N + T * hop, seed=77)
+    with BatchEstimator(cfg, n_inst, C_) as explicit, BatchEstimator(cfg, n_inst, C_) as stream:
+        want = np.zeros((T, n_inst, C_, 4))
+        mids = np.linspace(0.0, 0.9, T * n_inst).reshape(T, n_inst)
+        for t in range(T):
+            want[t] = explicit.estimate(x[:, t * hop:t * hop + N].reshape(n_inst, C_, N), mids[t])
+        assert stream.stream_begin(hop=hop, max_frames_per_push=F, history=x[:, :N - hop].reshape(n_inst, C_, N - hop)) == hop
+        got = np.zeros_like(want)
+        for p in range(pushes):
+            blk = np.stack([x[:, N - hop + t * hop:N + t * hop].reshape(n_inst, C_, hop) for t in range(p * F, (p + 1) * F)])
+            got[p * F:(p + 1) * F] = stream.stream_push(blk, mids[p * F:(p + 1) * F])
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("fmt", ["i16", "f32", "native_async"])
+def test_stream_push_narrow_formats_and_async_pushes_equal_explicit_windows(fmt):
+    """pmub_stream_push_ex: int16 ADC counts (x per-stream scale) and float samples are promoted on the device, exactly,
+    so the frames are those of explicit double windows holding the promoted values; asynchronous pushes from two
+    alternating buffers give the frames of synchronous ones."""
+    cfg = configs.DEFAULT_INI
+    n_inst, C_, F = 19, 6, 2
+    N, hop = configs.win_len(cfg), configs.hop(cfg)
+    pushes = 7
+    T = pushes * F
+    x = _long_streams(cfg, n_inst * C_, N + T * hop, seed=5)
+    scale = None
+    if fmt == "i16":
+        scale = np.abs(x).max(axis=1) / 30000.0
+        q = np.round(x / scale[:, None]).astype(np.int16)
+        x = scale[:, None] * q.astype(np.float64)          # what the device computes: scale * (double)count
+        src = q
+    elif fmt == "f32":
+        src = x.astype(np.float32)
+        x = src.astype(np.float64)
+    else:
+        src = x
+    with BatchEstimator(cfg, n_inst, C_) as explicit, BatchEstimator(cfg, n_inst, C_) as stream:
+        want = np.zeros((T, n_inst, C_, 4))
+        mids = np.zeros((T, n_inst))
+        for t in range(T):
+            mids[t] = signals.mid_fracsec(cfg, t)
+            want[t] = explicit.estimate(x[:, t * hop:t * hop + N].reshape(n_inst, C_, N), mids[t])
+        stream.stream_begin(hop=0, max_frames_per_push=F, history=x[:, :N - hop].reshape(n_inst, C_, N - hop))
+        if scale is not None:
+            stream.stream_set_scale(scale)
+        got = np.zeros_like(want)
+        blocks = [np.ascontiguousarray(np.stack([src[:, N - hop + t * hop:N + t * hop].reshape(n_inst, C_, hop)
+                                                 for t in range(p * F, (p + 1) * F)])) for p in range(pushes)]
+        tickets = []
+        for p in range(pushes):
+            out, tk = stream.stream_push(blocks[p], mids[p * F:(p + 1) * F].copy(), out=got[p * F:(p + 1) * F], asynchronous=True)
+            tickets.append(tk)
+            if p >= 2:
+                stream.stream_wait(tickets[p - 2])
+        for tk in tickets:
+            stream.stream_wait(tk)
+        stream.sync()
+    assert tickets == sorted(tickets) and len(set(tickets)) == pushes
+    assert np.array_equal(got, want)
 
 
 @pytest.mark.parametrize("cfgname,dtype", [("cfg5_600", np.float64), ("p_class_config.ini", np.float64),
