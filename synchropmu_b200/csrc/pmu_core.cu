@@ -270,17 +270,24 @@ __global__ void ring_scatter_kernel(RingT* __restrict__ ring, const SrcT* __rest
                                     long long n_streams, long long w0, long long w1, int n_frames, int hop, long long cap,
                                     long long wpos)
 {
-    const long long per_frame = (w1 - w0) * hop;
-    const long long total = per_frame * n_frames;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int f = (int)(i / per_frame);
-        const long long r = i - (long long)f * per_frame;
-        const long long w = w0 + r / hop;
-        const int j = (int)(r % hop);
-        long long p = wpos + (long long)f * hop + j;
-        p %= cap;
-        const SrcT v = src[((long long)f * n_streams + w) * hop + j];
-        ring[w * cap + p] = scale ? (RingT)(scale[w] * (double)v) : (RingT)v;
+    // one warp per (frame, stream) row of `hop` consecutive samples: coalesced on both sides, one division per row
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long n_w = w1 - w0;
+    const long long rows = n_w * n_frames;
+    for (long long row = (((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; row < rows; row += warps) {
+        const int f = (int)(row / n_w);
+        const long long w = w0 + (row - (long long)f * n_w);
+        const long long p0 = (wpos + (long long)f * hop) % cap;
+        const SrcT* __restrict__ s = src + ((long long)f * n_streams + w) * hop;
+        RingT* __restrict__ d = ring + w * cap;
+        const double sc = scale ? scale[w] : 1.0;
+        for (int j = lane; j < hop; j += 32) {
+            long long p = p0 + j;
+            if (p >= cap) p -= cap;
+            const SrcT v = s[j];
+            d[p] = scale ? (RingT)(sc * (double)v) : (RingT)v;
+        }
     }
 }
 
@@ -288,8 +295,8 @@ template <typename SrcT>
 static cudaError_t launch_scatter(pmub_batch* b, const void* src, const double* scale, long long w0, long long w1, int n_frames,
                                   cudaStream_t s)
 {
-    const long long total = (w1 - w0) * b->hop * n_frames;
-    int blocks = (int)((total + 255) / 256);
+    const long long rows = (w1 - w0) * n_frames;          // a warp per row, 8 warps per block
+    int blocks = (int)((rows + 7) / 8);
     if (blocks > b->num_sms * 16) blocks = b->num_sms * 16;
     if (blocks < 1) blocks = 1;
     if (b->dtype == PMUB_F64)

@@ -299,6 +299,7 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
     for (int m : cand)
         if (N % m == 0 && (N / m >= 32 || m == 1)) { p.M = m; break; }
     p.L = N / p.M;
+    if (p.M == 1 && p.KC == 24 && s == 8) return make_wide_plan(c, max_smem, out);   // see launch_kc (pmu_launch.cuh)
 
     if (p.M == 16) {
         // fixed row pitch: slabs are at most PMU_PITCH16 residues wide, rows PMU_PITCH16 elements apart; 1024-sample
@@ -414,6 +415,21 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
             for (int cand_raw = nr_max; cand_raw > base_raw; --cand_raw)
                 if (layout(nc, cand_raw) >= ns_keep) { nr = cand_raw; break; }
             layout(nc, nr);
+            // Few stages (wide bin accumulators and/or multi-slab windows whose scratch eats the shared memory): a
+            // consumer warp holds a stage for as long as it transforms it, so warps beyond n_stage - 3 only starve the
+            // loads in flight.  Trade consumer warps (and raw buffers) for ring stages.
+            if (p.n_stage < 7 && forced_raw < 2 && env_int("PMU_REBALANCE", 1)) {
+                int best_nc = nc, best_nr = nr, best_eff = (nc < p.n_stage - 3 ? nc : p.n_stage - 3), best_ns = p.n_stage;
+                for (int c2 = nc; c2 >= 3; --c2)
+                    for (int r2 = nr; r2 >= 3; --r2) {
+                        const int ns = layout(c2, r2);
+                        const int eff = c2 < ns - 3 ? c2 : ns - 3;
+                        if (eff > best_eff || (eff == best_eff && ns > best_ns && c2 >= best_nc)) {
+                            best_eff = eff; best_nc = c2; best_nr = r2; best_ns = ns;
+                        }
+                    }
+                layout(best_nc, best_nr);
+            }
             ok = true;
             break;
         }

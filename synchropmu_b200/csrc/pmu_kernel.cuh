@@ -584,6 +584,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             const bool whole = (a.nslab == 1 && pitch == a.L);
             int st = 0, sl = 0, t = 0, f = 0;      // running (stage, slab, pass, frame) of slab i
             uint32_t par = 0;
+            long long ring_pos = a.ring_cap ? a.ring_start % a.ring_cap : 0;   // ring position of frame f's first sample
             for (int i = 0; i < total_slabs; ++i) {
                 if (lane == 0) mbar_wait(&ctrl->empty[st], par ^ 1u);
                 __syncwarp();
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                     src = reinterpret_cast<const InT*>(a.windows) + ((size_t)f * a.frame_stride + (size_t)(w_begin + tw)) * a.N;
                 } else {
                     src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + tw) * a.ring_cap;
-                    start = (a.ring_start + (long long)f * a.hop) % a.ring_cap;
+                    start = ring_pos;
                 }
                 if (whole) {
                     if (lane == 0) {
@@ -627,12 +628,17 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 if (++st == a.n_stage) { st = 0; par ^= 1u; }
                 if (++sl == a.nslab) {
                     sl = 0;
-                    if (++t == n_packs) { t = 0; ++f; }
+                    if (++t == n_packs) {
+                        t = 0; ++f;
+                        ring_pos += a.hop;
+                        if (a.ring_cap && ring_pos >= a.ring_cap) ring_pos -= a.ring_cap;
+                    }
                 }
             }
         } else {
             int st = 0, sl = 0, t = 0, f = 0;
             uint32_t par = 0;
+            long long ring_pos = a.ring_cap ? a.ring_start % a.ring_cap : 0;
             for (int i = 0; i < total_slabs; ++i) {
                 mbar_wait(&ctrl->empty[st], par ^ 1u);
                 InT* dst = reinterpret_cast<InT*>(stages + (size_t)st * a.stage_bytes);
@@ -644,7 +650,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                     src = reinterpret_cast<const InT*>(a.windows) + ((size_t)f * a.frame_stride + (size_t)(w_begin + tw)) * a.N;
                 } else {
                     src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + tw) * a.ring_cap;
-                    start = (a.ring_start + (long long)f * a.hop) % a.ring_cap;
+                    start = ring_pos;
                 }
                 if constexpr (WP == 1) {
                     const int a_lo = sl * a.W;
@@ -669,7 +675,11 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 if (++st == a.n_stage) { st = 0; par ^= 1u; }
                 if (++sl == a.nslab) {
                     sl = 0;
-                    if (++t == n_packs) { t = 0; ++f; }
+                    if (++t == n_packs) {
+                        t = 0; ++f;
+                        ring_pos += a.hop;
+                        if (a.ring_cap && ring_pos >= a.ring_cap) ring_pos -= a.ring_cap;
+                    }
                 }
             }
         }
@@ -729,7 +739,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             const int w_s = min(a.W, a.L - a_lo);
             const int n_it = (w_s + G - 1) / G;
             const bool all_full = (w_s % G) == 0;
-            for (int ii = 0; ii < n_it; ++ii) {
+            auto residue_group = [&](int ii) {
                 const int a_loc = gl + G * ii;
                 CT x[M];
                 // only the last residue group of a slab can be partly out of range
@@ -742,7 +752,8 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 } else {
                     accumulate_residue<M, KC, false, CT>(x, u, ar, ai);
                 }
-            }
+            };
+            for (int ii = 0; ii < n_it; ++ii) residue_group(ii);
             __syncwarp();
             if (lane == 0) {
                 *reinterpret_cast<volatile int*>(&ctrl->stage_seq[st]) = use + 1;

@@ -64,7 +64,11 @@ int launch_kc(int KC, const KernelArgs& a, int grid, int block, int smem, cudaSt
         case 10: return launch_inst<T, M, 10, PITCH, WP>(a, grid, block, smem, s);
         case 12: return launch_inst<T, M, 12, PITCH, WP>(a, grid, block, smem, s);
         case 16: return launch_inst<T, M, 16, PITCH, WP>(a, grid, block, smem, s);
-        case 24: return launch_inst<T, M, 24, PITCH, WP>(a, grid, block, smem, s);
+        case 24:
+            // odd window lengths (direct DFT, M = 1) with 16..23 bins in double run on the general kernel instead: the
+            // 48 accumulators plus 24 twiddle loads of the tiny loop body do not fit the register file without spills
+            if constexpr (!(M == 1 && sizeof(T) == 8)) return launch_inst<T, M, 24, PITCH, WP>(a, grid, block, smem, s);
+            break;
     }
     pmu::set_error("[pmu_estimate] ERROR: unsupported bin-count specialisation");
     return -1;
