@@ -174,6 +174,22 @@ def _ptr(x) -> int:
     raise TypeError(type(x))
 
 
+def _ingest(x):
+    """numpy arrays and torch tensors pass through; any other object that speaks ``__cuda_array_interface__``
+    (CuPy, Numba, RAPIDS ...) or DLPack (``__dlpack__``: JAX, CuPy, TensorFlow ...) becomes a zero-copy torch view of
+    the same memory, so device buffers of other frameworks can be handed to the estimator directly (the reference's
+    wrapper copies a Python list element by element, python/pmu_estimator.py:153-156)."""
+    if x is None or isinstance(x, np.ndarray) or hasattr(x, "data_ptr"):
+        return x
+    if hasattr(x, "__cuda_array_interface__") or hasattr(x, "__dlpack__"):
+        import torch
+
+        if hasattr(x, "__cuda_array_interface__"):
+            return torch.as_tensor(x, device=torch.device("cuda", torch.cuda.current_device()))
+        return torch.from_dlpack(x)
+    return x
+
+
 class BatchEstimator:
     """``n_instances`` independent estimators x ``n_channels`` channels on one GPU.
 
@@ -236,6 +252,7 @@ class BatchEstimator:
     def estimate(self, windows, mid_fracsec, out=None):
         """Synchronous estimate; host or device containers (see class docstring)."""
         n, c = self.n_instances, self.n_channels
+        windows, mid_fracsec, out = _ingest(windows), _ingest(mid_fracsec), _ingest(out)
         is_torch = hasattr(windows, "data_ptr")
         if is_torch:
             import torch
@@ -259,6 +276,7 @@ class BatchEstimator:
         mid_fracsec ``[F, n_instances]`` -> frames ``[F, n_instances, n_channels, 4]``.  Same results as
         F calls of :meth:`estimate`; the kernel carries the ROCOF state from frame to frame."""
         n, c = self.n_instances, self.n_channels
+        windows, mid_fracsec, out = _ingest(windows), _ingest(mid_fracsec), _ingest(out)
         is_torch = hasattr(windows, "data_ptr")
         if is_torch:
             import torch
@@ -315,6 +333,7 @@ class BatchEstimator:
         n, c = self.n_instances, self.n_channels
         if getattr(self, "hop", None) is None:
             raise RuntimeError("stream_push before stream_begin")
+        new_samples, mid_fracsec, out = _ingest(new_samples), _ingest(mid_fracsec), _ingest(out)
         is_torch = hasattr(new_samples, "data_ptr")
         F = int(new_samples.shape[0])
         if not 1 <= F <= self.max_frames_per_push:

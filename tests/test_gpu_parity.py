@@ -253,6 +253,40 @@ def test_device_and_host_pointers_and_unaligned_loads_agree():
     assert np.array_equal(dev, una)
 
 
+def test_cuda_array_interface_and_dlpack_inputs():
+    """Device buffers of other frameworks: objects that only expose __cuda_array_interface__ (CuPy / Numba style) or
+    only DLPack are accepted zero-copy and give the frames of the same data passed as a torch tensor."""
+    torch = pytest.importorskip("torch")
+
+    class CaiOnly:
+        def __init__(self, t):
+            self._t = t
+            self.__cuda_array_interface__ = t.__cuda_array_interface__
+
+    class DlpackOnly:
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, stream=None, **kw):
+            return self._t.__dlpack__(stream=stream) if stream is not None else self._t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+
+    cfg = configs.DEFAULT_INI
+    n_inst = 40
+    win, mid = three_phase_batch(cfg, n_inst, 1, seed=9)
+    w = torch.as_tensor(win[0], device="cuda")
+    m = torch.as_tensor(mid[0], device="cuda")
+    with BatchEstimator(cfg, n_inst, 6) as a, BatchEstimator(cfg, n_inst, 6) as b, BatchEstimator(cfg, n_inst, 6) as c:
+        want = a.estimate(w, m)
+        got_cai = b.estimate(CaiOnly(w), CaiOnly(m))
+        got_dl = c.estimate(DlpackOnly(w), DlpackOnly(m))
+    assert got_cai.is_cuda and got_dl.is_cuda
+    assert torch.equal(got_cai, want) and torch.equal(got_dl, want)
+    assert np.isfinite(want.cpu().numpy()).all()
+
+
 def test_rocof_state_checkpoint_resume_and_reset():
     cfg = configs.DEFAULT_INI
     n_inst, T = 12, 6
@@ -694,8 +728,9 @@ def test_packed_short_windows_aligned_and_unaligned_sources_agree(cfgname, dtype
 
 @pytest.mark.parametrize("seed,dtype", [(1, np.float64), (2, np.float64), (3, np.float64), (4, np.float64), (5, np.float64),
                                         (6, np.float64), (7, np.float32), (8, np.float32)])
-def test_random_valid_configurations_match_oracle(seed, dtype):
+def test_random_valid_configurations_match_oracle(seed, dtype, capsys):
     plans = set()
+    clear_fracs = []
     tol = "f64" if dtype == np.float64 else "f32"
     for cfg in random_valid_configs(14, seed):
         N = configs.win_len(cfg)
@@ -728,7 +763,8 @@ def test_random_valid_configurations_match_oracle(seed, dtype):
                     # float build: a one-ulp frequency difference may flip a ROCOF threshold decision that the oracle
                     # itself takes within 2e-3 Hz/s of the threshold; those streams are compared without ROCOF
                     clear = ~amb[t]
-                    assert clear.mean() > 0.8, cfg
+                    clear_fracs.append(float(clear.mean()))
+                    assert clear.mean() >= 0.85, (cfg, clear.mean())   # measured minimum over the sweep: 0.87
                     assert_frames_close(seq[t][clear], want[t][clear], tol, f"{cfg} frame {t}")
                     g3, w3 = seq[t].copy(), want[t].copy()
                     g3[..., 3] = w3[..., 3] = 0
@@ -736,6 +772,13 @@ def test_random_valid_configurations_match_oracle(seed, dtype):
             # the same frames in one call (one launch where the plan allows it): bit-identical
             assert np.array_equal(multi.estimate_frames(win, mid), seq, equal_nan=True), cfg
     assert len(plans) >= 4, plans                     # the draw really covered several kernel plans
+    if clear_fracs:
+        # how much of the float sweep had its ROCOF compared (streams whose threshold decisions are not within 2e-3 Hz/s
+        # of a threshold in the oracle itself): logged so that the fraction is visible in the test output
+        with capsys.disabled():
+            print(f"\n[f32 sweep seed {seed}] ROCOF compared on {100 * np.mean(clear_fracs):.1f} % of the streams "
+                  f"(min over configurations/frames {100 * min(clear_fracs):.1f} %)")
+        assert np.mean(clear_fracs) >= 0.95
 
 
 def test_launch_ordering_with_producer_kernels_on_the_same_stream():
@@ -1007,3 +1050,38 @@ def test_config4_full_sweep_matches_oracle(cfgname):
     assert_frames_close(got, want, "f64", f"config 4 sweep / {cfgname}")
     assert np.array_equal(km, km_want[:, :, 0])
     assert S == 21 + 98 + 30 + 7 + 11 and n_trig > 50          # the interharmonic / harmonic cases run the Q loop
+
+
+# ---------------------------------------------------------------------------------------
+# the hand-rolled synchronisation under starved resources (compute-sanitizer is not available on the pool): the core
+# parity tests re-run in a child process with the launch plan squeezed, so that every wait path (stage_seq, raw_owner,
+# grp_done, mbarrier parities) is exercised far harder than with the default plan.  tools/gpu_stress.sh runs the whole
+# suite the same way.
+# ---------------------------------------------------------------------------------------
+STRESS_VARIANTS = {
+    "two_stages_two_raw_buffers": dict(PMU_STAGES="2", PMU_RAW_BUFFERS="2"),
+    "three_consumer_warps": dict(PMU_STAGES="3", PMU_CONSUMER_WARPS="3", PMU_RAW_BUFFERS="3"),
+    "per_element_loader": dict(PMU_FORCE_ELEM_LOAD="1"),
+    "row_copies_batched_small_launches_no_pdl": dict(PMU_NO_TENSOR_MAP="1", PMU_WARP_PER_WINDOW_MAX="0", PMU_ZERO_COPY_MAX="0",
+                                                     PMU_NO_PDL="1"),
+    "no_window_packing": dict(PMU_PACK="1"),
+}
+STRESS_SELECT = ("three_phase or multi_frame or stream_push or golden or config2 or config4 or odd_window or "
+                 "device_and_host or long_stream or hostile")
+
+
+@pytest.mark.skipif(bool(__import__("os").environ.get("PMU_STRESS_CHILD")), reason="already inside a stress child")
+@pytest.mark.parametrize("variant", sorted(STRESS_VARIANTS))
+def test_parity_under_starved_resources(variant):
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, PMU_STRESS_CHILD="1", **STRESS_VARIANTS[variant])
+    sel = STRESS_SELECT + (" and not warp_per_window" if "WARP_PER_WINDOW" in "".join(STRESS_VARIANTS[variant]) else "")
+    r = subprocess.run([sys.executable, "-m", "pytest", str(Path(__file__)), "-x", "-q", "-m", "gpu", "-k", sel,
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=900,
+                       cwd=str(Path(__file__).resolve().parent.parent))
+    tail = "\n".join(r.stdout.splitlines()[-15:])
+    assert r.returncode == 0, f"{variant}: {tail}\n{r.stderr[-1500:]}"
+    assert " passed" in tail and "failed" not in tail

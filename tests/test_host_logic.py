@@ -121,6 +121,47 @@ def test_validation_rejects_what_the_reference_rejects(bad):
     assert "ERROR" in api.last_error()
 
 
+REF_WRAPPER = Path("/root/reference/python/pmu_estimator.py")
+
+
+@pytest.mark.skipif(not REF_WRAPPER.exists(), reason="the reference tree is not on this box")
+def test_reference_python_wrapper_binds_our_library_unchanged():
+    """The reference's OWN ctypes wrapper (python/pmu_estimator.py, imported from where it lies, unmodified) against
+    libpmu_estimator.so: it must load, find the three symbols it declares argtypes for, its (oversized) context buffer
+    must cover our pmu_context, and on this GPU-less box pmu_init must refuse with -1 and a message instead of crashing
+    or silently estimating on the CPU; pmu_estimate on the unconfigured context returns None like the reference's
+    "not initialized" path.  (On the GPU box the same structs are exercised by the emulation in
+    tests/test_gpu_parity.py::test_reference_python_wrapper_layout_is_safe, since /root/reference does not travel.)"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_pmu_estimator", REF_WRAPPER)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    lib = api.lib_path(np.float64, 1)
+    est = ref.PMUEstimator(lib_path=str(lib))
+    for sym in ("pmu_init", "pmu_estimate", "pmu_deinit"):
+        assert hasattr(est.lib, sym)
+    # the wrapper's context mirror is sized for 2 channels of doubles: it must be at least as large as the real one
+    from synchropmu_b200.pmu_estimator import _structs
+
+    assert C.sizeof(ref.PmuContext) >= C.sizeof(_structs(C.c_double, 1)[1])
+    d = configs.DEFAULT_INI
+    cfg = ref.EstimatorConfig(d["n_cycles"], d["f0"], d["frame_rate"], d["fs"], d["n_bins"], d["P"], d["Q"], d["interf_trig"],
+                              d["rocof_thresh"], d["rocof_low_pass_coeffs"], bool(d["iter_eipdft"]))
+    torch = pytest.importorskip("torch")
+    rc = est.configure_from_class(cfg)
+    if torch.cuda.is_available():
+        assert rc == 0
+        t = np.arange(configs.win_len(d)) / d["fs"]
+        got = est.estimate(list(2 * np.cos(2 * np.pi * 50 * t + 1)), 0.0)
+        assert abs(got["amp"] - 2) < 1e-9 and abs(got["freq"] - 50) < 1e-7 and abs(got["ph"] - 1) < 1e-9
+        assert est.deinit() == 0
+    else:
+        assert rc == -1                                   # no CUDA device: loud refusal, no CPU path
+        assert est.estimate([0.0] * configs.win_len(d), 0.0) is None
+        assert est.deinit() == -1                          # "not initialized", as in the reference (:280-284)
+
+
 def test_create_without_gpu_fails_loudly():
     """No CPU fallback: on a box without a CUDA device creation must raise, never estimate."""
     torch = pytest.importorskip("torch")
