@@ -258,29 +258,31 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// The peak search with lane = bin.  |Y_j|^2 >= 0, and the bit patterns of non-negative doubles order like unsigned
+// integers, so the maximum is two warp-wide integer reductions (REDUX: high words, then the low words of the lanes that
+// tie on the high word) and the first maximum is the lowest lane of a ballot - a third of the latency of a five-round
+// shuffle butterfly on (value, index) pairs.  NaNs are keyed as 0 (never win) unless at bin 0.  Every lane takes the
+// square root of its own bin while the reductions are in flight, so the interpolation tail starts from magnitudes.
 __device__ __forceinline__ int ipdft_warp(const PostParams& p, double yr, double yi, int j, bool valid, Tone* out, int* km_out)
 {
     const double v = yr * yr + yi * yi;
+    const double mag = pmu_sqrt(v);
+    const unsigned long long bits = (valid && v == v) ? (unsigned long long)__double_as_longlong(v) : 0ull;
+    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    const unsigned hi_max = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned lo_max = __reduce_max_sync(0xffffffffu, hi == hi_max ? lo : 0u);
+    const unsigned winners = __ballot_sync(0xffffffffu, hi == hi_max && lo == lo_max);
     const double v0 = __shfl_sync(0xffffffffu, v, 0);
-    double key = (valid && v == v) ? v : -INFINITY;   // NaN never wins ...
-    int idx = j;
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const double ok = __shfl_xor_sync(0xffffffffu, key, off);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
-        if (ok > key || (ok == key && oi < idx)) { key = ok; idx = oi; }   // first maximum on ties
-    }
-    const int km = (v0 != v0) ? 0 : idx;                // ... unless it sits at bin 0
-    Peak pk;
-    pk.km = km;
-    pk.best = __shfl_sync(0xffffffffu, v, km);
-    pk.left = __shfl_sync(0xffffffffu, v, km > 0 ? km - 1 : 0);
-    pk.right = __shfl_sync(0xffffffffu, v, km + 1 < p.K ? km + 1 : km);
-    pk.yr = __shfl_sync(0xffffffffu, yr, km);
-    pk.yi = __shfl_sync(0xffffffffu, yi, km);
-    pk.prev = 0.0;
+    int km = __ffs((int)winners) - 1;
+    km = (v0 != v0 || km >= p.K) ? 0 : km;              // a NaN wins only at bin 0; idle lanes (keyed 0) never
+    const double mk = __shfl_sync(0xffffffffu, mag, km);
+    const double ml = __shfl_sync(0xffffffffu, mag, km > 0 ? km - 1 : 0);                // kl = km when km == 0 (:718)
+    const double mr_raw = __shfl_sync(0xffffffffu, mag, km + 1 < p.K ? km + 1 : km);
+    const double pyr = __shfl_sync(0xffffffffu, yr, km);
+    const double pyi = __shfl_sync(0xffffffffu, yi, km);
+    const double mr = (km == p.K - 1) ? ml : mr_raw;                                     // kr = km-1 at the last bin (:719)
     if (km_out) *km_out = km;
-    return ipdft_finish(p, pk, out);
+    return ipdft_tail(p, km, mk, km == 0 ? mk : ml, mr, pyr, pyi, out);
 }
 
 // value at bin j of wf(j, f, z) for this lane (three reciprocals, no sliding window)
@@ -365,7 +367,9 @@ __device__ __forceinline__ void finish_window(const KernelArgs& a, const Tone& f
 template <typename InT>
 __device__ __noinline__ void post_window_warp(const KernelArgs& a, const double* row, long long w, int frame, int lane)
 {
-    const PostParams& pp = a.post;
+    // a private copy (registers): through the reference the loop-invariant parameters are re-read with generic loads
+    // (~30 cycles each on the single warp's critical path) wherever the compiler cannot prove they do not alias a store
+    const PostParams pp = a.post;
     const int K = pp.K;
     const bool valid = lane < K;
     const int j = valid ? lane : K - 1;
@@ -411,7 +415,7 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, unsign
                                         int bsz, int batch_id, int lane)
 {
     unsigned char* smem = pmu_smem;
-    const PostParams& pp = a.post;   // stays in the kernel-parameter constant bank
+    const PostParams pp = a.post;    // private copy: see post_window_warp
     CtrlBlock* ctrl = reinterpret_cast<CtrlBlock*>(smem + a.off_ctrl);
     const int K = pp.K;
     double* row = reinterpret_cast<double*>(smem + a.off_raw) + ((size_t)raw_buf * PMU_WARP + lane) * a.raw_stride;

@@ -79,22 +79,20 @@ PMU_HD void pmu_sincospi_half(double x, double* s, double* c)
 #if PMU_FAST_TRIG
     const double t = (0.5 * PMU_PI) * x;
     const double u = t * t;
-    double sp = -7.6471637318198164759e-13;          // -1/15!
-    sp = fma(sp, u, 1.6059043836821614599e-10);      //  1/13!
-    sp = fma(sp, u, -2.5052108385441718775e-08);     // -1/11!
-    sp = fma(sp, u, 2.7557319223985890653e-06);      //  1/9!
-    sp = fma(sp, u, -1.9841269841269841270e-04);     // -1/7!
-    sp = fma(sp, u, 8.3333333333333333333e-03);      //  1/5!
-    sp = fma(sp, u, -1.6666666666666666667e-01);     // -1/3!
+    // Estrin's scheme: the two degree-7 polynomials in u are evaluated as trees of depth 4 instead of Horner chains of
+    // depth 8 (same coefficients; two more multiplies each) - the estimator is bound by dependent-issue latency
+    const double u2 = u * u, u4 = u2 * u2;
+    const double s01 = fma(8.3333333333333333333e-03, u, -1.6666666666666666667e-01);   //  1/5! u - 1/3!
+    const double s23 = fma(2.7557319223985890653e-06, u, -1.9841269841269841270e-04);   //  1/9! u - 1/7!
+    const double s45 = fma(1.6059043836821614599e-10, u, -2.5052108385441718775e-08);   // 1/13! u - 1/11!
+    const double s6 = -7.6471637318198164759e-13;                                       // -1/15!
+    const double sp = fma(fma(s6, u2, s45), u4, fma(s23, u2, s01));
     const double sh = fma(sp * u, t, t);
-    double cp = 4.7794773323873852974e-14;           //  1/16!
-    cp = fma(cp, u, -1.1470745597729724714e-11);     // -1/14!
-    cp = fma(cp, u, 2.0876756987868098979e-09);      //  1/12!
-    cp = fma(cp, u, -2.7557319223985890653e-07);     // -1/10!
-    cp = fma(cp, u, 2.4801587301587301587e-05);      //  1/8!
-    cp = fma(cp, u, -1.3888888888888888889e-03);     // -1/6!
-    cp = fma(cp, u, 4.1666666666666666667e-02);      //  1/4!
-    cp = fma(cp, u, -0.5);
+    const double c01 = fma(4.1666666666666666667e-02, u, -0.5);                          //  1/4! u - 1/2!
+    const double c23 = fma(2.4801587301587301587e-05, u, -1.3888888888888888889e-03);   //  1/8! u - 1/6!
+    const double c45 = fma(2.0876756987868098979e-09, u, -2.7557319223985890653e-07);   // 1/12! u - 1/10!
+    const double c67 = fma(4.7794773323873852974e-14, u, -1.1470745597729724714e-11);   // 1/16! u - 1/14!
+    const double cp = fma(fma(c67, u2, c45), u4, fma(c23, u2, c01));
     const double ch = fma(cp, u, 1.0);
     *s = 2.0 * sh * ch;
     *c = (ch - sh) * (ch + sh);
@@ -310,15 +308,12 @@ struct Peak {
 // |delta| <= 1e-11 (the reference's literal 10e-12, :603).
 //   reference: amp = |Y| |(d^2-1) pi d / sin(pi d)|,  ph = arg(Y) - pi d
 //   here     : exp(i ph) = (Y/|Y|) exp(-i pi d), sin(pi d) from the same sincospi.
-PMU_HD int ipdft_finish(const PostParams& p, const Peak& pk, Tone* t)
+PMU_HD int ipdft_tail(const PostParams& p, int km, double mk, double ml, double mr, double yr, double yi, Tone* t)
 {
-    double mk = pmu_sqrt(pk.best);
-    double ml = (pk.km == 0) ? mk : pmu_sqrt(pk.left);          // kl = km when km == 0 (:718)
-    double mr = (pk.km == p.K - 1) ? ml : pmu_sqrt(pk.right);   // kr = km-1 at the last bin (:719)
     double d = 2 * (mr - ml) * pmu_rcp(ml + mr + 2 * mk);       // :598
-    t->freq = (pk.km + d) * p.df;                               // :601
+    t->freq = (km + d) * p.df;                                  // :601
     double inv = pmu_rcp(mk);
-    double ur = pk.yr * inv, ui = pk.yi * inv;                  // exp(i arg Y)
+    double ur = yr * inv, ui = yi * inv;                        // exp(i arg Y)
     if (fabs(d) <= 10e-12) {                                    // :603-613
         t->amp = mk;
         t->cr = ur;
@@ -332,6 +327,14 @@ PMU_HD int ipdft_finish(const PostParams& p, const Peak& pk, Tone* t)
     t->cr = ur * cd + ui * sd;                                  // :617  exp(i(arg Y - pi d))
     t->ci = ui * cd - ur * sd;
     return 0;
+}
+
+PMU_HD int ipdft_finish(const PostParams& p, const Peak& pk, Tone* t)
+{
+    double mk = pmu_sqrt(pk.best);
+    double ml = (pk.km == 0) ? mk : pmu_sqrt(pk.left);          // kl = km when km == 0 (:718)
+    double mr = (pk.km == p.K - 1) ? ml : pmu_sqrt(pk.right);   // kr = km-1 at the last bin (:719)
+    return ipdft_tail(p, pk.km, mk, ml, mr, pk.yr, pk.yi, t);
 }
 
 // Column view of a [K][32] complex array (lane = window); shared memory on the device.
