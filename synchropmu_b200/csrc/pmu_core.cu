@@ -170,6 +170,11 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     a.st_state = b->st_state + w0;
     a.n_windows = w1 - w0;
     a.n_frames = n_frames;
+    // streaming front end: the frames of a group of streams back to back, so that the overlapping part of consecutive
+    // windows is re-read from L2 rather than from HBM (PMU_GROUP_MAJOR=0 keeps the frame-major order, 2 forces
+    // group-major for explicit windows as well)
+    static const int gm_env = getenv("PMU_GROUP_MAJOR") ? atoi(getenv("PMU_GROUP_MAJOR")) : 1;
+    a.group_major = (n_frames > 1 && ((ring && gm_env >= 1) || gm_env >= 2)) ? 1 : 0;
     a.frame_stride = b->n_windows;
     a.mid_frame_stride = b->n_inst;
     a.dbg = b->debug ? b->d_dbg + w0 : nullptr;

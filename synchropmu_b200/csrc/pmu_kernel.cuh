@@ -75,6 +75,10 @@ struct KernelArgs {
     long long n_windows;         // windows (streams) handled by this launch
     // consecutive frames processed by this launch, in order, per stream (ROCOF state carried)
     int n_frames;
+    // item order of a multi-frame launch: 0 = frame-major (all streams of frame 0, then frame 1, ...), 1 = group-major
+    // (the n_frames windows of a group of <= 32 streams back to back: in ring mode consecutive windows of a stream
+    // overlap by win_len - hop samples, which are then still in L2 when the next frame reads them)
+    int group_major;
     long long frame_stride;      // streams per frame in the caller's arrays (>= n_windows: a launch
                                  // may cover a sub-range of the batch), in windows
     long long mid_frame_stride;  // instances per frame in `mid`
@@ -234,6 +238,22 @@ struct BatchMap {
         by_q.init((unsigned)q);
         by_q1.init((unsigned)(q + 1));
     }
+    // group-major item order of a launch with F frames: item -> (frame, pass).  Plain divisions: this runs once per
+    // window in streaming launches only, and keeping four more magic numbers alive costs the 24-bin kernels spills.
+    __device__ __forceinline__ void item_group_major(int item, int F, int* f, int* t) const
+    {
+        const int big_items = rem * (q + 1) * F;
+        if (item < big_items) {
+            const int g = item / ((q + 1) * F), r = item - g * (q + 1) * F;
+            *f = r / (q + 1);
+            *t = g * (q + 1) + (r - *f * (q + 1));
+        } else {
+            const int i2 = item - big_items;
+            const int gg = i2 / (q * F), r = i2 - gg * q * F;
+            *f = r / q;
+            *t = rem * (q + 1) + gg * q + (r - *f * q);
+        }
+    }
     __device__ __forceinline__ void locate(int t, int* g, int* slot, int* size, int* first) const
     {
         int big = rem * (q + 1);
@@ -244,6 +264,52 @@ struct BatchMap {
             int gg = (int)by_q.div((unsigned)(t - big), &r);
             *g = rem + gg; *slot = (int)r; *size = q; *first = big + gg * q;
         }
+    }
+};
+
+// ---- the producer's walk over the launch's items, in the same order the consumers decode their tickets --------------
+struct ItemWalker {
+    int f, t;               // frame and pass of the current item
+    long long ring_pos;     // ring position of frame f's first sample (streaming front end)
+    // frame-major: t runs over the passes, then f advances; group-major: slot runs over the group, then f, then the group
+    int group_major, n_packs, F, hop;
+    long long cap, pos0;
+    int g, slot, gsize, gfirst, q, rem;
+    __device__ __forceinline__ void init(const BatchMap& bm, int n_packs_, int n_frames, int group_major_, long long ring_cap,
+                                         long long ring_start, int hop_)
+    {
+        group_major = group_major_ && n_frames > 1;
+        n_packs = n_packs_; F = n_frames; hop = hop_; cap = ring_cap;
+        pos0 = ring_cap ? ring_start % ring_cap : 0;
+        ring_pos = pos0;
+        f = 0; t = 0; g = 0; slot = 0; gfirst = 0;
+        q = bm.q; rem = bm.rem;
+        gsize = rem > 0 ? q + 1 : q;
+    }
+    __device__ __forceinline__ void next_frame()
+    {
+        ++f;
+        ring_pos += hop;
+        if (cap && ring_pos >= cap) ring_pos -= cap;
+    }
+    __device__ __forceinline__ void advance()
+    {
+        if (!group_major) {
+            if (++t == n_packs) { t = 0; next_frame(); }
+            return;
+        }
+        if (++slot == gsize) {
+            slot = 0;
+            next_frame();
+            if (f == F) {
+                f = 0;
+                ring_pos = pos0;
+                gfirst += gsize;
+                ++g;
+                gsize = g < rem ? q + 1 : q;
+            }
+        }
+        t = gfirst + slot;
     }
 };
 
@@ -364,12 +430,18 @@ __device__ __forceinline__ void finish_window(const KernelArgs& a, const Tone& f
     }
 }
 
-template <typename InT>
+template <typename InT, bool PRIVATE_PP>
 __device__ __noinline__ void post_window_warp(const KernelArgs& a, const double* row, long long w, int frame, int lane)
 {
     // a private copy (registers): through the reference the loop-invariant parameters are re-read with generic loads
     // (~30 cycles each on the single warp's critical path) wherever the compiler cannot prove they do not alias a store
-    const PostParams pp = a.post;
+    PostParams pp_copy;
+    const PostParams* pp_ptr = &a.post;
+    if constexpr (PRIVATE_PP) {
+        pp_copy = a.post;
+        pp_ptr = &pp_copy;
+    }
+    const PostParams& pp = *pp_ptr;
     const int K = pp.K;
     const bool valid = lane < K;
     const int j = valid ? lane : K - 1;
@@ -410,12 +482,24 @@ __device__ __noinline__ void post_window_warp(const KernelArgs& a, const double*
 // residual spectrum W lives in the posting warp's lane-reduction scratch, which is idle until the warp
 // transforms its next window.  Every consumer warp can therefore post a batch at the same time; the raw
 // buffer goes back to the ring when the estimator is done with X.
-template <typename InT>
-__device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, unsigned w_off, long long w_first, int frame,
-                                        int bsz, int batch_id, int lane)
+// PRIVATE_PP: work on a register copy of the parameters (see post_window_warp).  The 24-bin kernels keep the reference:
+// their transform already needs every register, and the copy would make the call site spill.
+template <typename InT, bool PRIVATE_PP>
+__device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, long long w_first, int frame_group, int bsz,
+                                        int batch_id)
 {
+    // (few scalar arguments: beyond the register-passed ones the ABI goes through local memory)
+    const int lane = threadIdx.x % PMU_WARP;
+    const int frame = frame_group >> 8, group = frame_group & 0xff;          // group < PMU_MAX_GROUPS = 256
+    const unsigned w_off = (unsigned)a.off_red + (unsigned)(threadIdx.x / PMU_WARP - 1) * (unsigned)a.red_bytes;
     unsigned char* smem = pmu_smem;
-    const PostParams pp = a.post;    // private copy: see post_window_warp
+    PostParams pp_copy;
+    const PostParams* pp_ptr = &a.post;
+    if constexpr (PRIVATE_PP) {
+        pp_copy = a.post;
+        pp_ptr = &pp_copy;
+    }
+    const PostParams& pp = *pp_ptr;
     CtrlBlock* ctrl = reinterpret_cast<CtrlBlock*>(smem + a.off_ctrl);
     const int K = pp.K;
     double* row = reinterpret_cast<double*>(smem + a.off_raw) + ((size_t)raw_buf * PMU_WARP + lane) * a.raw_stride;
@@ -446,6 +530,16 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, unsign
         *reinterpret_cast<volatile int*>(&ctrl->raw_owner[raw_buf]) = batch_id + a.n_raw;
     }
 
+    // Launches that carry several frames: the estimate above has no cross-frame dependency (the batches of a stream group's
+    // consecutive frames run concurrently on different warps); only the ROCOF recurrence below needs the state its
+    // predecessor frame leaves, so the hand-over (a shared-memory counter per group) is waited for HERE, not before the
+    // estimate.
+    if (a.n_frames > 1) {
+        if (lane == 0)
+            while (ld_volatile_s32(&ctrl->grp_done[group]) != frame) __nanosleep(64);
+        __syncwarp();
+        __threadfence_block();
+    }
     if (active) {
         RocofState rs;
         // the previous frame's state may have been written by another warp of this CTA
@@ -484,6 +578,10 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, unsign
         }
     }
     __syncwarp();
+    if (a.n_frames > 1 && lane == 0) {
+        __threadfence_block();
+        *reinterpret_cast<volatile int*>(&ctrl->grp_done[group]) = frame + 1;
+    }
 }
 
 // Load the M samples of one residue from a stage (row pitch in elements).  FULL: every lane of
@@ -586,10 +684,15 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             // lane b issues row b, so the address arithmetic of the rows runs in parallel instead of as one thread's
             // serial chain (which capped multi-slab windows at ~13 M copies/s per SM).
             const bool whole = (a.nslab == 1 && pitch == a.L);
-            int st = 0, sl = 0, t = 0, f = 0;      // running (stage, slab, pass, frame) of slab i
+            int st = 0, sl = 0;                    // running (stage, slab) of slab i
             uint32_t par = 0;
-            long long ring_pos = a.ring_cap ? a.ring_start % a.ring_cap : 0;   // ring position of frame f's first sample
+            BatchMap pbm;
+            pbm.init(n_packs, PMU_WARP / WP);
+            ItemWalker wk;                         // (frame, pass) of the item slab i belongs to
+            wk.init(pbm, n_packs, a.n_frames, a.group_major, a.ring_cap, a.ring_start, a.hop);
             for (int i = 0; i < total_slabs; ++i) {
+                const int t = wk.t, f = wk.f;
+                const long long ring_pos = wk.ring_pos;
                 if (lane == 0) mbar_wait(&ctrl->empty[st], par ^ 1u);
                 __syncwarp();
                 unsigned char* dst = stages + (size_t)st * a.stage_bytes;
@@ -632,18 +735,19 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 if (++st == a.n_stage) { st = 0; par ^= 1u; }
                 if (++sl == a.nslab) {
                     sl = 0;
-                    if (++t == n_packs) {
-                        t = 0; ++f;
-                        ring_pos += a.hop;
-                        if (a.ring_cap && ring_pos >= a.ring_cap) ring_pos -= a.ring_cap;
-                    }
+                    wk.advance();
                 }
             }
         } else {
-            int st = 0, sl = 0, t = 0, f = 0;
+            int st = 0, sl = 0;
             uint32_t par = 0;
-            long long ring_pos = a.ring_cap ? a.ring_start % a.ring_cap : 0;
+            BatchMap pbm;
+            pbm.init(n_packs, PMU_WARP / WP);
+            ItemWalker wk;
+            wk.init(pbm, n_packs, a.n_frames, a.group_major, a.ring_cap, a.ring_start, a.hop);
             for (int i = 0; i < total_slabs; ++i) {
+                const int t = wk.t, f = wk.f;
+                const long long ring_pos = wk.ring_pos;
                 mbar_wait(&ctrl->empty[st], par ^ 1u);
                 InT* dst = reinterpret_cast<InT*>(stages + (size_t)st * a.stage_bytes);
                 const int tw = t * WP;
@@ -679,11 +783,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 if (++st == a.n_stage) { st = 0; par ^= 1u; }
                 if (++sl == a.nslab) {
                     sl = 0;
-                    if (++t == n_packs) {
-                        t = 0; ++f;
-                        ring_pos += a.hop;
-                        if (a.ring_cap && ring_pos >= a.ring_cap) ring_pos -= a.ring_cap;
-                    }
+                    wk.advance();
                 }
             }
         }
@@ -716,9 +816,13 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         }
         int f = 0, t = item;
         if (a.n_frames > 1) {
-            unsigned r;
-            f = (int)by_nlocal.div((unsigned)item, &r);
-            t = (int)r;
+            if (a.group_major) {
+                bm.item_group_major(item, a.n_frames, &f, &t);
+            } else {
+                unsigned r;
+                f = (int)by_nlocal.div((unsigned)item, &r);
+                t = (int)r;
+            }
         }
 
         // ---- pruned rectangular DFT of pass t (streams t*WP ... t*WP + WP-1 of this CTA), frame f ----
@@ -805,7 +909,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 __syncwarp();
                 __threadfence_block();
             }
-            post_window_warp<InT>(a, myrow, w_begin + t, f, lane);
+            post_window_warp<InT, (KC < 24)>(a, myrow, w_begin + t, f, lane);
             if (a.n_frames > 1) {
                 __syncwarp();
                 if (lane == 0) {
@@ -817,9 +921,10 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         }
         int g, slot, bsz, first_t;                 // in passes; converted to streams below when WP > 1
         bm.locate(t, &g, &slot, &bsz, &first_t);
-        const int gb = f * bm.nb + g;              // batch id over the whole launch, in ticket order
+        const int gb = a.group_major ? g * a.n_frames + f : f * bm.nb + g;   // batch id over the whole launch, in ticket order
         unsigned rb_u;
-        by_nraw.div((unsigned)gb, &rb_u);
+        if constexpr (KC >= 24) rb_u = (unsigned)gb % (unsigned)a.n_raw;   // the 24-bin kernels have no register to spare for the magic number
+        else by_nraw.div((unsigned)gb, &rb_u);
         const int rb = (int)rb_u;
         if (lane == 0) {
             while (ld_volatile_s32(&ctrl->raw_owner[rb]) != gb) __nanosleep(64);
@@ -857,18 +962,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             }
             // ---- this warp post-processes batch (f, g) ----
             __threadfence_block();
-            // frame f of these streams needs the ROCOF state left by frame f-1
-            if (a.n_frames > 1) {
-                if (lane == 0)
-                    while (ld_volatile_s32(&ctrl->grp_done[g]) != f) __nanosleep(64);
-                __syncwarp();
-                __threadfence_block();
-            }
-            post_batch<InT>(a, rb, red_off, w_begin + first_t, f, bsz, gb, lane);
-            if (a.n_frames > 1 && lane == 0) {
-                __threadfence_block();
-                *reinterpret_cast<volatile int*>(&ctrl->grp_done[g]) = f + 1;
-            }
+            post_batch<InT, (KC < 24)>(a, rb, w_begin + first_t, (f << 8) | g, bsz, gb);
         }
     }
     if (tl && lane == 0) tl[3] = global_ns();

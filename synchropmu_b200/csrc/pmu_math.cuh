@@ -511,14 +511,28 @@ struct RocofState {
     int st;
 };
 
-// Two-state ROCOF estimator + first-order low-pass (src/pmu_estimator.c:236-260).
+// Two-state ROCOF estimator + first-order low-pass (src/pmu_estimator.c:236-260).  Written with explicitly rounded
+// multiplies and adds (no FMA contraction): the kernel contains several inlined copies of this recurrence (single-frame
+// batches, the multi-frame ROCOF pass, the lane = bin path) and they must agree bit for bit - and this is also what the
+// reference's x86 build computes.
+#if defined(__CUDA_ARCH__)
+#define PMU_DMUL(a, b) __dmul_rn((a), (b))
+#define PMU_DADD(a, b) __dadd_rn((a), (b))
+#define PMU_DSUB(a, b) __dsub_rn((a), (b))
+#else
+PMU_HD double pmu_dround(double v) { volatile double t = v; return t; }
+#define PMU_DMUL(a, b) pmu_dround((a) * (b))
+#define PMU_DADD(a, b) pmu_dround((a) + (b))
+#define PMU_DSUB(a, b) pmu_dround((a) - (b))
+#endif
 PMU_HD double rocof_step(const PostParams& p, double freq, RocofState* s)
 {
-    double r = (freq - s->f_old) * p.frame_rate;                                   // :236
-    double rd = (r - s->dl0) * p.frame_rate;                                       // :237
+    double r = PMU_DMUL(PMU_DSUB(freq, s->f_old), p.frame_rate);                   // :236
+    double rd = PMU_DMUL(PMU_DSUB(r, s->dl0), p.frame_rate);                       // :237
     if (!s->st && (fabs(r) > p.thr0 || fabs(rd) > p.thr1)) s->st = 1;              // :240
     if (s->st && fabs(r) < p.thr2) s->st = 0;                                      // :241
-    double y = s->st ? r : (p.lp1 * r + p.lp2 * s->dl0 - p.lp0 * s->dl1);          // :244-253
+    double y = r;                                                                  // :244-253, left to right
+    if (!s->st) y = PMU_DSUB(PMU_DADD(PMU_DMUL(p.lp1, r), PMU_DMUL(p.lp2, s->dl0)), PMU_DMUL(p.lp0, s->dl1));
     s->f_old = freq;                                                               // :256-260
     s->dl0 = r;
     s->dl1 = y;
