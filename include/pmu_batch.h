@@ -185,6 +185,40 @@ int pmub_c37118_pack(int dtype, const void *frames, void *out, unsigned n_instan
                      unsigned n_channels, unsigned idcode0, unsigned soc, unsigned fracsec,
                      unsigned stat);
 
+/* The full C37.118.2-2011 format family, selected by the FORMAT word the CFG-2 frame announces:
+ *   bit 0  phasors: 0 rectangular (real, imaginary)      1 polar (magnitude, angle)
+ *   bit 1  phasors: 0 16-bit integer, scaled by PHUNIT    1 IEEE float
+ *   bit 3  FREQ / DFREQ: 0 16-bit integer (deviation from nominal in mHz, ROCOF in 0.01 Hz/s)   1 IEEE float (Hz, Hz/s)
+ * 16-bit phasor counts = value / (phunit[c] * 1e-5) (magnitudes unsigned, rectangular parts signed, saturating;
+ * polar angles = radians * 1e4).  pmub_c37118_frame_bytes_ex(n_ch, format) = 16 + n_ch * (4 | 8) + 2 * (2 | 4) + 2.
+ * `cuda_stream` (may be NULL = the legacy default stream) orders the packer after the estimator on the same stream -
+ * pass what was given to pmub_set_stream; with device `frames` and `out` the call does not synchronise.  Host buffers go
+ * through a staging area kept between calls. */
+#define PMUB_C37_POLAR 1u
+#define PMUB_C37_FLOAT_PHASORS 2u
+#define PMUB_C37_FLOAT_FREQ 8u
+#define PMUB_C37_FLOAT_POLAR (PMUB_C37_POLAR | PMUB_C37_FLOAT_PHASORS | PMUB_C37_FLOAT_FREQ)
+typedef struct {
+    unsigned format;      /* FORMAT word, bits 0..3 */
+    unsigned idcode0;     /* IDCODE of instance 0; instance i uses idcode0 + i */
+    unsigned soc, fracsec, stat;
+    unsigned f_nominal;   /* 50 or 60 (0 = 50): reference of the integer FREQ format, FNOM of CFG-2 */
+    const unsigned *phunit;            /* host, [n_channels] 24-bit conversion factors (1e-5 units per count); NULL = 1 */
+    const unsigned char *phunit_is_current; /* host, [n_channels] 0 = voltage, 1 = current (CFG-2 only); NULL = voltages */
+    unsigned cfg_count;   /* CFGCNT of CFG-2 */
+} pmub_c37_options;
+int pmub_c37118_frame_bytes_ex(unsigned n_channels, unsigned format);
+int pmub_c37118_pack_ex(int dtype, const void *frames, void *out, unsigned n_instances, unsigned n_channels,
+                        const pmub_c37_options *opt, void *cuda_stream);
+/* CFG-2 configuration frame (host side) of instance `instance`: one PMU block with its n_channels phasors, no analog
+ * or digital words.  station_name NULL = "PMU<instance>", channel_names NULL = "PH00".."PHnn", time_base = FRACSEC
+ * counts per second, data_rate = frames per second.  Returns the number of bytes written (<= cap) or -1. */
+int pmub_c37118_cfg2(unsigned char *out, unsigned cap, unsigned n_channels, const pmub_c37_options *opt,
+                     unsigned instance, const char *station_name, const char *const *channel_names,
+                     unsigned time_base, int data_rate);
+int pmub_sequence_components_on(int dtype, const void *frames, void *out, unsigned n_instances,
+                                unsigned n_channels, void *cuda_stream);
+
 /* ---- frames straight into another GPU's memory (optional gather, no collective) ---------
  * rank 0: pmub_peer_alloc -> device buffer + 64-byte CUDA IPC handle (ship the handle to the other
  * processes by any means); rank r: pmub_peer_open(handle) -> a pointer valid in r's address space;

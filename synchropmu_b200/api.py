@@ -66,6 +66,33 @@ class BatchInfo(C.Structure):
     ]
 
 
+class C37Options(C.Structure):
+    """``pmub_c37_options`` (include/pmu_batch.h)."""
+
+    _fields_ = [("format", C.c_uint), ("idcode0", C.c_uint), ("soc", C.c_uint), ("fracsec", C.c_uint), ("stat", C.c_uint),
+                ("f_nominal", C.c_uint), ("phunit", C.POINTER(C.c_uint)), ("phunit_is_current", C.POINTER(C.c_ubyte)),
+                ("cfg_count", C.c_uint)]
+
+
+C37_POLAR, C37_FLOAT_PHASORS, C37_FLOAT_FREQ = 1, 2, 8
+C37_FLOAT_POLAR = C37_POLAR | C37_FLOAT_PHASORS | C37_FLOAT_FREQ
+
+
+def _c37_options(n_ch, fmt, idcode0, soc, fracsec, stat, f_nominal, phunit, is_current, cfg_count=0):
+    o = C37Options()
+    o.format, o.idcode0, o.soc, o.fracsec, o.stat, o.f_nominal, o.cfg_count = fmt, idcode0, soc, fracsec, stat, f_nominal, cfg_count
+    keep = []
+    if phunit is not None:
+        arr = (C.c_uint * n_ch)(*[int(u) for u in phunit])
+        o.phunit = C.cast(arr, C.POINTER(C.c_uint))
+        keep.append(arr)
+    if is_current is not None:
+        arr = (C.c_ubyte * n_ch)(*[1 if u else 0 for u in is_current])
+        o.phunit_is_current = C.cast(arr, C.POINTER(C.c_ubyte))
+        keep.append(arr)
+    return o, keep
+
+
 def lib_path(dtype=np.float64, n_channels: int = 1) -> Path:
     """The ABI variant for (float_p, NUM_CHANLS); the pmub_* core is identical in all of them."""
     name = "libpmu_estimator"
@@ -128,12 +155,18 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.pmub_sequence_components.argtypes = [ip, vp, vp, C.c_uint, C.c_uint]
     lib.pmub_c37118_frame_bytes.argtypes = [C.c_uint]
     lib.pmub_c37118_pack.argtypes = [ip, vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
+    lib.pmub_c37118_frame_bytes_ex.argtypes = [C.c_uint, C.c_uint]
+    lib.pmub_c37118_pack_ex.argtypes = [ip, vp, vp, C.c_uint, C.c_uint, C.POINTER(C37Options), vp]
+    lib.pmub_c37118_cfg2.argtypes = [vp, C.c_uint, C.c_uint, C.POINTER(C37Options), C.c_uint, C.c_char_p,
+                                     C.POINTER(C.c_char_p), C.c_uint, ip]
+    lib.pmub_sequence_components_on.argtypes = [ip, vp, vp, C.c_uint, C.c_uint, vp]
     lib.pmub_peer_alloc.argtypes = [C.c_size_t, ip, C.POINTER(vp), vp]
     lib.pmub_peer_open.argtypes = [vp, ip, C.POINTER(vp)]
     lib.pmub_peer_close.argtypes = [vp]
     lib.pmub_peer_read.argtypes = [vp, vp, C.c_size_t]
     lib.pmub_peer_free.argtypes = [vp]
-    for fn in ("pmub_sequence_components", "pmub_c37118_frame_bytes", "pmub_c37118_pack", "pmub_peer_alloc",
+    for fn in ("pmub_sequence_components", "pmub_sequence_components_on", "pmub_c37118_frame_bytes", "pmub_c37118_pack",
+               "pmub_c37118_frame_bytes_ex", "pmub_c37118_pack_ex", "pmub_c37118_cfg2", "pmub_peer_alloc",
                "pmub_peer_open", "pmub_peer_close", "pmub_peer_read", "pmub_peer_free"):
         getattr(lib, fn).restype = ip
     for fn in ("pmub_validate", "pmub_parse_ini", "pmub_create", "pmub_create_ini", "pmub_destroy",
@@ -434,29 +467,38 @@ class BatchEstimator:
                 (spec[..., 0] + 1j * spec[..., 1]).reshape(shape + (self.n_bins,)))
 
 
-def sequence_components(frames, lib=None):
+def sequence_components(frames, lib=None, out=None, cuda_stream: int | None = None):
     """Symmetrical components of every three-phase channel group: frames ``[n_inst, n_ch, 4]`` (numpy or
-    torch, host or CUDA) -> ``[n_inst, n_ch // 3, 3, 2]`` = (amp, ph) of positive, negative, zero sequence."""
+    torch, host or CUDA) -> ``[n_inst, n_ch // 3, 3, 2]`` = (amp, ph) of positive, negative, zero sequence.
+    ``cuda_stream`` orders the kernel on the estimator's stream (device buffers: no synchronisation)."""
     lib = lib or load_library()
+    frames = _ingest(frames)
     n_inst, n_ch = int(frames.shape[0]), int(frames.shape[1])
     if hasattr(frames, "data_ptr"):
         import torch
 
         code = PMUB_F64 if frames.dtype == torch.float64 else PMUB_F32
-        out = torch.empty((n_inst, n_ch // 3, 3, 2), dtype=frames.dtype, device=frames.device)
+        if out is None:
+            out = torch.empty((n_inst, n_ch // 3, 3, 2), dtype=frames.dtype, device=frames.device)
         frames = frames.contiguous()
     else:
         frames = np.ascontiguousarray(frames)
         code = PMUB_F64 if frames.dtype == np.float64 else PMUB_F32
-        out = np.empty((n_inst, n_ch // 3, 3, 2), dtype=frames.dtype)
-    if lib.pmub_sequence_components(code, _ptr(frames), _ptr(out), n_inst, n_ch) != 0:
+        if out is None:
+            out = np.empty((n_inst, n_ch // 3, 3, 2), dtype=frames.dtype)
+    if lib.pmub_sequence_components_on(code, _ptr(frames), _ptr(out), n_inst, n_ch, C.c_void_p(cuda_stream or 0)) != 0:
         raise RuntimeError(f"pmub_sequence_components failed: {last_error(lib)}")
     return out
 
 
-def c37118_pack(frames, idcode0: int = 1, soc: int = 0, fracsec: int = 0, stat: int = 0, lib=None) -> np.ndarray:
-    """One IEEE C37.118.2 data frame per instance -> uint8 ``[n_inst, 26 + 8 n_ch]`` (host)."""
+def c37118_pack(frames, idcode0: int = 1, soc: int = 0, fracsec: int = 0, stat: int = 0, lib=None, fmt: int = C37_FLOAT_POLAR,
+                f_nominal: int = 50, phunit=None, cuda_stream: int | None = None, out=None):
+    """One IEEE C37.118.2 data frame per instance -> uint8 ``[n_inst, frame_bytes]``.  ``fmt`` is the FORMAT word
+    (``C37_POLAR | C37_FLOAT_PHASORS | C37_FLOAT_FREQ`` bits); ``phunit`` the per-channel conversion factors of the
+    16-bit phasor formats.  Host frames give a host array; CUDA tensors may be packed into a CUDA ``out`` tensor on
+    ``cuda_stream`` without synchronising."""
     lib = lib or load_library()
+    frames = _ingest(frames)
     n_inst, n_ch = int(frames.shape[0]), int(frames.shape[1])
     if hasattr(frames, "data_ptr"):
         import torch
@@ -466,10 +508,30 @@ def c37118_pack(frames, idcode0: int = 1, soc: int = 0, fracsec: int = 0, stat: 
     else:
         frames = np.ascontiguousarray(frames)
         code = PMUB_F64 if frames.dtype == np.float64 else PMUB_F32
-    out = np.empty((n_inst, lib.pmub_c37118_frame_bytes(n_ch)), dtype=np.uint8)
-    if lib.pmub_c37118_pack(code, _ptr(frames), out.ctypes.data, n_inst, n_ch, idcode0, soc, fracsec, stat) != 0:
-        raise RuntimeError(f"pmub_c37118_pack failed: {last_error(lib)}")
+    fb = lib.pmub_c37118_frame_bytes_ex(n_ch, fmt)
+    if out is None:
+        out = np.empty((n_inst, fb), dtype=np.uint8)
+    o, _keep = _c37_options(n_ch, fmt, idcode0, soc, fracsec, stat, f_nominal, phunit, None)
+    if lib.pmub_c37118_pack_ex(code, _ptr(frames), _ptr(out), n_inst, n_ch, C.byref(o), C.c_void_p(cuda_stream or 0)) != 0:
+        raise RuntimeError(f"pmub_c37118_pack_ex failed: {last_error(lib)}")
     return out
+
+
+def c37118_cfg2(n_channels: int, instance: int = 0, idcode0: int = 1, soc: int = 0, fracsec: int = 0, fmt: int = C37_FLOAT_POLAR,
+                f_nominal: int = 50, phunit=None, is_current=None, station_name: str | None = None, channel_names=None,
+                time_base: int = 1_000_000, data_rate: int = 50, cfg_count: int = 0, lib=None) -> bytes:
+    """The CFG-2 configuration frame that announces the data frames of :func:`c37118_pack` for one instance."""
+    lib = lib or load_library()
+    o, _keep = _c37_options(n_channels, fmt, idcode0, soc, fracsec, 0, f_nominal, phunit, is_current, cfg_count)
+    names = None
+    if channel_names is not None:
+        names = (C.c_char_p * n_channels)(*[n.encode() for n in channel_names])
+    buf = (C.c_ubyte * 65535)()
+    n = lib.pmub_c37118_cfg2(buf, 65535, n_channels, C.byref(o), instance, station_name.encode() if station_name else None,
+                             names, time_base, data_rate)
+    if n < 0:
+        raise RuntimeError(f"pmub_c37118_cfg2 failed: {last_error(lib)}")
+    return bytes(buf[:n])
 
 
 class RawDevicePtr:

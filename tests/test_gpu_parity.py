@@ -910,33 +910,130 @@ def test_sequence_components_match_numpy():
     assert abs(got[0, 0, 0, 0] - 230.0) < 1e-9 and got[0, 0, 1, 0] < 1e-9 and got[0, 0, 2, 0] < 1e-9
 
 
-def test_c37118_data_frames_match_python_packer():
+def _crc_ccitt(data: bytes) -> int:
+    crc = 0xFFFF
+    for byte in data:
+        crc ^= byte << 8
+        for _ in range(8):
+            crc = ((crc << 1) ^ 0x1021) & 0xFFFF if crc & 0x8000 else (crc << 1) & 0xFFFF
+    return crc
+
+
+def _py_c37_frame(fr, i, fmt, id0, soc, fracsec, stat, f_nom, phunit):
+    """Independent packer of one C37.118.2-2011 data frame (section 6.3, table 6/9) for instance i."""
     import struct
 
-    def crc_ccitt(data: bytes) -> int:
-        crc = 0xFFFF
-        for byte in data:
-            crc ^= byte << 8
-            for _ in range(8):
-                crc = ((crc << 1) ^ 0x1021) & 0xFFFF if crc & 0x8000 else (crc << 1) & 0xFFFF
-        return crc
+    n_ch = fr.shape[1]
+    size = 16 + n_ch * (8 if fmt & 2 else 4) + 2 * (4 if fmt & 8 else 2) + 2
+    body = struct.pack(">HHHIIH", 0xAA01, size, (id0 + i) & 0xFFFF, soc, fracsec, stat)
 
-    assert crc_ccitt(b"123456789") == 0x29B1                                     # CRC-16/CCITT-FALSE check value
-    rng = np.random.default_rng(8)
-    n_inst, n_ch = 300, 6
-    fr = rng.uniform(-100, 100, (n_inst, n_ch, 4))
-    fr[..., 2] = 50 + rng.uniform(-1, 1, (n_inst, n_ch))
-    soc, fracsec, stat, id0 = 1_700_000_000, (0x0F << 24) | 123456, 0x0000, 7
-    got = api.c37118_pack(fr, idcode0=id0, soc=soc, fracsec=fracsec, stat=stat)
-    size = 26 + 8 * n_ch
-    assert got.shape == (n_inst, size)
-    for i in (0, 1, 150, 299):
-        body = struct.pack(">HHHIIH", 0xAA01, size, (id0 + i) & 0xFFFF, soc, fracsec, stat)
-        for c in range(n_ch):
-            body += struct.pack(">ff", fr[i, c, 0], fr[i, c, 1])
+    def s16(v):
+        return int(min(32767, max(-32768, np.rint(v))))
+
+    for c in range(n_ch):
+        amp, ph = float(fr[i, c, 0]), float(fr[i, c, 1])
+        unit = (phunit[c] if phunit is not None else 1) * 1e-5
+        if fmt & 2:
+            body += struct.pack(">ff", amp, ph) if fmt & 1 else struct.pack(">ff", amp * math.cos(ph), amp * math.sin(ph))
+        elif fmt & 1:
+            body += struct.pack(">Hh", int(min(65535, max(0, np.rint(amp / unit)))), s16(ph * 1e4))
+        else:
+            body += struct.pack(">hh", s16(amp * math.cos(ph) / unit), s16(amp * math.sin(ph) / unit))
+    if fmt & 8:
         body += struct.pack(">ff", fr[i, 0, 2], fr[i, 0, 3])
-        body += struct.pack(">H", crc_ccitt(body))
-        assert bytes(got[i]) == body
+    else:
+        body += struct.pack(">hh", s16((float(fr[i, 0, 2]) - f_nom) * 1000.0), s16(float(fr[i, 0, 3]) * 100.0))
+    return body + struct.pack(">H", _crc_ccitt(body))
+
+
+@pytest.mark.parametrize("fmt", [api.C37_FLOAT_POLAR, api.C37_FLOAT_PHASORS | api.C37_FLOAT_FREQ, api.C37_POLAR, 0,
+                                 api.C37_POLAR | api.C37_FLOAT_FREQ, api.C37_FLOAT_PHASORS],
+                         ids=["float_polar", "float_rect", "int_polar", "int_rect", "int_polar_float_freq", "float_rect_int_freq"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_c37118_data_frames_match_python_packer(fmt, dtype):
+    assert _crc_ccitt(b"123456789") == 0x29B1                                     # CRC-16/CCITT-FALSE check value
+    rng = np.random.default_rng(8)
+    n_inst, n_ch = 301, 6                          # 301: the last block of 128 threads is short
+    fr = np.zeros((n_inst, n_ch, 4))
+    fr[..., 0] = rng.uniform(0.0, 400.0, (n_inst, n_ch))
+    fr[..., 1] = rng.uniform(-math.pi, math.pi, (n_inst, n_ch))
+    fr[..., 2] = 50 + rng.uniform(-1, 1, (n_inst, n_ch))
+    fr[..., 3] = rng.uniform(-5, 5, (n_inst, n_ch))
+    fr[3, 0, 0] = 1e9                              # saturates the 16-bit formats
+    fr = fr.astype(dtype)
+    phunit = [1000, 1000, 1000, 50, 50, 50]        # 0.01 V and 0.0005 A per count
+    soc, fracsec, stat, id0 = 1_700_000_000, (0x0F << 24) | 123456, 0x0000, 7
+    got = api.c37118_pack(fr, idcode0=id0, soc=soc, fracsec=fracsec, stat=stat, fmt=fmt, f_nominal=50, phunit=phunit)
+    assert got.shape == (n_inst, api.load_library().pmub_c37118_frame_bytes_ex(n_ch, fmt))
+    near_tie = 0
+    for i in (0, 1, 3, 127, 128, 150, 300):
+        want = _py_c37_frame(fr.astype(np.float64), i, fmt, id0, soc, fracsec, stat, 50, phunit)
+        if bytes(got[i]) != want:
+            # 16-bit fields may differ by one count where sin/cos of the two libraries round the other way at a tie
+            a, b = np.frombuffer(bytes(got[i])[16:-2], dtype=">i2"), np.frombuffer(want[16:-2], dtype=">i2")
+            assert not (fmt & 2) and np.max(np.abs(a.astype(int) - b.astype(int))) <= 1, (i, fmt)
+            near_tie += 1
+            body = bytes(got[i])[:-2]
+            assert int.from_bytes(bytes(got[i])[-2:], "big") == _crc_ccitt(body)
+    assert near_tie <= 2
+    if fmt == api.C37_FLOAT_POLAR and dtype == np.float64:
+        # the round-1 entry point is this format
+        assert np.array_equal(api.load_library() and got, api.c37118_pack(fr, idcode0=id0, soc=soc, fracsec=fracsec, stat=stat))
+
+
+def test_c37118_cfg2_round_trip_and_device_side_packing_on_a_stream():
+    """CFG-2 parsed back field by field (it must describe the data frames the packer emits), and the packer running on
+    the estimator's stream with device frames and a device output, without a host synchronisation in between."""
+    import struct
+
+    torch = pytest.importorskip("torch")
+    n_ch = 6
+    phunit = [915527, 915527, 915527, 45776, 45776, 45776]
+    names = ["VA", "VB", "VC", "IA", "IB", "IC"]
+    fmt = api.C37_POLAR                                  # 16-bit polar phasors, integer FREQ
+    cfg2 = api.c37118_cfg2(n_ch, instance=5, idcode0=100, soc=1_700_000_000, fracsec=42, fmt=fmt, f_nominal=60, phunit=phunit,
+                           is_current=[0, 0, 0, 1, 1, 1], station_name="SUB", channel_names=names, time_base=1_000_000,
+                           data_rate=60, cfg_count=3)
+    sync, size, idcode, soc, fracsec, time_base, num_pmu = struct.unpack(">HHHIIIH", cfg2[:20])
+    assert (sync, size, idcode, soc, fracsec, time_base, num_pmu) == (0xAA31, len(cfg2), 105, 1_700_000_000, 42, 1_000_000, 1)
+    assert cfg2[20:36] == b"SUB5".ljust(16)
+    idc, fword, phnmr, annmr, dgnmr = struct.unpack(">HHHHH", cfg2[36:46])
+    assert (idc, fword, phnmr, annmr, dgnmr) == (105, fmt, n_ch, 0, 0)
+    off = 46
+    for c in range(n_ch):
+        assert cfg2[off:off + 16] == names[c].encode().ljust(16)
+        off += 16
+    for c in range(n_ch):
+        (u,) = struct.unpack(">I", cfg2[off:off + 4])
+        assert u == ((1 << 24) if c >= 3 else 0) | phunit[c]
+        off += 4
+    fnom, cfgcnt, rate, chk = struct.unpack(">HHhH", cfg2[off:off + 8])
+    assert (fnom, cfgcnt, rate) == (0, 3, 60) and off + 8 == len(cfg2)      # FNOM bit 0 clear = 60 Hz
+    assert chk == _crc_ccitt(cfg2[:-2])
+    # data frames sized as CFG-2 announces: 16 + PHNMR * 4 + 2 + 2 + 2
+    lib = api.load_library()
+    assert lib.pmub_c37118_frame_bytes_ex(n_ch, fword) == 16 + phnmr * 4 + 4 + 2
+
+    cfg = configs.DEFAULT_INI
+    n_inst = 257
+    win, mid = three_phase_batch(cfg, n_inst, 1, seed=4)
+    s = torch.cuda.Stream()
+    with BatchEstimator(cfg, n_inst, 6) as est, torch.cuda.stream(s):
+        est.set_stream(s.cuda_stream)
+        w, m = torch.as_tensor(win[0], device="cuda"), torch.as_tensor(mid[0], device="cuda")
+        frames = torch.empty((n_inst, 6, 4), dtype=torch.float64, device="cuda")
+        wire = torch.zeros((n_inst, lib.pmub_c37118_frame_bytes_ex(6, api.C37_FLOAT_POLAR)), dtype=torch.uint8, device="cuda")
+        seq = torch.empty((n_inst, 2, 3, 2), dtype=torch.float64, device="cuda")
+        s.wait_stream(torch.cuda.default_stream())
+        est.estimate_async(w, m, frames)
+        api.c37118_pack(frames, idcode0=9, soc=11, fracsec=12, stat=0, out=wire, cuda_stream=s.cuda_stream)   # no sync in between
+        api.sequence_components(frames, out=seq, cuda_stream=s.cuda_stream)
+        s.synchronize()
+    fr = frames.cpu().numpy()
+    wire = wire.cpu().numpy()
+    for i in (0, 128, 256):
+        assert bytes(wire[i]) == _py_c37_frame(fr, i, api.C37_FLOAT_POLAR, 9, 11, 12, 0, 50, None)
+    assert np.array_equal(seq.cpu().numpy(), api.sequence_components(fr))
 
 
 def test_frames_land_in_another_process_buffer():
