@@ -38,6 +38,9 @@ CASES = {
     "mc_trig": ("m_class_config.ini", np.float64, 4096, 8, TRIG),
     "pc": ("p_class_config.ini", np.float64, 8192, 8, ()),
     "q22_trig": ("test_c_q22", np.float64, 4096, 4, TRIG),
+    "t2": ("test2_16cyc", np.float64, 1024, 4, ()),
+    "pc_f32": ("p_class_config.ini", np.float32, 8192, 8, ()),
+    "c5_f32": ("cfg5_600", np.float32, 21846, 8, ()),
 }
 
 
