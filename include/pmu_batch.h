@@ -239,6 +239,12 @@ int pmub_peer_free(void *dptr);
  *   spectrum double [n_bins][2] : the Hann-windowed DFT bins (what pmue_fft_r yields,
  *                     src/pmu_estimator.c:200)
  * fetched (to host arrays, either may be NULL) by pmub_get_debug. */
+/* Batched form of the reference's inner plug point pmue_fft_r(in, out, out_len, n_bins) (src/func_stubs.h:60-62):
+ * out[w][k] = sum_n in[w][n] exp(-2 pi i k n / win_len), k < n_bins, for every window w of the batch (no window function:
+ * pmu_estimate feeds pmue_fft_r the Hann-weighted samples, src/pmu_estimator.c:184-200).  `in` host or device
+ * float_p [n_instances][n_channels][win_len]; `out` host float_p complex [n_instances][n_channels][n_bins].
+ * The ROCOF state is not touched. */
+int pmub_fft_r(pmub_batch *b, const void *in, void *out);
 int pmub_set_debug(pmub_batch *b, int enable);
 int pmub_get_debug(pmub_batch *b, int *flags, double *spectrum);
 

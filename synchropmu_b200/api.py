@@ -151,6 +151,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.pmub_get_state.argtypes = [vp, vp, vp, vp, vp]
     lib.pmub_set_state.argtypes = [vp, vp, vp, vp, vp]
     lib.pmub_set_debug.argtypes = [vp, ip]
+    lib.pmub_fft_r.argtypes = [vp, vp, vp]
+    lib.pmub_fft_r.restype = ip
     lib.pmub_get_debug.argtypes = [vp, vp, vp]
     lib.pmub_sequence_components.argtypes = [ip, vp, vp, C.c_uint, C.c_uint]
     lib.pmub_c37118_frame_bytes.argtypes = [C.c_uint]
@@ -451,6 +453,16 @@ class BatchEstimator:
              ("freq_old", "dl0", "dl1", "state")}
         self._check(self.lib.pmub_set_state(self._h, a["freq_old"].ctypes.data, a["dl0"].ctypes.data,
                                             a["dl1"].ctypes.data, a["state"].ctypes.data), "pmub_set_state")
+
+    def fft_r(self, windows) -> np.ndarray:
+        """The reference's ``pmue_fft_r`` for every window of the batch: the ``n_bins`` lowest DFT bins of the samples as
+        given (no window function) -> complex ``[n_instances, n_channels, n_bins]``; the ROCOF state is not touched."""
+        windows = _ingest(windows)
+        if not hasattr(windows, "data_ptr"):
+            windows = np.ascontiguousarray(windows, dtype=self.dtype)
+        out = np.empty((self.n_instances, self.n_channels, self.n_bins, 2), dtype=self.dtype)
+        self._check(self.lib.pmub_fft_r(self._h, _ptr(windows), out.ctypes.data), "pmub_fft_r")
+        return out[..., 0] + 1j * out[..., 1]
 
     # -- parity observability -----------------------------------------------
     def set_debug(self, enable: bool = True) -> None:

@@ -69,6 +69,7 @@ struct pmub_batch {
     double* d_spec;
     unsigned long long* d_timeline;   // profiling aid (pmub_debug_timeline)
     bool debug, mirror;
+    bool spec_raw;              // debug spectrum = rectangular-window bins (pmub_fft_r)
     // small-batch pinned staging
     unsigned char* h_in;
     unsigned char* h_out;
@@ -179,6 +180,7 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     a.mid_frame_stride = b->n_inst;
     a.dbg = b->debug ? b->d_dbg + w0 : nullptr;
     a.spec_out = b->debug ? b->d_spec + (size_t)w0 * b->cfg.n_bins * 2 : nullptr;
+    a.spec_raw = b->spec_raw ? 1 : 0;
     a.state_export = d_export_base ? d_export_base + (size_t)w0 * 4 : nullptr;
     a.timeline = b->d_timeline;
     // a handful of windows (the single-instance drop-in path): one warp per window end to end
@@ -933,6 +935,45 @@ int pmub_get_debug(pmub_batch* b, int* flags, double* spectrum)
     const size_t n = (size_t)b->n_windows;
     if (flags) CUDA_OK(cudaMemcpy(flags, b->d_dbg, n * sizeof(int), cudaMemcpyDeviceToHost));
     if (spectrum) CUDA_OK(cudaMemcpy(spectrum, b->d_spec, n * b->cfg.n_bins * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+/* The reference's inner plug point as a batched call: pmue_fft_r(in, out, out_len, n_bins) (src/func_stubs.h:60-62,
+ * default dft_r, src/pmu_estimator.c:487-510) for every window of the batch - the n_bins lowest bins of the DFT of the
+ * samples AS GIVEN (no window applied; pmu_estimate feeds it Hann-weighted samples, :184-200).
+ *   in   float_p [n_instances][n_channels][win_len], host or device
+ *   out  float_p complex (re, im interleaved) [n_instances][n_channels][n_bins], host
+ * Runs the same kernel (the transform is fused into it) with spectrum recording on; the ROCOF state is left untouched. */
+int pmub_fft_r(pmub_batch* b, const void* in, void* out)
+{
+    if (!b || !in || !out) { set_error("[pmu_fft_r] ERROR: bad argument"); return -1; }
+    CUDA_OK(cudaSetDevice(b->device));
+    if (pmub_sync(b)) return -1;
+    const size_t n = (size_t)b->n_windows, K = b->cfg.n_bins, sz = (size_t)b->dtype;
+    std::vector<double> f0(n), d0(n), d1(n);
+    std::vector<unsigned char> st(n);
+    if (pmub_get_state(b, f0.data(), d0.data(), d1.data(), st.data())) return -1;
+    const bool was_debug = b->debug, was_mirror = b->mirror;
+    if (pmub_set_debug(b, 1)) return -1;
+    b->spec_raw = true;
+    b->mirror = false;
+    int rc = -1;
+    unsigned char *d_fr = nullptr, *d_mid = nullptr;
+    if (cudaMalloc(&d_fr, n * 4 * sz) == cudaSuccess && cudaMalloc(&d_mid, (size_t)b->n_inst * sz) == cudaSuccess &&
+        cudaMemset(d_mid, 0, (size_t)b->n_inst * sz) == cudaSuccess)
+        rc = pmub_estimate(b, in, d_mid, d_fr);
+    cudaFree(d_fr);
+    cudaFree(d_mid);
+    b->spec_raw = false;
+    b->mirror = was_mirror;
+    std::vector<double> spec(n * K * 2);
+    if (rc == 0) rc = pmub_get_debug(b, nullptr, spec.data());
+    b->debug = was_debug;
+    if (pmub_set_state(b, f0.data(), d0.data(), d1.data(), st.data())) rc = -1;
+    if (rc) return -1;
+    if (sz == 8) memcpy(out, spec.data(), spec.size() * sizeof(double));
+    else
+        for (size_t i = 0; i < spec.size(); ++i) ((float*)out)[i] = (float)spec[i];
     return 0;
 }
 

@@ -94,6 +94,7 @@ struct KernelArgs {
     // optional debug / mirror outputs (may be null); frame-major like `frames`
     int* dbg;                    // [n_frames][frame_stride]  km | flags
     double* spec_out;            // [n_frames][frame_stride][K][2] Hann-windowed bins
+    int spec_raw;                // ... or the rectangular-window bins (what pmue_fft_r returns for the same samples)
     double* state_export;        // [frame_stride][4]  f_old, dl0, dl1, state after the last frame
     // small launches (a few windows, e.g. the single-instance pmu_estimate): each warp runs the estimator of
     // the window it has just transformed, lane = bin (peak search = warp-shuffle argmax), no batching
@@ -449,8 +450,8 @@ __device__ __noinline__ void post_window_warp(const KernelArgs& a, const double*
     const pmu_c xw = hann_combine(row, j);
     const double xr = xw.x, xi = xw.y;
     if (a.spec_out && valid) {
-        a.spec_out[((size_t)wf * K + j) * 2] = xr;
-        a.spec_out[((size_t)wf * K + j) * 2 + 1] = xi;
+        a.spec_out[((size_t)wf * K + j) * 2] = a.spec_raw ? row[2 * j] : xr;
+        a.spec_out[((size_t)wf * K + j) * 2 + 1] = a.spec_raw ? row[2 * j + 1] : xi;
     }
     // the same single loop as estimate_tone (pmu_math.cuh): "estimate a tone from Y, subtract it from X into W"
     Tone f;
@@ -512,8 +513,15 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, long l
     Tone t;
     int dbg = 0;
     if (active) {
+        if (a.spec_out && a.spec_raw) {
+            for (int k = 0; k < K; ++k) {
+                const pmu_c xr_ = X.get(k);
+                a.spec_out[((size_t)wf * K + k) * 2] = xr_.x;
+                a.spec_out[((size_t)wf * K + k) * 2 + 1] = xr_.y;
+            }
+        }
         hann_combine_inplace(X, K);
-        if (a.spec_out) {
+        if (a.spec_out && !a.spec_raw) {
             for (int k = 0; k < K; ++k) {
                 const pmu_c xw = X.get(k);
                 a.spec_out[((size_t)wf * K + k) * 2] = xw.x;

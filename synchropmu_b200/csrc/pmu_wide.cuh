@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(PMU_WIDE_THREADS) pmu_wide_kernel(const __grid
             const pmu_c x = hann_combine(rect, j);
             X[j] = x;
             if (a.spec_out) {
-                a.spec_out[((size_t)w * K + j) * 2] = x.x;
-                a.spec_out[((size_t)w * K + j) * 2 + 1] = x.y;
+                a.spec_out[((size_t)w * K + j) * 2] = a.spec_raw ? rect[2 * j] : x.x;
+                a.spec_out[((size_t)w * K + j) * 2 + 1] = a.spec_raw ? rect[2 * j + 1] : x.y;
             }
         }
         __syncwarp();

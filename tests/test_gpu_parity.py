@@ -287,6 +287,36 @@ def test_cuda_array_interface_and_dlpack_inputs():
     assert np.isfinite(want.cpu().numpy()).all()
 
 
+@pytest.mark.parametrize("cfgname,dtype", [("config.ini", np.float64), ("m_class_config.ini", np.float64), ("cfg5_600", np.float64),
+                                           ("config.ini", np.float32)])
+def test_batched_fft_r_matches_the_reference_plug_point(cfgname, dtype):
+    """pmub_fft_r = pmue_fft_r / dft_r (src/pmu_estimator.c:487-546) per window: the n_bins lowest bins of the plain DFT of
+    the given samples.  Checked against numpy's FFT of the same (Hann-weighted, as pmu_estimate feeds it) samples, for a
+    batch that takes the lane = window path and a small one that takes lane = bin; the ROCOF state must not move."""
+    cfg = configs.NAMED[cfgname]
+    N, K = configs.win_len(cfg), cfg["n_bins"]
+    hann = 0.5 * (1 - np.cos(2 * np.pi * np.arange(N) / N))
+    for n_inst in (3, 40):
+        win, mid = three_phase_batch(cfg, n_inst, 1, seed=n_inst)
+        sw = (win[0] * hann).astype(dtype)
+        with BatchEstimator(cfg, n_inst, 6, dtype=dtype) as est:
+            est.estimate(win[0].astype(dtype), mid[0].astype(dtype))
+            before = est.get_state()
+            got = est.fft_r(sw)
+            after = est.get_state()
+            # ... and the estimator still works afterwards, exactly as if nothing had happened in between
+            again = est.estimate(win[0].astype(dtype), mid[0].astype(dtype))
+        with BatchEstimator(cfg, n_inst, 6, dtype=dtype) as ref:
+            ref.estimate(win[0].astype(dtype), mid[0].astype(dtype))
+            want_again = ref.estimate(win[0].astype(dtype), mid[0].astype(dtype))
+        want = np.fft.fft(sw.astype(np.float64), axis=-1)[..., :K]
+        scale = np.abs(want).max(axis=-1, keepdims=True)
+        assert np.max(np.abs(got - want) / scale) < (1e-12 if dtype == np.float64 else 2e-6)
+        for k in before:
+            assert np.array_equal(before[k], after[k])
+        assert np.array_equal(again, want_again)
+
+
 def test_rocof_state_checkpoint_resume_and_reset():
     cfg = configs.DEFAULT_INI
     n_inst, T = 12, 6
