@@ -493,6 +493,8 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     a.n_stage = b->plan.n_stage; a.stage_bytes = b->plan.stage_bytes; a.n_cons = b->plan.n_cons;
     a.n_raw = b->plan.n_raw; a.raw_stride = b->plan.raw_stride; a.red_bytes = b->plan.red_bytes;
     a.n_u = b->plan.n_u;
+    a.interleave = (b->plan.nslab > 1 && 2 * b->plan.nslab > b->plan.n_stage &&
+                    !(getenv("PMU_NO_INTERLEAVE") && atoi(getenv("PMU_NO_INTERLEAVE")))) ? 1 : 0;
     a.off_ctrl = b->plan.off_ctrl; a.off_U = b->plan.off_U; a.off_V = b->plan.off_V; a.off_trig = b->plan.off_trig;
     a.off_raw = b->plan.off_raw; a.off_red = b->plan.off_red; a.off_stage = b->plan.off_stage;
     a.U = b->dU; a.V = b->dV; a.trig = b->dT;

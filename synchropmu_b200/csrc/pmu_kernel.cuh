@@ -79,6 +79,9 @@ struct KernelArgs {
     // (the n_frames windows of a group of <= 32 streams back to back: in ring mode consecutive windows of a stream
     // overlap by win_len - hop samples, which are then still in L2 when the next frame reads them)
     int group_major;
+    // multi-slab windows whose slabs would fill most of the ring: interleave the slabs of n_cons consecutive windows
+    // (see ItemWalker); windows of a few slabs in a deep ring (M-class: 2 slabs, 11 stages) stay window after window
+    int interleave;
     long long frame_stride;      // streams per frame in the caller's arrays (>= n_windows: a launch
                                  // may cover a sub-range of the batch), in windows
     long long mid_frame_stride;  // instances per frame in `mid`
@@ -209,27 +212,38 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p)
 
 // ---- division by a run-time constant without the ~25-instruction integer-divide sequence ----
 // q = umulhi(x, floor((2^32-1)/d)) is the true quotient or one less (x < 2^31): one correction.
-struct FastDiv {
+// PLAIN: an ordinary division instead (the 24-bin kernels have no registers to spare for the magic numbers; their
+// per-window work is large enough for the ~20-instruction sequence not to matter).
+template <bool PLAIN>
+struct FastDivT {
     unsigned d, m;
     __device__ __forceinline__ void init(unsigned dd)
     {
         d = dd;
-        m = 0xFFFFFFFFu / dd;
+        if constexpr (!PLAIN) m = 0xFFFFFFFFu / dd;
     }
     __device__ __forceinline__ unsigned div(unsigned x, unsigned* rem) const
     {
-        unsigned q = __umulhi(x, m);
-        unsigned r = x - q * d;
-        if (r >= d) { ++q; r -= d; }
-        *rem = r;
-        return q;
+        if constexpr (PLAIN) {
+            const unsigned q = x / d;
+            *rem = x - q * d;
+            return q;
+        } else {
+            unsigned q = __umulhi(x, m);
+            unsigned r = x - q * d;
+            if (r >= d) { ++q; r -= d; }
+            *rem = r;
+            return q;
+        }
     }
 };
+typedef FastDivT<false> FastDiv;
 
 // ---- window -> (batch, slot) mapping inside one CTA: balanced batches of <= 32 -----------
-struct BatchMap {
+template <bool PLAIN>
+struct BatchMapT {
     int nb, q, rem;  // batches, base size, number of batches with q+1 windows
-    FastDiv by_q, by_q1;
+    FastDivT<PLAIN> by_q, by_q1;
     __device__ __forceinline__ void init(int n, int cap = PMU_WARP)
     {
         nb = (n + cap - 1) / cap;
@@ -268,24 +282,57 @@ struct BatchMap {
     }
 };
 
-// ---- the producer's walk over the launch's items, in the same order the consumers decode their tickets --------------
+typedef BatchMapT<false> BatchMap;
+
+// ---- the producer's walk over the launch's slabs, in the order the consumers expect them in the ring ----------------
+// Items (one warp pass = one window, or WP packed ones) are numbered in ticket order: frame-major, or group-major for
+// streaming launches.  A single-slab item is one ring position.  Multi-slab windows are INTERLEAVED: the items are taken
+// in groups of C = n_cons consecutive ones (one per consumer warp) and the ring carries slab 0 of every item of the
+// group, then slab 1 of every item, ...  Filling the ring window after window would put all of one window's slabs into
+// the stages at once (a 16384-sample window is 8 slabs) and leave the other warps with nothing to work on.
+//   position of (item, slab) = gstart * nslab + slab * Cg + (item - gstart),  gstart = item / C * C, Cg = min(C, n_items - gstart)
 struct ItemWalker {
-    int f, t;               // frame and pass of the current item
+    int f, t, sl;           // frame, pass and slab of the current ring position
     long long ring_pos;     // ring position of frame f's first sample (streaming front end)
-    // frame-major: t runs over the passes, then f advances; group-major: slot runs over the group, then f, then the group
-    int group_major, n_packs, F, hop;
+    int group_major, n_packs, F, hop, nslab, C, n_items;
     long long cap, pos0;
-    int g, slot, gsize, gfirst, q, rem;
-    __device__ __forceinline__ void init(const BatchMap& bm, int n_packs_, int n_frames, int group_major_, long long ring_cap,
-                                         long long ring_start, int hop_)
+    int g, slot, gsize, gfirst, q, rem;      // single-slab walk
+    int gstart, Cg, j;                       // multi-slab walk
+    __device__ __forceinline__ void set_item(int item)
+    {
+        if (group_major) {
+            const int big_items = rem * (q + 1) * F;
+            if (item < big_items) {
+                const int gg = item / ((q + 1) * F), r = item - gg * (q + 1) * F;
+                f = r / (q + 1);
+                t = gg * (q + 1) + (r - f * (q + 1));
+            } else {
+                const int i2 = item - big_items;
+                const int gg = i2 / (q * F), r = i2 - gg * q * F;
+                f = r / q;
+                t = rem * (q + 1) + gg * q + (r - f * q);
+            }
+        } else {
+            f = item / n_packs;
+            t = item - f * n_packs;
+        }
+        ring_pos = pos0 + (long long)f * hop;
+        if (cap && ring_pos >= cap) ring_pos -= cap;
+    }
+    template <class Map>
+    __device__ __forceinline__ void init(const Map& bm, int n_packs_, int n_frames, int group_major_, long long ring_cap,
+                                         long long ring_start, int hop_, int nslab_, int n_cons, int interleave)
     {
         group_major = group_major_ && n_frames > 1;
-        n_packs = n_packs_; F = n_frames; hop = hop_; cap = ring_cap;
+        n_packs = n_packs_; F = n_frames; hop = hop_; cap = ring_cap; nslab = nslab_; C = interleave ? n_cons : 1;
+        n_items = n_packs_ * n_frames;
         pos0 = ring_cap ? ring_start % ring_cap : 0;
         ring_pos = pos0;
-        f = 0; t = 0; g = 0; slot = 0; gfirst = 0;
+        f = 0; t = 0; sl = 0; g = 0; slot = 0; gfirst = 0;
         q = bm.q; rem = bm.rem;
         gsize = rem > 0 ? q + 1 : q;
+        gstart = 0; j = 0;
+        Cg = C < n_items ? C : n_items;
     }
     __device__ __forceinline__ void next_frame()
     {
@@ -293,8 +340,22 @@ struct ItemWalker {
         ring_pos += hop;
         if (cap && ring_pos >= cap) ring_pos -= cap;
     }
-    __device__ __forceinline__ void advance()
+    __device__ __forceinline__ void advance()      // to the next ring position
     {
+        if (nslab > 1 && C > 1) {
+            if (++j == Cg) {
+                j = 0;
+                if (++sl == nslab) {
+                    sl = 0;
+                    gstart += Cg;
+                    Cg = C < n_items - gstart ? C : n_items - gstart;
+                }
+            }
+            set_item(gstart + j);
+            return;
+        }
+        if (++sl < nslab) return;      // window after window: the next slab of the same item
+        sl = 0;
         if (!group_major) {
             if (++t == n_packs) { t = 0; next_frame(); }
             return;
@@ -692,14 +753,14 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             // lane b issues row b, so the address arithmetic of the rows runs in parallel instead of as one thread's
             // serial chain (which capped multi-slab windows at ~13 M copies/s per SM).
             const bool whole = (a.nslab == 1 && pitch == a.L);
-            int st = 0, sl = 0;                    // running (stage, slab) of slab i
+            int st = 0;                            // stage of ring position i
             uint32_t par = 0;
             BatchMap pbm;
             pbm.init(n_packs, PMU_WARP / WP);
-            ItemWalker wk;                         // (frame, pass) of the item slab i belongs to
-            wk.init(pbm, n_packs, a.n_frames, a.group_major, a.ring_cap, a.ring_start, a.hop);
+            ItemWalker wk;                         // (frame, pass, slab) at ring position i
+            wk.init(pbm, n_packs, a.n_frames, a.group_major, a.ring_cap, a.ring_start, a.hop, a.nslab, a.n_cons, a.interleave);
             for (int i = 0; i < total_slabs; ++i) {
-                const int t = wk.t, f = wk.f;
+                const int t = wk.t, f = wk.f, sl = wk.sl;
                 const long long ring_pos = wk.ring_pos;
                 if (lane == 0) mbar_wait(&ctrl->empty[st], par ^ 1u);
                 __syncwarp();
@@ -741,20 +802,17 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                                           &ctrl->full[st]);
                 }
                 if (++st == a.n_stage) { st = 0; par ^= 1u; }
-                if (++sl == a.nslab) {
-                    sl = 0;
-                    wk.advance();
-                }
+                wk.advance();
             }
         } else {
-            int st = 0, sl = 0;
+            int st = 0;
             uint32_t par = 0;
             BatchMap pbm;
             pbm.init(n_packs, PMU_WARP / WP);
             ItemWalker wk;
-            wk.init(pbm, n_packs, a.n_frames, a.group_major, a.ring_cap, a.ring_start, a.hop);
+            wk.init(pbm, n_packs, a.n_frames, a.group_major, a.ring_cap, a.ring_start, a.hop, a.nslab, a.n_cons, a.interleave);
             for (int i = 0; i < total_slabs; ++i) {
-                const int t = wk.t, f = wk.f;
+                const int t = wk.t, f = wk.f, sl = wk.sl;
                 const long long ring_pos = wk.ring_pos;
                 mbar_wait(&ctrl->empty[st], par ^ 1u);
                 InT* dst = reinterpret_cast<InT*>(stages + (size_t)st * a.stage_bytes);
@@ -789,10 +847,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 }
                 cp_async_mbar_arrive(&ctrl->full[st]);
                 if (++st == a.n_stage) { st = 0; par ^= 1u; }
-                if (++sl == a.nslab) {
-                    sl = 0;
-                    wk.advance();
-                }
+                wk.advance();
             }
         }
         return;
@@ -802,15 +857,15 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     // ================= CONSUMERS =================
     unsigned long long* tl = a.timeline ? a.timeline + ((size_t)blockIdx.x * (PMU_BLOCK_THREADS / PMU_WARP) + warp) * 4 : nullptr;
     if (tl && lane == 0) { tl[0] = global_ns(); tl[1] = 0; }
-    BatchMap bm;                          // batches of <= 32 streams = <= 32 / WP passes
+    BatchMapT<(KC >= 24)> bm;             // batches of <= 32 streams = <= 32 / WP passes
     bm.init(n_packs, PMU_WARP / WP);
-    FastDiv by_nlocal, by_nstage;
+    FastDivT<(KC >= 24)> by_nlocal, by_nstage;
     by_nlocal.init((unsigned)n_packs);
     const int sub = lane / G;             // which stream of the pass this lane works on (0 when WP == 1)
     const int gl = lane % G;              // its lane index within that stream's group
     by_nstage.init((unsigned)a.n_stage);
     const int w_per_it = a.W / PMU_WARP;  // full-slab residue groups (W % 32 == 0 when nslab > 1)
-    FastDiv by_nraw;
+    FastDivT<(KC >= 24)> by_nraw;
     by_nraw.init((unsigned)a.n_raw);
     const unsigned red_off = (unsigned)a.off_red + (unsigned)(warp - 1) * (unsigned)a.red_bytes;
 
@@ -838,8 +893,15 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         CT* ar = acc;
         CT* ai = acc + KC;
         bool first = true;
+        // ring position of the item's slabs (interleaved within groups of n_cons items: see ItemWalker)
+        int idx0 = item * a.nslab, idx_step = 1;
+        if (WP == 1 && a.nslab > 1 && a.interleave) {   // packed windows are single-slab by construction
+            const int gstart = item / a.n_cons * a.n_cons;
+            idx_step = min(a.n_cons, n_items - gstart);
+            idx0 = gstart * a.nslab + (item - gstart);
+        }
         for (int sl = 0; sl < a.nslab; ++sl) {
-            const int idx = item * a.nslab + sl;
+            const int idx = idx0 + sl * idx_step;
             unsigned st_u;
             const int use = (int)by_nstage.div((unsigned)idx, &st_u);
             const int st = (int)st_u;
@@ -931,8 +993,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         bm.locate(t, &g, &slot, &bsz, &first_t);
         const int gb = a.group_major ? g * a.n_frames + f : f * bm.nb + g;   // batch id over the whole launch, in ticket order
         unsigned rb_u;
-        if constexpr (KC >= 24) rb_u = (unsigned)gb % (unsigned)a.n_raw;   // the 24-bin kernels have no register to spare for the magic number
-        else by_nraw.div((unsigned)gb, &rb_u);
+        by_nraw.div((unsigned)gb, &rb_u);
         const int rb = (int)rb_u;
         if (lane == 0) {
             while (ld_volatile_s32(&ctrl->raw_owner[rb]) != gb) __nanosleep(64);
