@@ -387,21 +387,32 @@ def stream_legs(B, est, cfg, n_inst, n_ch, tdt, npdt, win_all, args):
         tickets.append(est.stream_push(blocks[i % 2], None, out=d_out, asynchronous=True)[1])
     torch.cuda.synchronize()
     n_push = max(10, min(args.steps, 100))
+    ms_ingest = B.timed_launches(lambda i: est.stream_push(blocks[i % 2], None, out=d_out, asynchronous=True), n_push)
+    est.sync()
+    v_ingest = world * n_est_frame * F * n_push / (ms_ingest * 1e-3)
+    # ... and with the samples already IN the rings (a device-side producer writes them there itself,
+    # pmub_stream_ring_info + PMUB_PUSH_IN_PLACE): the estimator launch is the only kernel
+    for i in range(3):
+        est.stream_advance(F, d_out)
+    torch.cuda.synchronize()
     launches0 = est.launches
-    ms = B.timed_launches(lambda i: est.stream_push(blocks[i % 2], None, out=d_out, asynchronous=True), n_push)
+    ms = B.timed_launches(lambda i: est.stream_advance(F, d_out), n_push)
     est.sync()
     v = world * n_est_frame * F * n_push / (ms * 1e-3)
     s = itemsize
     alg = hop * s + 4 * s + 2 * (3 * s + 1)                  # new samples in, frame out, ROCOF state in and out
-    moved = N * s + 2 * hop * s + 4 * s + 2 * (3 * s + 1)    # what this implementation moves: whole window from the ring + ingest
+    moved = N * s + 4 * s + 2 * (3 * s + 1)                  # what the estimator launch requests: the whole window from its ring
     traffic = measured_traffic("stream_device_config3_f64") if (N, F, itemsize) == (2048, 8, 8) else None
     stream_device = dict(value=v, unit=UNIT, frames_per_push=F, pushes=n_push, ms_per_push=ms / n_push,
                          gpu_launches=int(est.launches - launches0),
+                         with_ingest=dict(value=v_ingest, unit=UNIT, ms_per_push=ms_ingest / n_push,
+                                          note="the same pushes with the new samples handed over as a device block and "
+                                               "scattered into the rings by the ingest kernel (+ 2 x hop x 8 B per estimate)"),
                          roofline=dict(bound="hbm", algorithmic_bytes_per_estimate=alg, frac=v / world * alg / 1e9 / B.peak,
                                        requested_bytes_per_estimate=moved, frac_of_bytes_requested=v / world * moved / 1e9 / B.peak,
                                        traffic=traffic, traffic_bytes_per_estimate=(traffic / (n_est_frame * F) if traffic else None),
                                        peak=B.peak, unit="GB/s"),
-                         note="sample rings and the new samples resident in HBM.  The estimator requests each whole window from "
+                         note="sample rings resident in HBM, the new samples already in them.  The estimator requests each whole window from "
                               "its ring, but a streaming launch walks its items group-major (the F consecutive windows of a "
                               "group of 32 streams back to back), so the win_len - hop samples that consecutive windows share "
                               "are re-read from L2: `traffic` is the DRAM traffic of the estimator launch measured by ncu "

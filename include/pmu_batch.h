@@ -150,10 +150,16 @@ int pmub_stream_push(pmub_batch *b, int n_frames, const void *new_samples, const
 #define PMUB_SAMPLES_F32 1
 #define PMUB_SAMPLES_I16 2
 #define PMUB_PUSH_ASYNC 1u
+/* PMUB_PUSH_IN_PLACE: `samples` is ignored (may be NULL) - device code of the caller has already written the n_frames * hop
+ * new samples of every stream into the rings, starting at the write position pmub_stream_ring_info reports (ring of stream
+ * w = base + w * cap_samples, in float_p; positions wrap at cap_samples).  No ingest pass at all: the estimator launch is
+ * the only kernel. */
+#define PMUB_PUSH_IN_PLACE 2u
 int pmub_stream_set_scale(pmub_batch *b, const double *scale);
 int pmub_stream_push_ex(pmub_batch *b, int n_frames, const void *samples, int sample_format,
                         const void *mid_fracsec, void *frames, unsigned flags, unsigned long long *ticket);
 int pmub_stream_wait(pmub_batch *b, unsigned long long ticket);
+int pmub_stream_ring_info(pmub_batch *b, void **base, long long *cap_samples, long long *write_pos);
 int pmub_sync(pmub_batch *b);
 /* Run on the caller's CUDA stream (cudaStream_t passed as void*); NULL = own stream. */
 int pmub_set_stream(pmub_batch *b, void *cuda_stream);

@@ -24,6 +24,7 @@ CSRC = PKG / "csrc"
 PMUB_F32, PMUB_F64 = 4, 8
 SAMPLES_NATIVE, SAMPLES_F32, SAMPLES_I16 = 0, 1, 2   # pmub_stream_push_ex sample formats
 PUSH_ASYNC = 1
+PUSH_IN_PLACE = 2
 
 
 class CoreConfig(C.Structure):
@@ -143,6 +144,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.pmub_stream_push_ex.argtypes = [vp, ip, vp, ip, vp, vp, C.c_uint, C.POINTER(C.c_ulonglong)]
     lib.pmub_stream_set_scale.argtypes = [vp, vp]
     lib.pmub_stream_wait.argtypes = [vp, C.c_ulonglong]
+    lib.pmub_stream_ring_info.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    lib.pmub_stream_ring_info.restype = ip
     lib.pmub_sync.argtypes = [vp]
     lib.pmub_set_stream.argtypes = [vp, vp]
     lib.pmub_launch_count.argtypes = [vp]
@@ -412,6 +415,24 @@ class BatchEstimator:
             self._keepalive = (getattr(self, "_keepalive", None) or [])[-3:] + [(new_samples, mid_fracsec, out)]
             return out, int(ticket.value)
         return out
+
+    def stream_ring_info(self):
+        """-> (device address of the rings, samples per stream ring, next write position): for device-side producers that
+        write the new samples into the rings themselves and then call :meth:`stream_advance`."""
+        base, cap, pos = C.c_void_p(), C.c_longlong(), C.c_longlong()
+        self._check(self.lib.pmub_stream_ring_info(self._h, C.byref(base), C.byref(cap), C.byref(pos)), "pmub_stream_ring_info")
+        return int(base.value), int(cap.value), int(pos.value)
+
+    def stream_advance(self, n_frames: int, out, mid_fracsec=None, asynchronous: bool = True):
+        """``n_frames`` more frames from samples the caller's device code already wrote into the rings
+        (``PMUB_PUSH_IN_PLACE``): no ingest pass, the estimator launch is the only kernel."""
+        out, mid_fracsec = _ingest(out), _ingest(mid_fracsec)
+        ticket = C.c_ulonglong(0)
+        flags = PUSH_IN_PLACE | (PUSH_ASYNC if asynchronous else 0)
+        self._check(self.lib.pmub_stream_push_ex(self._h, int(n_frames), None, SAMPLES_NATIVE,
+                                                 _ptr(mid_fracsec) if mid_fracsec is not None else None, _ptr(out), flags,
+                                                 C.byref(ticket)), "pmub_stream_push_ex")
+        return int(ticket.value)
 
     def stream_wait(self, ticket: int) -> None:
         """Block until the asynchronous push that returned ``ticket`` has delivered its frames."""

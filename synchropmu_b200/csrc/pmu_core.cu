@@ -796,11 +796,12 @@ int pmub_stream_push_ex(pmub_batch* b, int n_frames, const void* samples, int sa
 {
     if (!b || !b->d_ring) { set_error("[pmu_stream] ERROR: call pmub_stream_begin first"); return -1; }
     const size_t esz = b ? sample_bytes(b, sample_format) : 0;
-    if (!samples || !frames || n_frames < 1 || n_frames > b->stream_max_frames || esz == 0) {
+    const bool in_place = (flags & PMUB_PUSH_IN_PLACE) != 0;   // the caller's device code already wrote the samples into the rings
+    if ((!samples && !in_place) || !frames || n_frames < 1 || n_frames > b->stream_max_frames || esz == 0) {
         set_error("[pmu_stream] ERROR: bad argument (n_frames must be 1..max_frames_per_push, sample_format one of PMUB_SAMPLES_*)");
         return -1;
     }
-    if (sample_format == PMUB_SAMPLES_NATIVE && !(flags & PMUB_PUSH_ASYNC)) {
+    if (sample_format == PMUB_SAMPLES_NATIVE && !(flags & (PMUB_PUSH_ASYNC | PMUB_PUSH_IN_PLACE))) {
         if (ticket) *ticket = b->push_no;
         return pmub_stream_push(b, n_frames, samples, mid, frames);
     }
@@ -810,7 +811,7 @@ int pmub_stream_push_ex(pmub_batch* b, int n_frames, const void* samples, int sa
     const long long cap = b->ring_cap, hop = b->hop, N = b->d.N;
     const size_t mid_bytes = (size_t)b->n_inst * sz, fr_bytes = n * 4 * sz;   // per frame
     const size_t in_bytes = n * (size_t)hop * esz * n_frames;
-    const bool in_dev = is_device_ptr(samples), mid_dev = mid ? is_device_ptr(mid) : true, fr_dev = is_device_ptr(frames);
+    const bool in_dev = in_place || is_device_ptr(samples), mid_dev = mid ? is_device_ptr(mid) : true, fr_dev = is_device_ptr(frames);
     if (mid && !mid_dev && ensure_cap(&b->d_mid, &b->d_mid_cap, mid_bytes * n_frames)) return -1;
     if (!fr_dev && ensure_cap(&b->d_frames, &b->d_frames_cap, fr_bytes * n_frames)) return -1;
     const int slot = (int)(b->push_no & 1);
@@ -849,7 +850,7 @@ int pmub_stream_push_ex(pmub_batch* b, int n_frames, const void* samples, int sa
         }
     }
     unsigned char* dF = fr_dev ? (unsigned char*)frames : b->d_frames;
-    switch (sample_format) {
+    if (!in_place) switch (sample_format) {
         case PMUB_SAMPLES_NATIVE:
             if (sz == 8) CUDA_OK(launch_scatter<double>(b, src, nullptr, 0, (long long)n, n_frames, s_comp));
             else CUDA_OK(launch_scatter<float>(b, src, nullptr, 0, (long long)n, n_frames, s_comp));
@@ -873,6 +874,17 @@ int pmub_stream_push_ex(pmub_batch* b, int n_frames, const void* samples, int sa
     b->ring_wpos = (b->ring_wpos + (long long)n_frames * hop) % cap;
     b->stream_pushed += (unsigned long long)n_frames * (unsigned long long)hop;
     if (!(flags & PMUB_PUSH_ASYNC)) CUDA_OK(cudaEventSynchronize(b->ev_done[dslot]));
+    return 0;
+}
+
+// Where a device-side producer writes the next samples itself (PMUB_PUSH_IN_PLACE): ring base, samples per stream ring,
+// and the position (in samples, < cap) the next hop of every stream goes to; a block that crosses the end wraps to 0.
+int pmub_stream_ring_info(pmub_batch* b, void** base, long long* cap_samples, long long* write_pos)
+{
+    if (!b || !b->d_ring) { set_error("[pmu_stream] ERROR: call pmub_stream_begin first"); return -1; }
+    if (base) *base = b->d_ring;
+    if (cap_samples) *cap_samples = b->ring_cap;
+    if (write_pos) *write_pos = b->ring_wpos;
     return 0;
 }
 

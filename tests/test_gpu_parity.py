@@ -683,6 +683,43 @@ def test_stream_push_explicit_odd_hop_that_does_not_divide_the_window():
     assert np.array_equal(got, want)
 
 
+def test_stream_in_place_ring_writes_equal_pushes():
+    """A device-side producer writes the new samples straight into the rings (pmub_stream_ring_info) and calls
+    stream_advance (PMUB_PUSH_IN_PLACE, no ingest kernel): same frames as handing the same samples to stream_push."""
+    torch = pytest.importorskip("torch")
+
+    class Ring:     # a torch view of the library's rings through __cuda_array_interface__
+        def __init__(self, ptr, n, cap):
+            self.__cuda_array_interface__ = dict(shape=(n, cap), typestr="<f8", data=(ptr, False), version=3)
+
+    cfg = configs.DEFAULT_INI
+    n_inst, C_, F = 13, 6, 3
+    n = n_inst * C_
+    N, hop = configs.win_len(cfg), configs.hop(cfg)
+    pushes = 6                                   # 18 frames: the ring (N + 2 hops) wraps several times
+    x = _long_streams(cfg, n, N + pushes * F * hop, seed=21)
+    with BatchEstimator(cfg, n_inst, C_) as a, BatchEstimator(cfg, n_inst, C_) as b:
+        hist = x[:, :N - hop].reshape(n_inst, C_, N - hop)
+        a.stream_begin(hop=0, max_frames_per_push=F, history=hist)
+        b.stream_begin(hop=0, max_frames_per_push=F, history=hist)
+        base, cap, _ = b.stream_ring_info()
+        ring = torch.as_tensor(Ring(base, n, cap), device="cuda")
+        xd = torch.as_tensor(x, device="cuda")
+        out = torch.empty((F, n_inst, C_, 4), dtype=torch.float64, device="cuda")
+        for p in range(pushes):
+            lo = N - hop + p * F * hop
+            blk = np.stack([x[:, lo + f * hop:lo + (f + 1) * hop].reshape(n_inst, C_, hop) for f in range(F)])
+            want = a.stream_push(blk)
+            _, _, wpos = b.stream_ring_info()
+            idx = (wpos + torch.arange(F * hop, device="cuda")) % cap
+            ring[:, idx] = xd[:, lo:lo + F * hop]
+            torch.cuda.synchronize()
+            b.stream_wait(b.stream_advance(F, out))
+            got = out.cpu().numpy()
+            assert np.array_equal(got[..., [0, 2, 3]], want[..., [0, 2, 3]])
+            assert np.max(np.abs(got[..., 1] - want[..., 1])) < 1e-11
+
+
 @pytest.mark.parametrize("fmt", ["i16", "f32", "native_async"])
 def test_stream_push_narrow_formats_and_async_pushes_equal_explicit_windows(fmt):
     """pmub_stream_push_ex: int16 ADC counts (x per-stream scale) and float samples are promoted on the device, exactly,
