@@ -580,6 +580,7 @@ def test_warp_per_window_path_equals_batched_path(cfgname, dtype):
     ("dropin_single.c", ["-DPMU_FLOAT_P=float"], "pmu_estimator_f32"),
     ("batch_from_ini.c", ["-DNUM_CHANLS=6"], "pmu_estimator_c6"),
     ("stream_from_ini.c", [], "pmu_estimator"),
+    ("stream_adc_i16.c", [], "pmu_estimator"),
 ])
 def test_c_examples_build_and_run(tmp_path, src, defs, lib):
     import re
@@ -599,7 +600,9 @@ def test_c_examples_build_and_run(tmp_path, src, defs, lib):
         amp, ph, freq, rocof = map(float, m.groups())
         assert abs(amp - 2.0) < 1e-5 and abs(ph - 1.0) < 1e-5 and abs(freq - 50.0) < 1e-4 and abs(rocof) < 1e-3
         assert "already initialized" in r.stderr and "not initialized" in r.stderr
-    elif src == "stream_from_ini.c":
+    elif src in ("stream_from_ini.c", "stream_adc_i16.c"):
+        if src == "stream_adc_i16.c":
+            assert "CFG-2 114 bytes, data frames 34 bytes each" in r.stdout and "SYNC aa01" in r.stdout, r.stdout
         m = re.search(r"instance 0 frequency after 50 frames: ([\d.]+) Hz .* ROCOF ([-\d.]+) Hz/s", r.stdout)
         assert abs(float(m.group(1)) - 50.004) < 0.01 and abs(float(m.group(2)) - 0.2) < 0.02, r.stdout
     else:
