@@ -39,6 +39,9 @@ CASES = {
     "pc": ("p_class_config.ini", np.float64, 8192, 8, ()),
     "q22_trig": ("test_c_q22", np.float64, 4096, 4, TRIG),
     "t2": ("test2_16cyc", np.float64, 1024, 4, ()),
+    "mc_1f": ("m_class_config.ini", np.float64, 4096, 1, ()),
+    "c3_trig_1f": ("config.ini", np.float64, 4096, 1, TRIG),
+    "c3_small_1f": ("config.ini", np.float64, 1024, 1, ()),
     "pc_f32": ("p_class_config.ini", np.float32, 8192, 8, ()),
     "c5_f32": ("cfg5_600", np.float32, 21846, 8, ()),
 }
