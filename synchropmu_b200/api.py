@@ -113,6 +113,29 @@ def build_library(verbose: bool = False) -> None:
                    stdout=None if verbose else subprocess.DEVNULL)
 
 
+class _Missing:
+    """Stands in for an entry point an older build of the library does not export (A/B runs against earlier builds):
+    prototypes can be declared on it, calling it fails loudly."""
+
+    def __init__(self, name):
+        self._name = name
+
+    def __call__(self, *a, **k):
+        raise AttributeError(f"this build of libpmu_estimator does not export {self._name}")
+
+
+class _TolerantCDLL(C.CDLL):
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            if name.startswith("pmub_"):
+                m = _Missing(name)
+                setattr(self, name, m)
+                return m
+            raise
+
+
 _LIB = None
 
 
@@ -126,7 +149,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
         raise FileNotFoundError(
             f"{p} not built - run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU fallback for the estimator)")
-    lib = C.CDLL(str(p))
+    lib = _TolerantCDLL(str(p))
     vp, ip = C.c_void_p, C.c_int
     lib.pmub_last_error.restype = C.c_char_p
     lib.pmub_validate.argtypes = [C.POINTER(CoreConfig)]
