@@ -317,6 +317,39 @@ def test_batched_fft_r_matches_the_reference_plug_point(cfgname, dtype):
         assert np.array_equal(again, want_again)
 
 
+@pytest.mark.parametrize("Q", [3, 13])
+def test_reference_test2_sweep_point_16384_samples_matches_oracle(Q):
+    """The reference's own wall-time sweep (test/test2.c:62-76) at fs = 51.2 kHz, n_cycles = 16: 16384-sample windows,
+    18 bins - 8 slabs per window on the 24-bin kernel, whose ring positions are interleaved across the consumer warps.
+    Signal as in test2.c (51 Hz + 10 % 75 Hz, three phases), batched path (240 windows, a count that leaves the last
+    interleave group short), three frames sequentially and in one multi-frame launch, and through the streaming front end."""
+    cfg = dict(configs.NAMED["test2_16cyc"], Q=Q)
+    n_inst, T = 40, 3
+    N, hop = configs.win_len(cfg), configs.hop(cfg)
+    t = np.arange(N + (T - 1) * hop) / cfg["fs"]
+    rng = np.random.default_rng(Q)
+    ph = rng.uniform(-3, 3, (n_inst, 1)) + np.array([0, 2 * np.pi / 3, 4 * np.pi / 3, 0.3, 2 * np.pi / 3 + 0.3, 4 * np.pi / 3 + 0.3])
+    ph = ph.reshape(-1, 1)
+    f = 51.0 + rng.uniform(-0.3, 0.3, (n_inst, 1)).repeat(6, axis=1).reshape(-1, 1)
+    x = 2.0 * np.cos(2 * np.pi * f * t + ph) + 0.2 * np.cos(2 * np.pi * 75.0 * t + ph)
+    win = np.stack([x[:, k * hop:k * hop + N].reshape(n_inst, 6, N) for k in range(T)])
+    mid = np.array([[signals.mid_fracsec(cfg, k)] * n_inst for k in range(T)])
+    want, km_want, _ = checker(np.float64, 6).run(cfg, win, mid, n_threads=0)
+    with BatchEstimator(cfg, n_inst, 6) as seq, BatchEstimator(cfg, n_inst, 6) as multi, BatchEstimator(cfg, n_inst, 6) as stream:
+        assert seq.info.slabs_per_window == 8 and seq.info.dft_bins == 24
+        seq.set_debug(True)
+        got = np.zeros_like(want)
+        for k in range(T):
+            got[k] = seq.estimate(win[k], mid[k])
+            # the 6-channel reference build exposes the spectrum of the last channel only
+            assert np.array_equal(seq.get_debug()[0][:, 5], km_want[k][:, 5])
+        assert_frames_close(got, want, "f64", f"test2 point Q={Q}")
+        assert np.array_equal(multi.estimate_frames(win, mid), got)
+        stream.stream_begin(hop=0, max_frames_per_push=T, history=x[:, :N - hop].reshape(n_inst, 6, N - hop))
+        blk = np.stack([x[:, N - hop + k * hop:N + k * hop].reshape(n_inst, 6, hop) for k in range(T)])
+        assert np.array_equal(stream.stream_push(blk, mid), got)
+
+
 def test_rocof_state_checkpoint_resume_and_reset():
     cfg = configs.DEFAULT_INI
     n_inst, T = 12, 6
@@ -1234,7 +1267,7 @@ STRESS_VARIANTS = {
     "no_window_packing": dict(PMU_PACK="1"),
 }
 STRESS_SELECT = ("three_phase or multi_frame or stream_push or golden or config2 or config4 or odd_window or "
-                 "device_and_host or long_stream or hostile")
+                 "device_and_host or long_stream or hostile or test2_sweep_point or in_place")
 
 
 @pytest.mark.skipif(bool(__import__("os").environ.get("PMU_STRESS_CHILD")), reason="already inside a stress child")
