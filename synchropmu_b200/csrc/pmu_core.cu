@@ -188,6 +188,7 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     a.warp_per_window = (a.n_windows <= wpw_max && a.n_windows <= PMU_MAX_GROUPS && b->cfg.n_bins <= PMU_WARP) ? 1 : 0;
     if (a.warp_per_window && b->plan.wp > 1) {   // the unpacked instantiation of the same plan
         a.wp = 1;
+        a.pk = 1;
         a.U = b->dU1;
         a.n_u = b->n_u1;
     }
@@ -436,6 +437,7 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
         // small launches run one window per warp (lane = bin estimator): same plan, twiddles for 32 lanes per window
         pmu::Plan p1 = b->plan;
         p1.wp = 1;
+        p1.pk = 1;
         p1.n_u = ((p1.L + 31) / 32) * p1.KC;
         std::vector<pmu_c> U1, V1, T1;
         pmu::build_tables(p1, b->d.N, &U1, &V1, &T1);
@@ -489,7 +491,7 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     pp.lp0 = d.lp[0]; pp.lp1 = d.lp[1]; pp.lp2 = d.lp[2];
     pp.trig = b->dT;
     pp.trig_off = (unsigned)b->plan.off_trig;
-    a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.pitch = b->plan.pitch; a.wp = b->plan.wp; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
+    a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.pitch = b->plan.pitch; a.wp = b->plan.wp; a.pk = b->plan.pk; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
     a.n_stage = b->plan.n_stage; a.stage_bytes = b->plan.stage_bytes; a.n_cons = b->plan.n_cons;
     a.n_raw = b->plan.n_raw; a.raw_stride = b->plan.raw_stride; a.red_bytes = b->plan.red_bytes;
     a.n_u = b->plan.n_u;

@@ -28,9 +28,80 @@
 struct pmu_cf {
     float x, y;
 };
+
+// Two FP32 values that travel together through Blackwell's packed FP32 pipe (FADD2 / FMUL2 / FFMA2, sm_100): the float
+// build transforms TWO windows per lane, the same residue of both in one instruction stream, so its DFT stage issues
+// half the instructions of the scalar FP32 version.  Twiddles stay scalar (the hardware broadcasts a 32-bit operand to
+// both halves, negations fold into operand modifiers).  Each half is rounded exactly like the scalar operation.
+struct F2 {
+    float lo, hi;
+    PMU_HD F2() {}
+    PMU_HD F2(float a, float b) : lo(a), hi(b) {}
+    PMU_HD explicit F2(float a) : lo(a), hi(a) {}
+    PMU_HD explicit F2(double a) : lo((float)a), hi((float)a) {}
+    PMU_HD explicit F2(int a) : lo((float)a), hi((float)a) {}
+};
+#if defined(__CUDA_ARCH__)
+#define PMU_F2(v) make_float2((v).lo, (v).hi)
+PMU_HD F2 pmu_f2(float2 v) { return F2(v.x, v.y); }
+PMU_HD F2 operator+(F2 a, F2 b) { return pmu_f2(__fadd2_rn(PMU_F2(a), PMU_F2(b))); }
+PMU_HD F2 operator-(F2 a, F2 b) { return pmu_f2(__fadd2_rn(PMU_F2(a), make_float2(-b.lo, -b.hi))); }
+PMU_HD F2 operator*(F2 a, F2 b) { return pmu_f2(__fmul2_rn(PMU_F2(a), PMU_F2(b))); }
+PMU_HD F2 operator*(float w, F2 b) { return pmu_f2(__fmul2_rn(make_float2(w, w), PMU_F2(b))); }
+PMU_HD F2 pmu_fma(float w, F2 b, F2 c) { return pmu_f2(__ffma2_rn(make_float2(w, w), PMU_F2(b), PMU_F2(c))); }
+PMU_HD F2 pmu_fma(F2 a, F2 b, F2 c) { return pmu_f2(__ffma2_rn(PMU_F2(a), PMU_F2(b), PMU_F2(c))); }
+#else
+PMU_HD F2 operator+(F2 a, F2 b) { return F2(a.lo + b.lo, a.hi + b.hi); }
+PMU_HD F2 operator-(F2 a, F2 b) { return F2(a.lo - b.lo, a.hi - b.hi); }
+PMU_HD F2 operator*(F2 a, F2 b) { return F2(a.lo * b.lo, a.hi * b.hi); }
+PMU_HD F2 operator*(float w, F2 b) { return F2(w * b.lo, w * b.hi); }
+PMU_HD F2 pmu_fma(float w, F2 b, F2 c) { return F2(fmaf(w, b.lo, c.lo), fmaf(w, b.hi, c.hi)); }
+PMU_HD F2 pmu_fma(F2 a, F2 b, F2 c) { return F2(fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)); }
+#endif
+PMU_HD F2 operator-(F2 a) { return F2(-a.lo, -a.hi); }
+PMU_HD F2& operator+=(F2& a, F2 b) { a = a + b; return a; }
+
 template <typename R> struct CplxOf;
 template <> struct CplxOf<double> { typedef pmu_c type; };
 template <> struct CplxOf<float> { typedef pmu_cf type; };
+template <> struct CplxOf<F2> { typedef pmu_cf type; };          // scalar twiddles, broadcast by the hardware
+template <typename R> struct ScalarOf { typedef R type; };      // type of a twiddle component
+template <> struct ScalarOf<F2> { typedef float type; };
+template <typename R> struct IsPacked { static constexpr bool value = false; };
+template <> struct IsPacked<F2> { static constexpr bool value = true; };
+template <typename R> struct alignas(2 * sizeof(R)) RPair { R x, y; };   // one complex partial in the reduction scratch
+PMU_HD double ct_to_double(double v) { return v; }
+PMU_HD double ct_to_double(float v) { return (double)v; }
+PMU_HD double ct_to_double(F2 v) { return (double)v.lo; }   // (only instantiated, never reached, for packed kernels)
+template <typename R> struct IsDouble { static constexpr bool value = false; };
+template <> struct IsDouble<double> { static constexpr bool value = true; };
+
+// w_re * y_re - w_im * y_im, w_re * y_im + w_im * y_re and their accumulating forms.  The scalar versions are the plain
+// expressions (the compiler contracts them as it always did); the packed versions spell out the FFMA2s.
+template <typename S, typename R> PMU_HD R cmul_re(S wr, S wi, R yr, R yi) { return wr * yr - wi * yi; }
+template <typename S, typename R> PMU_HD R cmul_im(S wr, S wi, R yr, R yi) { return wr * yi + wi * yr; }
+template <typename S, typename R> PMU_HD void cmac(R& ar, R& ai, S wr, S wi, R yr, R yi)
+{
+    ar += wr * yr - wi * yi;
+    ai += wr * yi + wi * yr;
+}
+template <typename S, typename R> PMU_HD void rmac(R& ar, R& ai, S wr, S wi, R yr)   // y real
+{
+    ar += wr * yr;
+    ai += wi * yr;
+}
+PMU_HD F2 cmul_re(float wr, float wi, F2 yr, F2 yi) { return pmu_fma(wr, yr, -(wi * yi)); }
+PMU_HD F2 cmul_im(float wr, float wi, F2 yr, F2 yi) { return pmu_fma(wr, yi, wi * yr); }
+PMU_HD void cmac(F2& ar, F2& ai, float wr, float wi, F2 yr, F2 yi)
+{
+    ar = pmu_fma(-wi, yi, pmu_fma(wr, yr, ar));
+    ai = pmu_fma(wi, yr, pmu_fma(wr, yi, ai));
+}
+PMU_HD void rmac(F2& ar, F2& ai, float wr, float wi, F2 yr)
+{
+    ar = pmu_fma(wr, yr, ar);
+    ai = pmu_fma(wi, yr, ai);
+}
 
 // ---- compile-time loop ---------------------------------------------------------
 template <int I>
@@ -75,7 +146,7 @@ PMU_HD R cosv16()
 {
     constexpr int k = K16 & 15;
 #if defined(__CUDA_ARCH__)
-    if constexpr (sizeof(R) == 8) {
+    if constexpr (IsDouble<R>::value) {
         if constexpr (k == 1 || k == 15) return pmu_tw16[0];
         else if constexpr (k == 2 || k == 14) return pmu_tw16[1];
         else if constexpr (k == 3 || k == 13) return pmu_tw16[2];
@@ -103,9 +174,10 @@ PMU_HD void tw_mul(R orr, R oi, R* tr, R* ti)
     else if constexpr (k16 == 8) { *tr = -orr; *ti = -oi; }       // -1
     else if constexpr (k16 == 12) { *tr = -oi; *ti = orr; }       // +i
     else {
-        const R wr = cosv16<k16, R>(), wi = -sinv16<k16, R>();
-        *tr = wr * orr - wi * oi;
-        *ti = wr * oi + wi * orr;
+        typedef typename ScalarOf<R>::type S;
+        const S wr = cosv16<k16, S>(), wi = -sinv16<k16, S>();
+        *tr = cmul_re(wr, wi, orr, oi);
+        *ti = cmul_im(wr, wi, orr, oi);
     }
 }
 
@@ -117,10 +189,10 @@ struct RFFT {
     PMU_HD static void run(const R* x, R* re, R* im)
     {
         if constexpr (M == 1) {
-            re[0] = x[0]; im[0] = 0;
+            re[0] = x[0]; im[0] = (R)0;
         } else if constexpr (M == 2) {
-            re[0] = x[0] + x[1]; im[0] = 0;
-            re[1] = x[0] - x[1]; im[1] = 0;
+            re[0] = x[0] + x[1]; im[0] = (R)0;
+            re[1] = x[0] - x[1]; im[1] = (R)0;
         } else {
             constexpr int H = M / 2;
             R ev[H], od[H];
@@ -133,8 +205,8 @@ struct RFFT {
             RFFT<H, R>::run(od, qr, qi);
             // X[k] = E[k] + W^k O[k] and X[H-k] = conj(E[k] - W^k O[k]) share the twiddle product; E[0], E[H/2],
             // O[0], O[H/2] are real by symmetry
-            re[0] = er[0] + qr[0]; im[0] = 0;
-            re[H] = er[0] - qr[0]; im[H] = 0;
+            re[0] = er[0] + qr[0]; im[0] = (R)0;
+            re[H] = er[0] - qr[0]; im[H] = (R)0;
             re[H / 2] = er[H / 2]; im[H / 2] = -qr[H / 2];          // W^(H/2) = -i
             static_for<1, H / 2>([&](auto kc) {
                 constexpr int k = kc.value;
@@ -183,13 +255,8 @@ PMU_HD void accumulate_residue(const R* x, const typename CplxOf<R>::type* u, R*
             ar[0] += yr;  // W^0 = 1, Y[0] real
         } else {
             const typename CplxOf<R>::type w = u[k];
-            if constexpr (is_real) {
-                ar[k] += w.x * yr;
-                ai[k] += w.y * yr;
-            } else {
-                ar[k] += w.x * yr - w.y * yi;
-                ai[k] += w.x * yi + w.y * yr;
-            }
+            if constexpr (is_real) rmac(ar[k], ai[k], w.x, w.y, yr);
+            else cmac(ar[k], ai[k], w.x, w.y, yr, yi);
         }
     });
 }
@@ -201,8 +268,8 @@ PMU_HD void rotate_lane(const typename CplxOf<R>::type* v, int v_stride, R* ar, 
     static_for<1, KC>([&](auto kc) {
         constexpr int k = kc.value;
         const typename CplxOf<R>::type w = v[k * v_stride];
-        R r = ar[k] * w.x - ai[k] * w.y;
-        R i = ar[k] * w.y + ai[k] * w.x;
+        R r = cmul_re(w.x, w.y, ar[k], ai[k]);
+        R i = cmul_im(w.x, w.y, ar[k], ai[k]);
         ar[k] = r;
         ai[k] = i;
     });

@@ -337,7 +337,9 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
         p.wp = 2;   // 1024-sample windows, and 2048-sample windows of the float build
         p.stage_bytes = align_up(p.wp * N * s, 128);
     }
-    const int lanes_per_window = 32 / p.wp;
+    // float build with several windows per pass: two windows per lane on the packed FP32 pipe (FADD2 / FMUL2 / FFMA2)
+    p.pk = (s == 4 && p.wp >= 2 && env_int("PMU_F32X2", 1)) ? 2 : 1;
+    const int lanes_per_window = 32 * p.pk / p.wp;
     // TMA bulk copies: whole window when its rows are already contiguous at the stage pitch,
     // otherwise one copy per row; both need 16-byte granularity
     const bool whole = (p.nslab == 1 && p.pitch == p.L);
@@ -357,7 +359,7 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
     // 128-bit stores of a quarter warp hit distinct banks
     p.red_stride = 2 * p.KC + 2;  // compile-time in the kernel (immediate LDS offsets)
     // ... and the same region holds the estimator's residual spectrum W[K][32] while the warp posts a batch
-    const int dft_elem = (s == 4) ? 4 : 8;   // the float build reduces float partials
+    const int dft_elem = (s == 4 && p.pk == 1) ? 4 : 8;   // the float build reduces float partials (pairs of them when packed)
     p.red_bytes = align_up(32 * p.red_stride * dft_elem, 128);
     if (p.red_bytes < K * 32 * 16) p.red_bytes = K * 32 * 16;
 
@@ -459,7 +461,7 @@ void build_tables(const Plan& p, unsigned N, std::vector<pmu_c>* U, std::vector<
     if (p.M != 0) U->resize((size_t)p.n_u);
     for (int g = 0; g < n_groups; ++g)
         for (int k = 0; k < p.KC; ++k)
-            (*U)[(size_t)g * p.KC + k] = w((unsigned long long)(32 / p.wp) * (unsigned long long)g * (unsigned long long)k);
+            (*U)[(size_t)g * p.KC + k] = w((unsigned long long)(32 * (p.pk > 1 ? p.pk : 1) / p.wp) * (unsigned long long)g * (unsigned long long)k);
     if (p.M != 0) V->resize((size_t)p.KC * 32);
     for (int k = 0; p.M != 0 && k < p.KC; ++k)
         for (int l = 0; l < 32; ++l) (*V)[(size_t)k * 32 + l] = w((unsigned long long)l * (unsigned long long)k);

@@ -38,6 +38,7 @@ struct Plan {
     int L, W, nslab;    // residues, slab width, slabs per window
     int pitch;          // stage row pitch in elements (PMU_PITCH16 for the 16-point codelet, else W)
     int wp;             // windows per warp pass: 4 for short single-slab windows (8 lanes per window), else 1
+    int pk;             // 2 when the float build packs two windows per lane (FFMA2 pipe): 32 * pk / wp lanes per window
     int Kp;             // n_bins + 1
     int n_stage, stage_bytes;
     int n_cons, n_raw, raw_stride;

@@ -13,9 +13,13 @@
 
 namespace {
 
-template <typename T, int M, int KC, int PITCH, int WP = 1>
+template <typename T, int M, int KC, int PITCH, int WP = 1, typename CT = T>
 int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
 {
+    if constexpr (sizeof(T) == 4 && WP > 1 && !IsPacked<CT>::value) {
+        // float build, several windows per warp pass: two of them per lane on the packed FP32 pipe
+        if (a.pk == 2) return launch_inst<T, M, KC, PITCH, WP, F2>(a, grid, block, smem, s);
+    }
     // per device: has this instantiation been opted in to the device's maximum dynamic shared memory?  The attribute
     // is only ever set to that one value, so concurrent host threads (batches that share an instantiation but differ
     // in smem_bytes) cannot lower it under each other's launches.
@@ -26,7 +30,7 @@ int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t
         int max_optin = smem;
         e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(pmu_fused_kernel<T, T, M, KC, PITCH, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+            e = cudaFuncSetAttribute(pmu_fused_kernel<T, CT, M, KC, PITCH, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
         if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev].store(1, std::memory_order_release);
     }
     if (e == cudaSuccess) {
@@ -44,7 +48,7 @@ int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t
         attr[0].val.programmaticStreamSerializationAllowed = a.pdl ? 1 : 0;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, pmu_fused_kernel<T, T, M, KC, PITCH, WP>, a);
+        e = cudaLaunchKernelEx(&cfg, pmu_fused_kernel<T, CT, M, KC, PITCH, WP>, a);
     }
     if (e != cudaSuccess) {
         pmu::set_error(std::string("[pmu_estimate] CUDA ERROR launching the estimator kernel: ") + cudaGetErrorString(e));

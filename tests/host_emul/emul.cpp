@@ -24,7 +24,7 @@ static void window_bins_r(const pmu::Plan& p, const std::vector<pmu_c>& Ud, cons
     double sum_r[KC], sum_i[KC];
     for (int k = 0; k < KC; ++k) sum_r[k] = sum_i[k] = 0.0;
     const int w_per_it = p.W / 32;
-    const int G = 32 / p.wp;   // lanes per window (8 when four short windows share a warp pass)
+    const int G = 32 * (p.pk > 1 ? p.pk : 1) / p.wp;   // lanes per window (8 when four short windows share a warp pass; twice that when the float build packs two windows per lane)
     for (int lane = 0; lane < G; ++lane) {
         R ar[KC], ai[KC];
         bool first = true;
