@@ -42,3 +42,10 @@ def test_headline_kernels_keep_their_copy_engine_and_barrier_instructions(table)
         assert k["UTCMMA"] == 0 and k["LDTM"] == 0, name
         assert k["DFMA"] > 300, name
     assert table["pmu_fused_kernel<double, double, 16, 12, 96, 1>"]["UTMALDG"] > 0   # cp.async.bulk.tensor
+    # the float build's packed-window kernels run their transform on the packed FP32 pipe
+    for name in ("pmu_fused_kernel<float, F2, 16, 12, 128, 2>", "pmu_fused_kernel<float, F2, 8, 10, 0, 4>"):
+        k = table[name]
+        assert k["FFMA2"] > 20 and k["FADD2"] > 20 and k["FMUL2"] > 0, name
+        assert k["UBLKCP"] > 0 and k["LDL"] == 0 and k["STL"] == 0, name
+    # the lane = bin peak search of small launches is two integer warp reductions
+    assert table["pmu_fused_kernel<double, double, 16, 12, 128, 1>"]["CREDUX"] + table["pmu_fused_kernel<double, double, 16, 12, 128, 1>"]["REDUX"] >= 2

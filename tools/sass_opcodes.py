@@ -12,7 +12,8 @@ from collections import Counter
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-WATCH = ["UTMALDG", "UBLKCP", "SYNCS", "ACQBULK", "LDGSTS", "LDL", "STL", "DFMA", "DMUL", "DADD", "FFMA", "MUFU", "LDS", "STS",
+WATCH = ["UTMALDG", "UBLKCP", "SYNCS", "ACQBULK", "LDGSTS", "LDL", "STL", "DFMA", "DMUL", "DADD", "FFMA", "FFMA2", "FADD2", "FMUL2", "REDUX",
+         "CREDUX", "MUFU", "LDS", "STS",
          "SHFL", "BAR", "ATOMS", "NANOSLEEP", "UTCMMA", "LDTM"]
 
 
