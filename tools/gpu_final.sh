@@ -9,5 +9,5 @@ echo "== ours (driver-like: --steps 20 --warmup 5)"; timeout 900 python bench.py
 echo "== ours (defaults)"; timeout 900 python bench.py > gpurun_out/final_bench_default.json 2> gpurun_out/final_bench_default.err; echo "rc=$?"
 echo "== sweeps"; timeout 900 python tools/r2_sweep.py --tag final > gpurun_out/final_sweeps.jsonl 2>/dev/null; echo "rc=$?"
 SHORT="python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline --no-workloads --no-sustained"
-echo "== ncu launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/final_launches_ncu.csv $SHORT > /dev/null 2>&1; echo "rc=$?"
+echo "== ncu launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/final_launches_ncu.csv $SHORT > /dev/null 2>&1; echo "rc=$?"
 echo "== ncu full"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:pmu_fused -s 4 -c 1 -o /tmp/prof_final -f $SHORT > /dev/null 2>&1; echo "rc=$?"; ncu -i /tmp/prof_final.ncu-rep --page raw --csv > gpurun_out/final_ncu_full_raw.csv 2>/dev/null
