@@ -50,7 +50,21 @@ def load():
     lib.emul_run.restype = C.c_int
     lib.emul_run.argtypes = [C.POINTER(CoreConfig), C.c_int, C.c_int, C.c_long, C.c_long, C.c_void_p,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.emul_plan.restype = C.c_int
+    lib.emul_plan.argtypes = [C.POINTER(CoreConfig), C.c_int, C.c_int, C.c_void_p]
     return lib
+
+
+PLAN_FIELDS = ("M", "KC", "L", "W", "nslab", "pitch", "wp", "pk", "Kp", "n_stage", "stage_bytes", "n_cons", "n_raw", "raw_stride",
+               "red_bytes", "off_raw", "off_red", "off_stage", "smem_bytes", "aligned16")
+
+
+def plan(cfg: dict, dtype=np.float64, max_smem: int = 232448) -> dict | None:
+    """The kernel launch plan make_plan() picks for a configuration (None if it is rejected)."""
+    out = np.zeros(len(PLAN_FIELDS), dtype=np.int32)
+    if load().emul_plan(C.byref(core_config(cfg)), np.dtype(dtype).itemsize, max_smem, out.ctypes.data) != 0:
+        return None
+    return dict(zip(PLAN_FIELDS, (int(v) for v in out)))
 
 
 def run(cfg: dict, windows: np.ndarray, mid: np.ndarray, dtype=np.float64, n_channels: int = 1):

@@ -110,6 +110,20 @@ static void window_bins_m(const pmu::Plan& p, const std::vector<pmu_c>& U, const
 
 extern "C" {
 
+// The launch plan for a configuration, field by field, so that its invariants can be checked without a GPU.
+// out: M, KC, L, W, nslab, pitch, wp, pk, Kp, n_stage, stage_bytes, n_cons, n_raw, raw_stride, red_bytes, off_raw, off_red,
+//      off_stage, smem_bytes, aligned16   (20 ints).  Returns 0 / -1.
+int emul_plan(const pmub_config* cfg, int dtype, int max_smem, int* out)
+{
+    if (pmu::validate(*cfg)) return -1;
+    pmu::Plan p;
+    if (pmu::make_plan(*cfg, dtype, max_smem, &p)) return -1;
+    const int v[20] = {p.M, p.KC, p.L, p.W, p.nslab, p.pitch, p.wp, p.pk, p.Kp, p.n_stage, p.stage_bytes, p.n_cons, p.n_raw,
+                       p.raw_stride, p.red_bytes, p.off_raw, p.off_red, p.off_stage, p.smem_bytes, p.aligned16 ? 1 : 0};
+    for (int i = 0; i < 20; ++i) out[i] = v[i];
+    return 0;
+}
+
 // windows [T][S][N] (dtype), mid [T][S/C] (double), frames [T][S][4] (double),
 // flags [T][S], spectrum [T][S][K][2].  State starts fresh.  Returns 0 / -1.
 int emul_run(const pmub_config* cfg, int dtype, int n_channels, long n_streams, long n_frames, const void* windows,

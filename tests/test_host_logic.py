@@ -387,3 +387,47 @@ def test_random_valid_configurations_on_the_host_emulation(seed):
         ok = ~np.isnan(want[:, :, 0, :]).any(axis=-1)
         assert np.array_equal((flags & 0xFFFF)[ok], km[:, :, 0][ok]), cfg
     assert len(plans) >= 3, plans
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_launch_plan_invariants_on_random_configurations(seed):
+    """What the kernel silently relies on, for every plan make_plan() can produce (both float widths): the shared-memory
+    layout fits and is ordered, every consumer warp's reduction scratch can also hold the estimator's W columns, raw-bin
+    rows are 16-byte entries an odd number apart, packed windows are single-slab, the small-launch rows fit the raw
+    region, a slab fits its stage."""
+    import emul_lib
+    from random_configs import random_valid_configs
+
+    named = [configs.NAMED[k] for k in configs.NAMED]
+    seen = set()
+    for cfg in named + list(random_valid_configs(60, seed)):
+        for dt in (np.float64, np.float32):
+            p = emul_lib.plan(cfg, dt)
+            assert p is not None, cfg
+            s = np.dtype(dt).itemsize
+            N, K = configs.win_len(cfg), cfg["n_bins"]
+            assert p["smem_bytes"] <= 232448 and p["Kp"] == K + 1
+            if p["M"] == 0:                                   # the general kernel has its own layout
+                assert K + 1 > 24 or p["n_cons"] >= 1
+                continue
+            seen.add((p["M"], p["KC"], p["wp"], p["pk"], p["nslab"] > 1))
+            assert p["M"] * p["L"] == N and p["KC"] >= p["Kp"] and p["KC"] in (8, 10, 12, 16, 24)
+            assert p["n_stage"] >= 2 and 1 <= p["n_cons"] <= 7 and 2 <= p["n_raw"] <= 8
+            assert p["off_raw"] % 128 == 0 and p["off_red"] % 128 == 0 and p["off_stage"] % 128 == 0
+            assert p["off_raw"] + p["n_raw"] * 32 * p["raw_stride"] * 8 <= p["off_red"]
+            assert p["off_red"] + p["n_cons"] * p["red_bytes"] <= p["off_stage"]
+            assert p["off_stage"] + p["n_stage"] * p["stage_bytes"] == p["smem_bytes"]
+            # X in place: rows of 16-byte complex entries, an odd number of entries apart, K + 1 entries used
+            assert p["raw_stride"] % 2 == 0 and (p["raw_stride"] // 2) % 2 == 1 and p["raw_stride"] >= 2 * p["Kp"]
+            # the lane-reduction scratch doubles as the estimator's W[K][32] complex columns
+            elem = 4 if (s == 4 and p["pk"] == 1) else 8
+            assert p["red_bytes"] >= 32 * (2 * p["KC"] + 2) * elem and p["red_bytes"] >= K * 32 * 16
+            # small launches use one raw row per consumer warp
+            assert p["n_raw"] * 32 >= p["n_cons"]
+            assert p["wp"] in (1, 2, 4) and p["pk"] in (1, 2) and (p["pk"] == 1 or (s == 4 and p["wp"] >= 2))
+            if p["wp"] > 1:
+                assert p["nslab"] == 1 and p["pitch"] == p["L"] and p["wp"] * N * s <= p["stage_bytes"]
+            else:
+                assert p["M"] * p["pitch"] * s <= p["stage_bytes"] and p["W"] <= p["pitch"]
+            assert p["nslab"] == -(-p["L"] // p["W"])
+    assert len(seen) >= 8, seen
