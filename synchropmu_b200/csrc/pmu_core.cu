@@ -39,7 +39,7 @@ struct pmub_batch {
     // device memory
     pmu_c *dU, *dV, *dT;
     pmu_c* dU1;                 // U for one window per warp pass (small launches of a plan that packs windows)
-    int n_u1;
+    int n_u1, u_per_slab1;
     double *st_fold, *st_dl0, *st_dl1;
     unsigned char* st_state;
     unsigned char* d_windows;   // staging for host inputs (lazy, grows with the frame count)
@@ -188,9 +188,9 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     a.warp_per_window = (a.n_windows <= wpw_max && a.n_windows <= PMU_MAX_GROUPS && b->cfg.n_bins <= PMU_WARP) ? 1 : 0;
     if (a.warp_per_window && b->plan.wp > 1) {   // the unpacked instantiation of the same plan
         a.wp = 1;
-        a.pk = 1;
         a.U = b->dU1;
         a.n_u = b->n_u1;
+        a.u_per_slab = b->u_per_slab1;
     }
     // TMA bulk copies need 16-byte aligned sources; otherwise per-element cp.async
     bool ok16 = b->plan.aligned16 && (((uintptr_t)a.windows) % 16 == 0);
@@ -437,11 +437,12 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
         // small launches run one window per warp (lane = bin estimator): same plan, twiddles for 32 lanes per window
         pmu::Plan p1 = b->plan;
         p1.wp = 1;
-        p1.pk = 1;
-        p1.n_u = ((p1.L + 31) / 32) * p1.KC;
+        p1.u_per_slab = (p1.W + 32 * p1.pk - 1) / (32 * p1.pk);
+        p1.n_u = p1.nslab * p1.u_per_slab * p1.KC;
         std::vector<pmu_c> U1, V1, T1;
         pmu::build_tables(p1, b->d.N, &U1, &V1, &T1);
         b->n_u1 = p1.n_u;
+        b->u_per_slab1 = p1.u_per_slab;
         CK(cudaMalloc(&b->dU1, U1.size() * sizeof(pmu_c)));
         CK(cudaMemcpy(b->dU1, U1.data(), U1.size() * sizeof(pmu_c), cudaMemcpyHostToDevice));
     }
@@ -491,7 +492,7 @@ int pmub_create(pmub_batch** out, const pmub_config* cfg, int dtype, unsigned n_
     pp.lp0 = d.lp[0]; pp.lp1 = d.lp[1]; pp.lp2 = d.lp[2];
     pp.trig = b->dT;
     pp.trig_off = (unsigned)b->plan.off_trig;
-    a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.pitch = b->plan.pitch; a.wp = b->plan.wp; a.pk = b->plan.pk; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
+    a.N = (int)d.N; a.L = b->plan.L; a.W = b->plan.W; a.pitch = b->plan.pitch; a.wp = b->plan.wp; a.pk = b->plan.pk; a.u_per_slab = b->plan.u_per_slab; a.nslab = b->plan.nslab; a.Kp = b->plan.Kp;
     a.n_stage = b->plan.n_stage; a.stage_bytes = b->plan.stage_bytes; a.n_cons = b->plan.n_cons;
     a.n_raw = b->plan.n_raw; a.raw_stride = b->plan.raw_stride; a.red_bytes = b->plan.red_bytes;
     a.n_u = b->plan.n_u;

@@ -72,7 +72,9 @@ template <> struct IsPacked<F2> { static constexpr bool value = true; };
 template <typename R> struct alignas(2 * sizeof(R)) RPair { R x, y; };   // one complex partial in the reduction scratch
 PMU_HD double ct_to_double(double v) { return v; }
 PMU_HD double ct_to_double(float v) { return (double)v; }
-PMU_HD double ct_to_double(F2 v) { return (double)v.lo; }   // (only instantiated, never reached, for packed kernels)
+PMU_HD double hsum(double v) { return v; }
+PMU_HD float hsum(float v) { return v; }
+PMU_HD float hsum(F2 v) { return v.lo + v.hi; }
 template <typename R> struct IsDouble { static constexpr bool value = false; };
 template <> struct IsDouble<double> { static constexpr bool value = true; };
 
@@ -302,4 +304,18 @@ PMU_HD void hann_combine_inplace(const Col& X, int K)
         left = cur;
         cur = nxt;
     }
+}
+
+// ... and for packed kernels, whose two halves are different residues: pairs of twiddles (W_N^{2l k}, W_N^{(2l+1) k}).
+template <int KC, typename R>
+PMU_HD void rotate_lane_pairs(const RPair<R>* v, int v_stride, R* ar, R* ai)
+{
+    static_for<0, KC>([&](auto kc) {
+        constexpr int k = kc.value;
+        const RPair<R> w = v[k * v_stride];
+        R r = pmu_fma(ar[k], w.x, -(ai[k] * w.y));
+        R i = pmu_fma(ar[k], w.y, ai[k] * w.x);
+        ar[k] = r;
+        ai[k] = i;
+    });
 }

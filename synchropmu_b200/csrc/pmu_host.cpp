@@ -337,9 +337,12 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
         p.wp = 2;   // 1024-sample windows, and 2048-sample windows of the float build
         p.stage_bytes = align_up(p.wp * N * s, 128);
     }
-    // float build with several windows per pass: two windows per lane on the packed FP32 pipe (FADD2 / FMUL2 / FFMA2)
-    p.pk = (s == 4 && p.wp >= 2 && env_int("PMU_F32X2", 1)) ? 2 : 1;
-    const int lanes_per_window = 32 * p.pk / p.wp;
+    // float build: two adjacent residues per lane on the packed FP32 pipe (FADD2 / FMUL2 / FFMA2)
+#ifndef PMU_F32X2
+#define PMU_F32X2 1
+#endif
+    p.pk = (s == 4 && PMU_F32X2) ? 2 : 1;
+    const int lanes_per_window = (32 / p.wp) * p.pk;   // residues covered per iteration
     // TMA bulk copies: whole window when its rows are already contiguous at the stage pitch,
     // otherwise one copy per row; both need 16-byte granularity
     const bool whole = (p.nslab == 1 && p.pitch == p.L);
@@ -347,9 +350,9 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
                         : ((N * s) % 16 == 0 && (p.L * s) % 16 == 0 && (p.W * s) % 16 == 0 &&
                            ((p.L - (p.nslab - 1) * p.W) * s) % 16 == 0 && (p.pitch * s) % 16 == 0);
 
-    const int n_groups = (p.nslab == 1) ? (p.L + lanes_per_window - 1) / lanes_per_window
-                                        : (p.nslab - 1) * (p.W / 32) + ((p.L - (p.nslab - 1) * p.W) + 31) / 32;
-    p.n_u = n_groups * p.KC;
+    // U[slab][group][k] = W_N^{(slab * W + group * residues per iteration) k}: rectangular, the last slab may use fewer groups
+    p.u_per_slab = (p.W + lanes_per_window - 1) / lanes_per_window;
+    p.n_u = p.nslab * p.u_per_slab * p.KC;
     p.jlo = K + 2;
     p.jhi = 2 * K + 1;
     // one window's K+1 rectangular bins as 16-byte complex entries, rows an odd number of entries apart: the lane-per-
@@ -359,7 +362,7 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
     // 128-bit stores of a quarter warp hit distinct banks
     p.red_stride = 2 * p.KC + 2;  // compile-time in the kernel (immediate LDS offsets)
     // ... and the same region holds the estimator's residual spectrum W[K][32] while the warp posts a batch
-    const int dft_elem = (s == 4 && p.pk == 1) ? 4 : 8;   // the float build reduces float partials (pairs of them when packed)
+    const int dft_elem = (s == 4) ? 4 : 8;   // the float build reduces float partials
     p.red_bytes = align_up(32 * p.red_stride * dft_elem, 128);
     if (p.red_bytes < K * 32 * 16) p.red_bytes = K * 32 * 16;
 
@@ -374,7 +377,7 @@ int make_plan(const pmub_config& c, int dtype, int max_smem, Plan* out)
         int off = 0;
         p.off_ctrl = off; off += align_up((int)sizeof(CtrlBlock), 128);
         p.off_U = off;    off += align_up(p.n_u * 16, 128);
-        p.off_V = off;    off += align_up(p.KC * 32 * 16, 128);
+        p.off_V = off;    off += align_up(p.KC * 32 * 16, 128);   // (pairs of float twiddles per lane when pk == 2: same size)
         p.off_trig = off; off += align_up((p.jlo + p.jhi + 1) * 16, 128);
         p.off_raw = off;  off += align_up(p.n_raw * 32 * p.raw_stride * 8, 128);
         p.off_red = off;  off += p.n_cons * p.red_bytes;
@@ -457,14 +460,20 @@ void build_tables(const Plan& p, unsigned N, std::vector<pmu_c>* U, std::vector<
         for (unsigned m = 0; m < N; ++m) (*U)[m] = w(m);
         V->assign(1, w(0));
     }
-    const int n_groups = p.M == 0 ? 0 : p.n_u / p.KC;
-    if (p.M != 0) U->resize((size_t)p.n_u);
-    for (int g = 0; g < n_groups; ++g)
+    const int pk = p.pk > 1 ? p.pk : 1;
+    const int per_it = (32 / (p.wp > 0 ? p.wp : 1)) * pk;
+    if (p.M != 0) {
+        U->resize((size_t)p.n_u);
+        for (int sl = 0; sl < p.nslab; ++sl)
+            for (int g = 0; g < p.u_per_slab; ++g)
+                for (int k = 0; k < p.KC; ++k)
+                    (*U)[((size_t)sl * p.u_per_slab + g) * p.KC + k] =
+                        w(((unsigned long long)sl * p.W + (unsigned long long)g * per_it) * (unsigned long long)k);
+        // lane twiddles W_N^{a k} for the 32 * pk residues a of one iteration
+        V->resize((size_t)p.KC * 32 * pk);
         for (int k = 0; k < p.KC; ++k)
-            (*U)[(size_t)g * p.KC + k] = w((unsigned long long)(32 * (p.pk > 1 ? p.pk : 1) / p.wp) * (unsigned long long)g * (unsigned long long)k);
-    if (p.M != 0) V->resize((size_t)p.KC * 32);
-    for (int k = 0; p.M != 0 && k < p.KC; ++k)
-        for (int l = 0; l < 32; ++l) (*V)[(size_t)k * 32 + l] = w((unsigned long long)l * (unsigned long long)k);
+            for (int l = 0; l < 32 * pk; ++l) (*V)[(size_t)k * 32 * pk + l] = w((unsigned long long)l * (unsigned long long)k);
+    }
     trig->resize((size_t)(p.jlo + p.jhi + 1));
     for (int j = -p.jlo; j <= p.jhi; ++j) {
         long double ang = 3.14159265358979323846264338327950288L * (long double)j / (long double)N;

@@ -38,7 +38,9 @@ struct Plan {
     int L, W, nslab;    // residues, slab width, slabs per window
     int pitch;          // stage row pitch in elements (PMU_PITCH16 for the 16-point codelet, else W)
     int wp;             // windows per warp pass: 4 for short single-slab windows (8 lanes per window), else 1
-    int pk;             // 2 when the float build packs two windows per lane (FFMA2 pipe): 32 * pk / wp lanes per window
+    int pk;             // 2 in the float build: every lane carries two ADJACENT residues of its window through the packed
+                        // FP32 pipe (FADD2 / FMUL2 / FFMA2), so a pass covers (32 / wp) * pk residues per iteration
+    int u_per_slab;     // residue groups (U rows) per slab: ceil(W / ((32 / wp) * pk))
     int Kp;             // n_bins + 1
     int n_stage, stage_bytes;
     int n_cons, n_raw, raw_stride;

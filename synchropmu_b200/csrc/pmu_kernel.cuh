@@ -52,7 +52,8 @@ struct KernelArgs {
     int N, L, W, nslab, Kp;      // window length, residues (N/M), slab width, slabs per window, n_bins+1
     int pitch;                   // stage row pitch in elements (compile-time in the 16-point-codelet kernels)
     int wp;                      // windows per warp pass (1, or 4 for short windows: 8 lanes per window)
-    int pk;                      // 2: float build, two windows per lane through the packed FP32 pipe (CT = F2); else 1
+    int pk;                      // 2: float build, two adjacent residues per lane through the packed FP32 pipe (CT = F2); else 1
+    int u_per_slab;              // rows of U per slab
     int load_mode;               // PMU_LOAD_BULK / PMU_LOAD_ELEM
     int n_stage, stage_bytes;
     int n_cons;                  // consumer warps
@@ -656,17 +657,24 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, long l
 
 // Load the M samples of one residue from a stage (row pitch in elements).  FULL: every lane of
 // the group is a valid residue, no masking.
-template <typename InT, typename CT, int M, bool FULL>
-__device__ __forceinline__ void load_residue(const InT* xs, int pitch, int a_loc, int w_s, int next_window, CT* x)
+template <typename InT, typename CT, int M, int PITCH, bool FULL>
+__device__ __forceinline__ void load_residue(const InT* xs, int pitch, int a_loc, int w_s, CT* x)
 {
     if constexpr (IsPacked<CT>::value) {
-        // the same residue of two consecutive windows of the stage (next_window elements apart)
-        const bool valid = FULL || a_loc < w_s;
-        const int a_c = valid ? a_loc : 0;
+        // residues a_loc (even) and a_loc + 1 of the window: one 64-bit load per row when the pitch is even
+        const bool v0 = FULL || a_loc < w_s, v1 = FULL || a_loc + 1 < w_s;
+        const int a_c = v0 ? a_loc : 0;
 #pragma unroll
         for (int b = 0; b < M; ++b) {
-            const float v0 = (float)xs[b * pitch + a_c], v1 = (float)xs[next_window + b * pitch + a_c];
-            x[b] = valid ? CT(v0, v1) : CT(0.0f, 0.0f);
+            float f0, f1;
+            if constexpr (PITCH > 0 && PITCH % 2 == 0) {
+                const float2 v = *reinterpret_cast<const float2*>(xs + b * pitch + a_c);
+                f0 = v.x; f1 = v.y;
+            } else {
+                f0 = (float)xs[b * pitch + a_c];
+                f1 = (float)xs[b * pitch + (v1 ? a_c + 1 : a_c)];
+            }
+            x[b] = CT(v0 ? f0 : 0.0f, v1 ? f1 : 0.0f);
         }
     } else if constexpr (FULL) {
 #pragma unroll
@@ -695,10 +703,10 @@ template <typename InT, typename CT, int M, int KC, int PITCH, int WP = 1>
 __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const __grid_constant__ KernelArgs a)
 {
     // packed windows lie in the stage exactly as in memory (natural pitch); the plan guarantees pitch == L for them
-    // CT = F2 (float build): two windows per lane travel through the packed FP32 pipe together (pmu_dft.cuh)
+    // CT = F2 (float build): every lane carries two ADJACENT residues of its window through the packed FP32 pipe
+    // (pmu_dft.cuh); the lane partials are scalar again after the final rotation
     constexpr int PK = IsPacked<CT>::value ? 2 : 1;
-    static_assert(WP % PK == 0, "packed pairs need an even number of windows per pass");
-    constexpr int G = PMU_WARP * PK / WP;   // lanes per window (per pair of windows when packed)
+    constexpr int G = PMU_WARP / WP;        // lanes per window
     typedef typename ScalarOf<CT>::type cscal;
     typedef typename CplxOf<CT>::type ccplx;
     unsigned char* smem = pmu_smem;
@@ -741,10 +749,23 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         ccplx c; c.x = (cscal)w.x; c.y = (cscal)w.y;
         sU[i] = c;
     }
-    for (int i = tid; i < KC * PMU_WARP; i += nthreads) {
-        const pmu_c w = a.V[i];
-        ccplx c; c.x = (cscal)w.x; c.y = (cscal)w.y;
-        sV[i] = c;
+    if constexpr (PK == 2) {
+        // lane l rotates its two residues 2l, 2l+1: pairs of twiddles from the 64-lane table
+        RPair<CT>* sV2 = reinterpret_cast<RPair<CT>*>(sV);
+        for (int i = tid; i < KC * PMU_WARP; i += nthreads) {
+            const int k = i / PMU_WARP, l = i % PMU_WARP;
+            const pmu_c w0 = a.V[k * 2 * PMU_WARP + 2 * l], w1 = a.V[k * 2 * PMU_WARP + 2 * l + 1];
+            RPair<CT> c;
+            c.x = CT((float)w0.x, (float)w1.x);
+            c.y = CT((float)w0.y, (float)w1.y);
+            sV2[i] = c;
+        }
+    } else {
+        for (int i = tid; i < KC * PMU_WARP; i += nthreads) {
+            const pmu_c w = a.V[i];
+            ccplx c; c.x = (cscal)w.x; c.y = (cscal)w.y;
+            sV[i] = c;
+        }
     }
     for (int i = tid; i < a.post.jlo + a.post.jhi + 1; i += nthreads) sT[i] = a.trig[i];
     // Everything above reads only this estimator's own tables.  From here on the kernel touches the caller's windows,
@@ -875,10 +896,10 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     bm.init(n_packs, PMU_WARP / WP);
     FastDivT<(KC >= 24)> by_nlocal, by_nstage;
     by_nlocal.init((unsigned)n_packs);
-    const int sub = lane / G;             // which stream (pair of streams) of the pass this lane works on (0 when WP == 1)
+    const int sub = lane / G;             // which stream of the pass this lane works on (0 when WP == 1)
     const int gl = lane % G;              // its lane index within that stream's group
     by_nstage.init((unsigned)a.n_stage);
-    const int w_per_it = a.W / PMU_WARP;  // full-slab residue groups (W % 32 == 0 when nslab > 1)
+    const int w_per_it = a.u_per_slab;    // rows of U per slab
     FastDivT<(KC >= 24)> by_nraw;
     by_nraw.init((unsigned)a.n_raw);
     const unsigned red_off = (unsigned)a.off_red + (unsigned)(warp - 1) * (unsigned)a.red_bytes;
@@ -926,17 +947,17 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             __syncwarp();
             mbar_wait(&ctrl->full[st], (uint32_t)(use & 1));
             if (tl && lane == 0 && tl[1] == 0) tl[1] = global_ns();
-            const InT* xs = reinterpret_cast<const InT*>(stages + (size_t)st * a.stage_bytes) + (WP == 1 ? 0 : sub * PK * a.N);
+            const InT* xs = reinterpret_cast<const InT*>(stages + (size_t)st * a.stage_bytes) + (WP == 1 ? 0 : sub * a.N);
             const int a_lo = sl * a.W;
             const int w_s = min(a.W, a.L - a_lo);
-            const int n_it = (w_s + G - 1) / G;
-            const bool all_full = (w_s % G) == 0;
+            const int n_it = (w_s + PK * G - 1) / (PK * G);
+            const bool all_full = (w_s % (PK * G)) == 0;
             auto residue_group = [&](int ii) {
-                const int a_loc = gl + G * ii;
+                const int a_loc = PK * (gl + G * ii);
                 CT x[M];
                 // only the last residue group of a slab can be partly out of range
-                if (all_full || ii + 1 < n_it) load_residue<InT, CT, M, true>(xs, pitch, a_loc, w_s, a.N, x);
-                else load_residue<InT, CT, M, false>(xs, pitch, a_loc, w_s, a.N, x);
+                if (all_full || ii + 1 < n_it) load_residue<InT, CT, M, PITCH, true>(xs, pitch, a_loc, w_s, x);
+                else load_residue<InT, CT, M, PITCH, false>(xs, pitch, a_loc, w_s, x);
                 const ccplx* u = sU + (size_t)(sl * w_per_it + ii) * KC;
                 if (first) {
                     accumulate_residue<M, KC, true, CT>(x, u, ar, ai);
@@ -952,19 +973,22 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 mbar_arrive(&ctrl->empty[st]);
             }
         }
-        rotate_lane<KC, CT>(sV + gl, PMU_WARP, ar, ai);
+        if constexpr (PK == 2) rotate_lane_pairs<KC, CT>(reinterpret_cast<const RPair<CT>*>(sV) + gl, PMU_WARP, ar, ai);
+        else rotate_lane<KC, CT>(sV + gl, PMU_WARP, ar, ai);
 
         // ---- sum the 32 lane partials through shared memory: every lane drops its KC complex
         //      partials into its row of the warp's scratch (128-bit stores, conflict-free row
         //      stride), then lane c adds up column c of the 32 rows and deposits the total ----
-        constexpr int RS = 2 * KC + 2;  // row stride in CT elements: an odd number of complex slots
-        CT* red = reinterpret_cast<CT*>(smem + red_off);
+        constexpr int RS = 2 * KC + 2;  // row stride in scalar elements: an odd number of complex slots
+        cscal* red = reinterpret_cast<cscal*>(smem + red_off);
         {
-            RPair<CT>* my = reinterpret_cast<RPair<CT>*>(red + (size_t)lane * RS);
+            RPair<cscal>* my = reinterpret_cast<RPair<cscal>*>(red + (size_t)lane * RS);
 #pragma unroll
             for (int k = 0; k < KC; ++k)
                 if (k < a.Kp) {
-                    RPair<CT> c; c.x = ar[k]; c.y = ai[k];
+                    RPair<cscal> c;
+                    c.x = hsum(ar[k]);      // packed kernels: the two residues' partials are added here
+                    c.y = hsum(ai[k]);
                     my[k] = c;
                 }
         }
@@ -973,7 +997,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
             double* myrow = reinterpret_cast<double*>(smem + a.off_raw) + (size_t)(warp - 1) * a.raw_stride;
             __syncwarp();
             for (int c = lane; c < 2 * a.Kp; c += PMU_WARP) {
-                const CT* col = red + c;
+                const cscal* col = red + c;
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
                 for (int l = 0; l < PMU_WARP; l += 4) {
@@ -1015,31 +1039,12 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
         __syncwarp();
         __threadfence_block();
         double* row = reinterpret_cast<double*>(smem + a.off_raw) + ((size_t)rb * PMU_WARP + slot * WP) * a.raw_stride;
-        if constexpr (PK == 2) {
-            // pair pg of the pass: rows pg*G ... pg*G + G-1 of the scratch hold (window 2pg, window 2pg+1) in (lo, hi)
-#pragma unroll
-            for (int pg = 0; pg < WP / 2; ++pg) {
-                if (t * WP + 2 * pg >= n_local) break;             // the CTA's last pass may be short
-                const bool second = t * WP + 2 * pg + 1 < n_local;
-                for (int c = lane; c < 2 * a.Kp; c += PMU_WARP) {
-                    const CT* col = red + (size_t)pg * G * RS + c;
-                    double l0 = 0.0, l1 = 0.0, h0 = 0.0, h1 = 0.0;   // the column sums are always double
-#pragma unroll
-                    for (int l = 0; l < G; l += 2) {
-                        const CT v0 = col[(l + 0) * RS], v1 = col[(l + 1) * RS];
-                        l0 += (double)v0.lo; h0 += (double)v0.hi;
-                        l1 += (double)v1.lo; h1 += (double)v1.hi;
-                    }
-                    row[(size_t)(2 * pg) * a.raw_stride + c] = l0 + l1;
-                    if (second) row[(size_t)(2 * pg + 1) * a.raw_stride + c] = h0 + h1;
-                }
-            }
-        } else {
+        {
 #pragma unroll
         for (int s2 = 0; s2 < WP; ++s2) {          // stream s2 of the pass: rows s2*G ... s2*G + G-1 of the scratch
             if (WP > 1 && t * WP + s2 >= n_local) break;   // the CTA's last pass may be short
             for (int c = lane; c < 2 * a.Kp; c += PMU_WARP) {
-                const CT* col = red + (size_t)s2 * G * RS + c;
+                const cscal* col = red + (size_t)s2 * G * RS + c;
                 double s0 = 0.0, s1 = 0.0, s2_ = 0.0, s3 = 0.0;   // the column sums are always double
 #pragma unroll
                 for (int l = 0; l < G; l += 4) {

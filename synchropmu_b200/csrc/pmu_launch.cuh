@@ -11,15 +11,22 @@
 #include "pmu_kernel.cuh"
 #include "pmu_wide.cuh"
 
+#ifndef PMU_F32X2
+#define PMU_F32X2 1
+#endif
+
 namespace {
 
 template <typename T, int M, int KC, int PITCH, int WP = 1, typename CT = T>
 int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t s)
 {
-    if constexpr (sizeof(T) == 4 && WP > 1 && !IsPacked<CT>::value) {
-        // float build, several windows per warp pass: two of them per lane on the packed FP32 pipe
-        if (a.pk == 2) return launch_inst<T, M, KC, PITCH, WP, F2>(a, grid, block, smem, s);
-    }
+#if PMU_F32X2
+    if constexpr (sizeof(T) == 4 && !IsPacked<CT>::value) {
+        // float build: two adjacent residues per lane on the packed FP32 pipe (the scalar instantiation is not compiled)
+        return launch_inst<T, M, KC, PITCH, WP, F2>(a, grid, block, smem, s);
+    } else
+#endif
+    {
     // per device: has this instantiation been opted in to the device's maximum dynamic shared memory?  The attribute
     // is only ever set to that one value, so concurrent host threads (batches that share an instantiation but differ
     // in smem_bytes) cannot lower it under each other's launches.
@@ -55,6 +62,7 @@ int launch_inst(const KernelArgs& a, int grid, int block, int smem, cudaStream_t
         return -1;
     }
     return 0;
+    }
 }
 
 // The 16-point codelet always runs on stages with a fixed row pitch of PMU_PITCH16 elements (the plan never makes

@@ -23,8 +23,9 @@ static void window_bins_r(const pmu::Plan& p, const std::vector<pmu_c>& Ud, cons
     for (size_t i = 0; i < Vd.size(); ++i) { V[i].x = (R)Vd[i].x; V[i].y = (R)Vd[i].y; }
     double sum_r[KC], sum_i[KC];
     for (int k = 0; k < KC; ++k) sum_r[k] = sum_i[k] = 0.0;
-    const int w_per_it = p.W / 32;
-    const int G = 32 * (p.pk > 1 ? p.pk : 1) / p.wp;   // lanes per window (8 when four short windows share a warp pass; twice that when the float build packs two windows per lane)
+    const int w_per_it = p.u_per_slab;
+    // residues per iteration = virtual lanes per window: 32 / wp lanes, each carrying pk adjacent residues (float build: 2)
+    const int G = (32 / p.wp) * (p.pk > 1 ? p.pk : 1);
     for (int lane = 0; lane < G; ++lane) {
         R ar[KC], ai[KC];
         bool first = true;
@@ -42,7 +43,7 @@ static void window_bins_r(const pmu::Plan& p, const std::vector<pmu_c>& Ud, cons
                 else accumulate_residue<M, KC, false, R>(xv, u, ar, ai);
             }
         }
-        rotate_lane<KC, R>(V.data() + lane, 32, ar, ai);
+        rotate_lane<KC, R>(V.data() + lane, 32 * (p.pk > 1 ? p.pk : 1), ar, ai);   // the lane table covers every residue of one iteration
         for (int k = 0; k < KC; ++k) { sum_r[k] += (double)ar[k]; sum_i[k] += (double)ai[k]; }   // column sums in double
     }
     for (int k = 0; k < KC; ++k) { raw[2 * k] = sum_r[k]; raw[2 * k + 1] = sum_i[k]; }

@@ -420,11 +420,11 @@ def test_launch_plan_invariants_on_random_configurations(seed):
             # X in place: rows of 16-byte complex entries, an odd number of entries apart, K + 1 entries used
             assert p["raw_stride"] % 2 == 0 and (p["raw_stride"] // 2) % 2 == 1 and p["raw_stride"] >= 2 * p["Kp"]
             # the lane-reduction scratch doubles as the estimator's W[K][32] complex columns
-            elem = 4 if (s == 4 and p["pk"] == 1) else 8
+            elem = s
             assert p["red_bytes"] >= 32 * (2 * p["KC"] + 2) * elem and p["red_bytes"] >= K * 32 * 16
             # small launches use one raw row per consumer warp
             assert p["n_raw"] * 32 >= p["n_cons"]
-            assert p["wp"] in (1, 2, 4) and p["pk"] in (1, 2) and (p["pk"] == 1 or (s == 4 and p["wp"] >= 2))
+            assert p["wp"] in (1, 2, 4) and p["pk"] == (2 if s == 4 else 1)
             if p["wp"] > 1:
                 assert p["nslab"] == 1 and p["pitch"] == p["L"] and p["wp"] * N * s <= p["stage_bytes"]
             else:

@@ -33,7 +33,7 @@ def test_headline_kernels_keep_their_copy_engine_and_barrier_instructions(table)
     for name in ("pmu_fused_kernel<double, double, 16, 12, 128, 1>",     # config 3: one bulk copy per window
                  "pmu_fused_kernel<double, double, 16, 12, 96, 1>",      # M-class: one tiled TMA copy per slab
                  "pmu_fused_kernel<double, double, 8, 10, 0, 4>",        # config 5: four windows per bulk copy
-                 "pmu_fused_kernel<float, float, 16, 12, 128, 2>"):
+                 "pmu_fused_kernel<float, F2, 16, 12, 128, 2>"):       # float build: packed FP32 transform
         k = table[name]
         assert k["UBLKCP"] > 0, name          # cp.async.bulk.shared::cluster.global
         assert k["SYNCS"] > 0, name           # mbarrier arrive / try_wait
@@ -42,8 +42,10 @@ def test_headline_kernels_keep_their_copy_engine_and_barrier_instructions(table)
         assert k["UTCMMA"] == 0 and k["LDTM"] == 0, name
         assert k["DFMA"] > 300, name
     assert table["pmu_fused_kernel<double, double, 16, 12, 96, 1>"]["UTMALDG"] > 0   # cp.async.bulk.tensor
-    # the float build's packed-window kernels run their transform on the packed FP32 pipe
-    for name in ("pmu_fused_kernel<float, F2, 16, 12, 128, 2>", "pmu_fused_kernel<float, F2, 8, 10, 0, 4>"):
+    # every kernel of the float build runs its transform on the packed FP32 pipe (two adjacent residues per lane)
+    assert not [k for k in table if "pmu_fused_kernel<float, float" in k]
+    for name in ("pmu_fused_kernel<float, F2, 16, 12, 128, 2>", "pmu_fused_kernel<float, F2, 8, 10, 0, 4>",
+                 "pmu_fused_kernel<float, F2, 16, 12, 96, 1>"):
         k = table[name]
         assert k["FFMA2"] > 20 and k["FADD2"] > 20 and k["FMUL2"] > 0, name
         assert k["UBLKCP"] > 0 and k["LDL"] == 0 and k["STL"] == 0, name
