@@ -52,8 +52,6 @@ struct KernelArgs {
     int N, L, W, nslab, Kp;      // window length, residues (N/M), slab width, slabs per window, n_bins+1
     int pitch;                   // stage row pitch in elements (compile-time in the 16-point-codelet kernels)
     int wp;                      // windows per warp pass (1, or 4 for short windows: 8 lanes per window)
-    int pk;                      // 2: float build, two adjacent residues per lane through the packed FP32 pipe (CT = F2); else 1
-    int u_per_slab;              // rows of U per slab
     int load_mode;               // PMU_LOAD_BULK / PMU_LOAD_ELEM
     int n_stage, stage_bytes;
     int n_cons;                  // consumer warps
@@ -109,6 +107,9 @@ struct KernelArgs {
     // profiling aid: [gridDim.x][warps][4] globaltimer stamps (setup done, first window ready,
     // tickets exhausted, warp exit); null in normal operation
     unsigned long long* timeline;
+    // (appended so that the offsets of everything above stay what the double kernels were tuned with)
+    int pk;                      // 2: float build, two adjacent residues per lane through the packed FP32 pipe (CT = F2); else 1
+    int u_per_slab;              // rows of U per slab
 };
 
 struct CtrlBlock {
@@ -899,7 +900,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     const int sub = lane / G;             // which stream of the pass this lane works on (0 when WP == 1)
     const int gl = lane % G;              // its lane index within that stream's group
     by_nstage.init((unsigned)a.n_stage);
-    const int w_per_it = a.u_per_slab;    // rows of U per slab
+    const int w_per_it = PK == 1 ? a.W / PMU_WARP : a.u_per_slab;   // rows of U per slab (W % 32 == 0 when an unpacked plan has several slabs)
     FastDivT<(KC >= 24)> by_nraw;
     by_nraw.init((unsigned)a.n_raw);
     const unsigned red_off = (unsigned)a.off_red + (unsigned)(warp - 1) * (unsigned)a.red_bytes;
