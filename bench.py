@@ -302,6 +302,22 @@ class Bench:
             del x
         return win, mid
 
+    def make_record(self, cfg, n_inst, n_ch, tdt, first_sample, n_rows, harm, samples_per_row=None):
+        """[n_rows][n_inst][n_ch][samples_per_row] consecutive stretches (default: hops) of the SAME record make_inputs cuts
+        its windows from, starting at sample `first_sample`: what a streaming caller would push, hop after hop."""
+        torch = self.torch
+        prm = signals.three_phase_params(self.world * n_inst)
+        sl = slice(self.rank * n_inst * n_ch, (self.rank + 1) * n_inst * n_ch)
+        pt = {k: torch.as_tensor(v[sl], device=self.dev) for k, v in prm.items()}
+        L = configs.hop(cfg) if samples_per_row is None else int(samples_per_row)
+        rec = torch.empty((n_rows, n_inst, n_ch, L), dtype=tdt, device=self.dev)
+        for j in range(n_rows):
+            x = signals.steady(cfg, 0, pt["amp"], pt["freq"], pt["phase"], xp=torch, ramp=pt["ramp"], harmonics=harm,
+                               like=pt["amp"], span=(first_sample + j * L, L))
+            rec[j] = x.to(tdt).reshape(n_inst, n_ch, L)
+            del x
+        return rec
+
     def timed_launches(self, fn, steps):
         """CUDA-event time of `steps` calls of fn(i) on self.stream, max over ranks, in ms."""
         torch = self.torch
@@ -356,14 +372,15 @@ class Bench:
         return res
 
 
-def stream_legs(B, est, cfg, n_inst, n_ch, tdt, npdt, win_all, args):
+def stream_legs(B, est, cfg, n_inst, n_ch, tdt, npdt, harm, args):
     """The streaming front end (pmub_stream_*): sample rings resident in HBM, each push hands over the `hop` new samples
-    of every stream.  Three measurements:
+    of every stream.  All legs are fed from ONE record that is continuous in time (round 2 cycled two blocks of new
+    samples: the seam every other push put a phase jump into every window that straddled it, the interference loop
+    fired on those windows and the legs measured a partly triggered workload).  Three measurements:
       stream_device   new samples already in HBM, F frames per push, CUDA-event timed (no host copy)
       e2e_stream      pinned host samples in the batch dtype, one frame per synchronous push (as in round 1)
-      e2e_stream_i16  pinned host int16 ADC counts (promoted on the device, lossless), asynchronous pushes from two
-                      alternating buffers: the copy of push t+1 overlaps the kernels of push t; every push's frames are
-                      read on the host
+      e2e_stream_i16  pinned host int16 ADC counts (promoted on the device, lossless), asynchronous pushes: the copy of
+                      push t+1 overlaps the kernels of push t; every push's frames are read on the host
     """
     torch = B.torch
     world = B.world
@@ -372,99 +389,129 @@ def stream_legs(B, est, cfg, n_inst, n_ch, tdt, npdt, win_all, args):
     itemsize = 8 if tdt == torch.float64 else 4
     F = args.frames_per_step
     n_est_frame = n_inst * n_ch
-    n_res = win_all.shape[0]
+    warm = 3
+    n_push = max(10, min(args.steps, 16))
+    K = warm + n_push
+    # history = the record's first N - hop samples; rec[j] = its next hop samples: pushing rec[j] completes frame j
+    history = B.make_record(cfg, n_inst, n_ch, tdt, 0, 1, harm, samples_per_row=N - hop)[0]
+    rec = B.make_record(cfg, n_inst, n_ch, tdt, N - hop, K * F, harm)            # [K*F][n_inst][n_ch][hop]
 
     # ---- device-resident ------------------------------------------------------------------------------------------
+    # The rings are sized for the whole record (max_frames_per_push = K*F, cap = K*F + N/hop - 1 hops), so that after
+    # the ingest leg has pushed it once every sample of it is resident, contiguous in time, and the in-place leg can
+    # walk it a second time without a producer kernel in the timed region.
     torch.cuda.set_stream(B.stream)
     est.set_stream(B.stream.cuda_stream)
     est.reset()
-    est.stream_begin(hop=hop, max_frames_per_push=F, history=win_all[0][:, :, :N - hop].contiguous())
-    # frame t's new samples are the last `hop` samples of window t (t >= 1)
-    blocks = [torch.stack([win_all[(k * F + f + 1) % n_res][:, :, N - hop:] for f in range(F)]).contiguous() for k in range(2)]
+    est.stream_begin(hop=hop, max_frames_per_push=K * F, history=history)
     d_out = torch.empty((F, n_inst, n_ch, 4), dtype=tdt, device=B.dev)
-    tickets = []
-    for i in range(3):
-        tickets.append(est.stream_push(blocks[i % 2], None, out=d_out, asynchronous=True)[1])
+    for i in range(warm):
+        est.stream_push(rec[i * F:(i + 1) * F], None, out=d_out, asynchronous=True)
     torch.cuda.synchronize()
-    n_push = max(10, min(args.steps, 100))
-    ms_ingest = B.timed_launches(lambda i: est.stream_push(blocks[i % 2], None, out=d_out, asynchronous=True), n_push)
+    ms_ingest = B.timed_launches(lambda i: est.stream_push(rec[(warm + i) * F:(warm + i + 1) * F], None, out=d_out,
+                                                           asynchronous=True), n_push)
     est.sync()
+    finite_ingest = bool(torch.isfinite(d_out).all().item())
     v_ingest = world * n_est_frame * F * n_push / (ms_ingest * 1e-3)
     # ... and with the samples already IN the rings (a device-side producer writes them there itself,
-    # pmub_stream_ring_info + PMUB_PUSH_IN_PLACE): the estimator launch is the only kernel
-    for i in range(3):
+    # pmub_stream_ring_info + PMUB_PUSH_IN_PLACE): the estimator launch is the only kernel.  The write position is back
+    # at 0 now (cap = K*F + N/hop - 1 hops), so the next frames replay the record: N/hop - 1 windows straddle its
+    # end/start seam - they fall into the warm-up pushes - then frames 0, 1, ... again.
+    _, cap, wpos = est.stream_ring_info()
+    if wpos != 0:                                           # (hop does not divide win_len: cap was rounded up to whole hops)
+        raise RuntimeError("stream_device: the record does not fill the rings exactly (cap %d, write position %d)" % (cap, wpos))
+    for i in range(warm):
         est.stream_advance(F, d_out)
     torch.cuda.synchronize()
     launches0 = est.launches
     ms = B.timed_launches(lambda i: est.stream_advance(F, d_out), n_push)
     est.sync()
+    finite = bool(torch.isfinite(d_out).all().item())
+    launches = int(est.launches - launches0)
+    est.set_debug(True)                                      # how many streams run the interference loop on the next frame
+    est.stream_advance(1, d_out[:1])
+    est.sync()
+    trig_frac = float(est.get_debug()[1].mean())
+    est.set_debug(False)
     v = world * n_est_frame * F * n_push / (ms * 1e-3)
+    # the same launches for >= 1 s (the power cap sets the clocks): the rings are replayed over and over, so N/hop - 1 of every
+    # K*F frames straddle the record's seam and run the interference loop (2 %)
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(n_push, int(math.ceil(1200.0 / (ms / n_push))))
+        ms_sus = B.timed_launches(lambda i: est.stream_advance(F, d_out), n_sus)
+        est.sync()
+        sustained = dict(value=world * n_est_frame * F * n_sus / (ms_sus * 1e-3), unit=UNIT, pushes=n_sus,
+                         seconds=ms_sus * 1e-3, ms_per_push=ms_sus / n_sus,
+                         seam_frames_fraction=(N // hop - 1) / float(K * F))
     s = itemsize
     alg = hop * s + 4 * s + 2 * (3 * s + 1)                  # new samples in, frame out, ROCOF state in and out
     moved = N * s + 4 * s + 2 * (3 * s + 1)                  # what the estimator launch requests: the whole window from its ring
     traffic = measured_traffic("stream_device_config3_f64") if (N, F, itemsize) == (2048, 8, 8) else None
     stream_device = dict(value=v, unit=UNIT, frames_per_push=F, pushes=n_push, ms_per_push=ms / n_push,
-                         gpu_launches=int(est.launches - launches0),
-                         with_ingest=dict(value=v_ingest, unit=UNIT, ms_per_push=ms_ingest / n_push,
-                                          note="the same pushes with the new samples handed over as a device block and "
-                                               "scattered into the rings by the ingest kernel (+ 2 x hop x 8 B per estimate)"),
+                         gpu_launches=launches, outputs_finite=finite, triggered_fraction=trig_frac, sustained=sustained,
+                         with_ingest=dict(value=v_ingest, unit=UNIT, ms_per_push=ms_ingest / n_push, outputs_finite=finite_ingest,
+                                          note="the same record pushed as device blocks of F x n_streams x hop new samples, "
+                                               "scattered into the rings by the ingest kernel (+ 2 x hop x %d B per estimate)" % s),
                          roofline=dict(bound="hbm", algorithmic_bytes_per_estimate=alg, frac=v / world * alg / 1e9 / B.peak,
                                        requested_bytes_per_estimate=moved, frac_of_bytes_requested=v / world * moved / 1e9 / B.peak,
                                        traffic=traffic, traffic_bytes_per_estimate=(traffic / (n_est_frame * F) if traffic else None),
                                        peak=B.peak, unit="GB/s"),
-                         note="sample rings resident in HBM, the new samples already in them.  The estimator requests each whole window from "
-                              "its ring, but a streaming launch walks its items group-major (the F consecutive windows of a "
-                              "group of 32 streams back to back), so the win_len - hop samples that consecutive windows share "
-                              "are re-read from L2: `traffic` is the DRAM traffic of the estimator launch measured by ncu "
-                              "(6.8 KB per estimate instead of 16.4 KB).  `frac` is against the streaming-algorithmic bytes "
-                              "(hop new samples + frame + state); at this point the kernel is FP64-issue bound, not HBM bound")
-    del blocks, d_out
+                         note="sample rings resident in HBM, the new samples already in them, one record continuous in time.  "
+                              "The estimator requests each whole window from its ring, but a streaming launch walks its items "
+                              "group-major (the F consecutive windows of a group of 32 streams back to back), so the "
+                              "win_len - hop samples that consecutive windows share are re-read from L2: `traffic` is the DRAM "
+                              "traffic of the estimator launch measured by ncu.  `frac` is against the streaming-algorithmic "
+                              "bytes (hop new samples + frame + state), `frac_of_bytes_requested` against what the window-mode "
+                              "launch would have read from HBM")
+    del d_out
 
     # ---- end to end, batch dtype, synchronous, one frame per push ---------------------------------------------------
     torch.cuda.set_stream(torch.cuda.default_stream(B.dev))
     est.set_stream(None)
     est.reset()
-    est.stream_begin(hop=hop, max_frames_per_push=1, history=win_all[0][:, :, :N - hop].contiguous())
-    h_new = [torch.empty((1, n_inst, n_ch, hop), dtype=tdt).pin_memory() for _ in range(2)]
-    for i in range(2):
-        h_new[i][0].copy_(win_all[(i + 1) % n_res][:, :, N - hop:])
+    est.stream_begin(hop=hop, max_frames_per_push=1, history=history)
+    n_push = min(args.e2e_steps * 4, K * F - 3)
+    n_host = n_push + 3                                       # frames of the record staged in pinned host memory
+    h_new = torch.empty((n_host, n_inst, n_ch, hop), dtype=tdt).pin_memory()
+    h_new.copy_(rec[:n_host])
     h_out = [torch.empty((1, n_inst, n_ch, 4), dtype=tdt).pin_memory() for _ in range(2)]
-    hn = [h.numpy() for h in h_new]
+    hn = h_new.numpy()
     ho = [h.numpy() for h in h_out]
-    for i in range(2):
-        est.stream_push(hn[i % 2], None, out=ho[0])
+    for i in range(3):
+        est.stream_push(hn[i:i + 1], None, out=ho[0])
     B.barrier()
-    n_push = args.e2e_steps * 4
     t0 = time.perf_counter()
     for i in range(n_push):
-        est.stream_push(hn[i % 2], None, out=ho[0])
+        est.stream_push(hn[3 + i:4 + i], None, out=ho[0])
         _ = float(ho[0][0, 0, 0, 2])
     dt = B.max_over_ranks(time.perf_counter() - t0)
     e2e_stream = dict(value=world * n_est_frame * n_push / dt, unit=UNIT,
                       h2d_bytes_per_step=int(n_est_frame * hop * itemsize), d2h_bytes_per_step=int(n_est_frame * 4 * itemsize),
                       steps=n_push, ms_per_step=dt / n_push * 1e3, host_memory="pinned", numa_node=B.numa_node,
+                      outputs_finite=bool(np.isfinite(ho[0]).all()),
                       note="pmub_stream_push (synchronous): sample rings resident in HBM, one frame per call, only the "
                            "%d new samples per stream are copied in, as %d-byte values" % (hop, itemsize))
+    del h_new, hn
 
     # ---- end to end, int16 ADC counts, asynchronous double-buffered pushes --------------------------------------------
     est.reset()
-    est.stream_begin(hop=hop, max_frames_per_push=1, history=win_all[0][:, :, :N - hop].contiguous())
-    amax = win_all[0].abs().amax(dim=2).clamp_min(1e-30)          # per stream
+    est.stream_begin(hop=hop, max_frames_per_push=1, history=history)
+    amax = torch.maximum(history.abs().amax(dim=2), rec[:n_host].abs().amax(dim=3).amax(dim=0)).clamp_min(1e-30)   # per stream
     scale = (amax / 32000.0).double()
     est.stream_set_scale(scale.reshape(-1).cpu().numpy())
-    q_new = [torch.empty((1, n_inst, n_ch, hop), dtype=torch.int16).pin_memory() for _ in range(2)]
-    for i in range(2):
-        q = torch.round(win_all[(i + 1) % n_res][:, :, N - hop:].double() / scale[:, :, None]).clamp_(-32768, 32767)
-        q_new[i][0].copy_(q.to(torch.int16))
-    qn = [h.numpy() for h in q_new]
+    q_new = torch.empty((n_host, n_inst, n_ch, hop), dtype=torch.int16).pin_memory()
+    for j in range(n_host):
+        q_new[j].copy_(torch.round(rec[j].double() / scale[:, :, None]).clamp_(-32768, 32767).to(torch.int16))
+    qn = q_new.numpy()
     prev = None
     for i in range(3):
-        _, tk = est.stream_push(qn[i % 2], None, out=ho[i % 2], asynchronous=True)
+        _, tk = est.stream_push(qn[i:i + 1], None, out=ho[i % 2], asynchronous=True)
         est.stream_wait(tk)
     B.barrier()
     t0 = time.perf_counter()
     for i in range(n_push):
-        _, tk = est.stream_push(qn[i % 2], None, out=ho[i % 2], asynchronous=True)
+        _, tk = est.stream_push(qn[3 + i:4 + i], None, out=ho[i % 2], asynchronous=True)
         if prev is not None:
             est.stream_wait(prev[0])
             _ = float(ho[prev[1]][0, 0, 0, 2])     # the previous push's frames, read on the host while this one runs
@@ -478,9 +525,11 @@ def stream_legs(B, est, cfg, n_inst, n_ch, tdt, npdt, win_all, args):
                           steps=n_push, ms_per_step=dt / n_push * 1e3, host_memory="pinned", numa_node=B.numa_node,
                           outputs_finite=finite,
                           note="pmub_stream_push_ex(PMUB_SAMPLES_I16, PMUB_PUSH_ASYNC): int16 ADC counts x per-stream scale, promoted "
-                               "to the batch dtype on the device (exact), two alternating pinned buffers; every push's frames are read "
-                               "on the host one push later")
+                               "to the batch dtype on the device (exact), consecutive hops of one pinned record; every push's frames "
+                               "are read on the host one push later")
     est.stream_set_scale(None)
+    del rec, history, q_new, qn
+    torch.cuda.empty_cache()
     return stream_device, e2e_stream, e2e_stream_i16
 
 
@@ -693,11 +742,12 @@ def main():
     stream_device = None
     e2e_stream = None
     e2e_stream_i16 = None
+    del win_all, mid_all, out
+    torch.cuda.empty_cache()
     if not args.no_e2e:
-        stream_device, e2e_stream, e2e_stream_i16 = stream_legs(B, est, cfg, n_inst, n_ch, tdt, npdt, win_all, args)
+        stream_device, e2e_stream, e2e_stream_i16 = stream_legs(B, est, cfg, n_inst, n_ch, tdt, npdt, harm, args)
 
     est.close()
-    del win_all, mid_all, out
     torch.cuda.empty_cache()
 
     # ---------------- the other configurations (short runs) ---------------------------------------------------------

@@ -43,10 +43,22 @@ struct alignas(16) pmu_c {
 #define PMU_PI 3.14159265358979323846 /* M_PI, reference src/func_stubs.h:33 */
 #endif
 
+#if defined(__CUDACC__)
+// the general-range routine, out of line: it is only reached when an interpolated peak is more than half a bin away
+// from its bin, and inlined into the estimator's loops its 75 instructions are pure instruction-cache ballast
+static __device__ __noinline__ double2 pmu_sincospi_general(double x)
+{
+    double s, c;
+    sincospi(x, &s, &c);
+    return make_double2(s, c);
+}
+#endif
 PMU_HD void pmu_sincospi(double x, double* s, double* c)
 {
 #if defined(__CUDA_ARCH__)
-    sincospi(x, s, c);
+    const double2 sc = pmu_sincospi_general(x);
+    *s = sc.x;
+    *c = sc.y;
 #else
     // host emulation only: |x| <= ~0.5 here, argument rounding costs < 1 ulp of pi*x
     *s = sin(PMU_PI * x);
@@ -59,11 +71,14 @@ PMU_HD void pmu_sincospi(double x, double* s, double* c)
 #endif
 // unroll factors of the estimator's bin loops (independent reciprocal / sweep chains per bin: the loops are latency-,
 // not issue-bound, so several bins in flight per lane pay)
+// (measured again on the one-copy estimator, profiles/r2_ab_variants.jsonl: NOT unrolling is best - the smaller the
+//  estimator's code, the fewer instruction-cache misses with seven warps at different places in it: 1 / 1 against 2 / 2
+//  gives +3 % triggered, +1.5 % config 5, +5 % float build)
 #ifndef PMU_UNROLL_COMP
-#define PMU_UNROLL_COMP 2
+#define PMU_UNROLL_COMP 1
 #endif
 #ifndef PMU_UNROLL_RES
-#define PMU_UNROLL_RES 2
+#define PMU_UNROLL_RES 1
 #endif
 #ifndef PMU_FAST_SQRT
 #define PMU_FAST_SQRT 1

@@ -49,16 +49,28 @@ def mid_fracsec(cfg: dict, frame: int) -> float:
     return t - math.floor(t)
 
 
-def steady(cfg, frame, amp, freq, phase, xp=np, harmonics=(), ramp=None, like=None):
+def span_times(cfg: dict, first_sample: int, n_samples: int, xp=np, like=None):
+    """Sample times [n_samples] (seconds) of the samples ``first_sample ...`` of the record frame 0 starts."""
+    return (_arange(xp, n_samples, like) + float(first_sample)) / float(cfg["fs"])
+
+
+def steady(cfg, frame, amp, freq, phase, xp=np, harmonics=(), ramp=None, like=None, span=None):
     """Windows [S, N] of ``amp cos(2 pi f t + pi R t^2 + ph)`` plus extra tones.
 
     amp/freq/phase/ramp are per-stream arrays of length S.  ``harmonics`` is a
     sequence of ``(rel_amp, freq_hz_or_array, phase_offset)`` added as
     ``amp*rel_amp*cos(2 pi f_h t + ph + phase_offset)``: (0.1, 75.0, 0.0)
     reproduces the interharmonic of test/test.c:60.
+
+    ``span=(first_sample, n_samples)`` replaces the window of ``frame`` by any
+    stretch of the same record (frame t is its samples ``t*hop ... t*hop+N-1``):
+    the streaming front end is fed from one continuous record, hop by hop.
     """
     a = _col(xp, amp, like)
-    t = frame_times(cfg, frame, xp, a if xp is not np else None).reshape(1, -1)
+    if span is None:
+        t = frame_times(cfg, frame, xp, a if xp is not np else None).reshape(1, -1)
+    else:
+        t = span_times(cfg, int(span[0]), int(span[1]), xp, a if xp is not np else None).reshape(1, -1)
     f = _col(xp, freq, a if xp is not np else None)
     p = _col(xp, phase, a if xp is not np else None)
     arg = 2.0 * math.pi * f * t + p

@@ -44,7 +44,8 @@ def main():
     res["config3_f64_detail"] = l[-1]
     res["config3_f64_algorithmic"] = 196608 * (2048 * 8 + 32 + 50 + 8 / 6)
     # streaming front end, rings in HBM, 8 frames per push
-    l = capture([sys.executable, "tools/stream_dev.py", "config.ini", "8", "6"], 6, 2, out / "traffic_stream.csv")
+    # (3 + 6 pushes through the ingest kernel, then 3 + 6 in place: take two of the timed in-place launches)
+    l = capture([sys.executable, "tools/stream_dev.py", "config.ini", "8", "6", "-", "both"], 13, 2, out / "traffic_stream.csv")
     res["stream_device_config3_f64"] = l[-1]["dram__bytes_read.sum"] + l[-1]["dram__bytes_write.sum"]
     res["stream_device_config3_f64_detail"] = l[-1]
     (ROOT / "profiles" / "traffic_per_launch.json").write_text(json.dumps(res, indent=1) + "\n")
