@@ -431,3 +431,21 @@ def test_launch_plan_invariants_on_random_configurations(seed):
                 assert p["M"] * p["pitch"] * s <= p["stage_bytes"] and p["W"] <= p["pitch"]
             assert p["nslab"] == -(-p["L"] // p["W"])
     assert len(seen) >= 8, seen
+
+
+def test_signal_record_spans_agree_with_frames():
+    """A stretch of the record cut with ``span=`` is the same samples the per-frame generator yields: the streaming bench
+    legs push hops of ONE continuous record (a seam between recycled blocks would put a phase jump into every window across
+    it and trigger the interference loop there)."""
+    cfg = configs.DEFAULT_INI
+    N, hop = configs.win_len(cfg), configs.hop(cfg)
+    prm = signals.three_phase_params(2)
+    kw = dict(ramp=prm["ramp"], harmonics=[(0.1, 75.0, 0.0)])
+    frames = [signals.steady(cfg, t, prm["amp"], prm["freq"], prm["phase"], **kw) for t in range(4)]
+    hist = signals.steady(cfg, 0, prm["amp"], prm["freq"], prm["phase"], span=(0, N - hop), **kw)
+    np.testing.assert_array_equal(hist, frames[0][:, :N - hop])
+    for t in range(4):
+        new = signals.steady(cfg, 0, prm["amp"], prm["freq"], prm["phase"], span=(N - hop + t * hop, hop), **kw)
+        np.testing.assert_array_equal(new, frames[t][:, N - hop:])
+    # ... and consecutive frames overlap exactly (no seam inside the record)
+    np.testing.assert_array_equal(frames[1][:, :N - hop], frames[0][:, hop:])
