@@ -1285,3 +1285,104 @@ def test_parity_under_starved_resources(variant):
     tail = "\n".join(r.stdout.splitlines()[-15:])
     assert r.returncode == 0, f"{variant}: {tail}\n{r.stderr[-1500:]}"
     assert " passed" in tail and "failed" not in tail
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's threading contract: different contexts may be driven concurrently
+# ---------------------------------------------------------------------------------------
+def test_contexts_driven_from_concurrent_host_threads_agree_with_sequential_runs():
+    """Four host threads, each with its own batch (different plans: codelet size, bins, shared-memory size, dtype) and
+    its own drop-in context, all estimating at once: every frame equals the one a sequential run produces.  (ctypes
+    releases the GIL around the calls, so the launches, the one-time kernel attribute set-up and the copies interleave.)"""
+    import threading
+
+    jobs = [(configs.DEFAULT_INI, np.float64, 96), (configs.CFG5_600, np.float64, 192),
+            (configs.M_CLASS_INI, np.float32, 64), (configs.P_CLASS_INI, np.float64, 128)]
+    T = 6
+    inputs, want = [], []
+    for k, (cfg, dt, n_inst) in enumerate(jobs):
+        win, mid = three_phase_batch(cfg, n_inst, T, seed=500 + k)
+        win, mid = win.astype(dt), mid.astype(dt)
+        inputs.append((win, mid))
+        with BatchEstimator(cfg, n_inst, 6, dtype=dt) as est:
+            want.append(np.stack([est.estimate(win[t], mid[t]).copy() for t in range(T)]))
+    # the drop-in path as a fifth participant
+    pmu_win = inputs[0][0][:, 0, 0, :].astype(np.float64)
+    pmu = PMUEstimator(n_channels=1, dtype=np.float64)
+    assert pmu.configure_from_class(EstimatorConfig.from_dict(configs.DEFAULT_INI)) == 0
+    pmu_want = [pmu.estimate(pmu_win[t], float(inputs[0][1][t, 0])) for t in range(T)]
+    assert pmu.deinit() == 0
+
+    got = [None] * len(jobs)
+    pmu_got = []
+    errors = []
+    start = threading.Barrier(len(jobs) + 1)
+
+    def run_batch(k):
+        try:
+            cfg, dt, n_inst = jobs[k]
+            win, mid = inputs[k]
+            start.wait()
+            for _rep in range(3):                         # fresh batches while the others are mid-flight
+                with BatchEstimator(cfg, n_inst, 6, dtype=dt) as est:
+                    got[k] = np.stack([est.estimate(win[t], mid[t]).copy() for t in range(T)])
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    def run_dropin():
+        try:
+            p = PMUEstimator(n_channels=1, dtype=np.float64)
+            assert p.configure_from_class(EstimatorConfig.from_dict(configs.DEFAULT_INI)) == 0
+            start.wait()
+            for t in range(T):
+                pmu_got.append(p.estimate(pmu_win[t], float(inputs[0][1][t, 0])))
+            assert p.deinit() == 0
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=run_batch, args=(k,)) for k in range(len(jobs))] + [threading.Thread(target=run_dropin)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=300)
+    assert not errors, errors
+    for k in range(len(jobs)):
+        assert got[k] is not None and np.array_equal(got[k], want[k], equal_nan=True), "thread %d differs from its sequential run" % k
+    assert pmu_got == pmu_want
+
+
+def test_create_use_destroy_cycles_return_all_device_memory():
+    """Batches (with rings, debug buffers, staging areas, asynchronous push slots) created, used and closed 25 times
+    leave the device's free memory where it was."""
+    import torch
+
+    cfg = configs.DEFAULT_INI
+    N, hop = configs.win_len(cfg), configs.hop(cfg)
+    n_inst = 256
+    win, mid = three_phase_batch(cfg, n_inst, 2, seed=77)
+    hist = np.ascontiguousarray(win[0][:, :, :N - hop])
+    new = np.ascontiguousarray(win[1][:, :, N - hop:]).reshape(1, n_inst, 6, hop)
+    q = np.clip(np.round(new / 0.02), -32768, 32767).astype(np.int16)
+
+    def cycle():
+        with BatchEstimator(cfg, n_inst, 6) as est:
+            est.estimate(win[0], mid[0])
+            est.set_debug(True)
+            est.estimate(win[1], mid[1])
+            est.get_debug()
+            est.set_debug(False)
+            est.stream_begin(hop=hop, max_frames_per_push=4, history=hist)
+            est.stream_push(new, None)
+            est.stream_set_scale(np.full(n_inst * 6, 0.02))
+            _, tk = est.stream_push(q, None, asynchronous=True)
+            est.stream_wait(tk)
+
+    for _ in range(3):
+        cycle()                                           # one-time allocations (context, module load, pools)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(25):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < (4 << 20), "device memory shrank by %.1f MB over 25 create/use/destroy cycles" % ((free0 - free1) / 2**20)
