@@ -661,6 +661,16 @@ def main():
         v1 = world * n_inst * n_ch / (ms1 * 1e-3)
         single = dict(value=v1, unit=UNIT, frac=v1 / world * bpe / 1e9 / B.peak, ms_per_launch=ms1,
                       note="one frame (%d estimates) per kernel launch" % (n_inst * n_ch))
+        # the same launches with pmub_set_overlap: every input is resident before the first launch, so a launch may start
+        # on the SMs its predecessor has already left (the kernel waits for it at the ROCOF step only)
+        est.set_overlap(True)
+        for i in range(5):
+            est.estimate_async(win_all[i % n_frames_res], mid_all[i % n_frames_res], out1)
+        ms1o = B.timed_launches(lambda i: est.estimate_async(win_all[i % n_frames_res], mid_all[i % n_frames_res], out1), n1) / n1
+        est.set_overlap(False)
+        v1o = world * n_inst * n_ch / (ms1o * 1e-3)
+        single["overlapped"] = dict(value=v1o, unit=UNIT, frac=v1o / world * bpe / 1e9 / B.peak, ms_per_launch=ms1o,
+                                    note="pmub_set_overlap(1): consecutive launches overlap")
 
     # ---------------- frames written straight into rank 0's HBM by the kernel (P2P stores over NVLink,
     # CUDA IPC buffer): the gather without a collective ------------------------------------------------

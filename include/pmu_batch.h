@@ -163,6 +163,16 @@ int pmub_stream_ring_info(pmub_batch *b, void **base, long long *cap_samples, lo
 int pmub_sync(pmub_batch *b);
 /* Run on the caller's CUDA stream (cudaStream_t passed as void*); NULL = own stream. */
 int pmub_set_stream(pmub_batch *b, void *cuda_stream);
+/* Let consecutive launches of this batch OVERLAP (off by default).  By enabling it the caller promises that nothing enqueued
+ * on the batch's stream between one launch of this batch and the next writes what that next launch reads - device windows,
+ * device mid_fracsec, ring samples written in place (PMUB_PUSH_IN_PLACE): they were complete before the previous launch was
+ * enqueued, or their writer is ordered through an event, another stream or the host.  The estimator kernel then waits for
+ * its predecessor only where it consumes that predecessor's results (the ROCOF state of the previous frame, the frame and
+ * state stores) instead of at its top: on every SM the previous launch has already left, the transforms of the next one
+ * start while the last CTAs of the previous one are still in their estimator tail.  Results are identical; calls that
+ * copy from host memory or ingest samples through the library's own kernels are not affected.  Applies to
+ * pmub_estimate_async / pmub_estimate_frames_async and to in-place pmub_stream_push_ex. */
+int pmub_set_overlap(pmub_batch *b, int enable);
 /* Kernels launched by this batch so far. */
 long long pmub_launch_count(const pmub_batch *b);
 

@@ -171,6 +171,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.pmub_stream_ring_info.restype = ip
     lib.pmub_sync.argtypes = [vp]
     lib.pmub_set_stream.argtypes = [vp, vp]
+    lib.pmub_set_overlap.argtypes = [vp, C.c_int]
     lib.pmub_launch_count.argtypes = [vp]
     lib.pmub_launch_count.restype = C.c_longlong
     lib.pmub_reset.argtypes = [vp]
@@ -200,7 +201,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
     for fn in ("pmub_validate", "pmub_parse_ini", "pmub_create", "pmub_create_ini", "pmub_destroy",
                "pmub_get_info", "pmub_estimate", "pmub_estimate_async", "pmub_estimate_frames",
                "pmub_estimate_frames_async", "pmub_stream_begin", "pmub_stream_push", "pmub_stream_push_ex",
-               "pmub_stream_set_scale", "pmub_stream_wait", "pmub_sync", "pmub_set_stream",
+               "pmub_stream_set_scale", "pmub_stream_wait", "pmub_sync", "pmub_set_stream", "pmub_set_overlap",
                "pmub_reset", "pmub_get_state", "pmub_set_state", "pmub_set_debug", "pmub_get_debug"):
         getattr(lib, fn).restype = ip
     if path is None:
@@ -476,6 +477,13 @@ class BatchEstimator:
     def set_stream(self, cuda_stream: int | None) -> None:
         """Run on the caller's CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
         self._check(self.lib.pmub_set_stream(self._h, C.c_void_p(cuda_stream or 0)), "pmub_set_stream")
+
+    def set_overlap(self, enable: bool = True) -> None:
+        """Let consecutive launches of this batch overlap (``pmub_set_overlap``): the caller promises that nothing enqueued
+        on the batch's stream between two launches writes what the second one reads (device windows, ``mid_fracsec``,
+        ring samples written in place).  The kernel then waits for its predecessor at the ROCOF step instead of at its
+        top, so a launch's transforms start while the previous launch's last CTAs finish.  Same results."""
+        self._check(self.lib.pmub_set_overlap(self._h, 1 if enable else 0), "pmub_set_overlap")
 
     @property
     def launches(self) -> int:

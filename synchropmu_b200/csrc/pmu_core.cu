@@ -69,6 +69,7 @@ struct pmub_batch {
     double* d_spec;
     unsigned long long* d_timeline;   // profiling aid (pmub_debug_timeline)
     bool debug, mirror;
+    bool overlap;   // pmub_set_overlap: launches may start before their predecessor has drained (KernelArgs::defer_wait)
     bool spec_raw;              // debug spectrum = rectangular-window bins (pmub_fft_r)
     // small-batch pinned staging
     unsigned char* h_in;
@@ -148,7 +149,7 @@ struct RingSrc {
 
 static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames, const void* d_windows_base,
                         const void* d_mid_base, void* d_frames_base, double* d_export_base, cudaStream_t s,
-                        const RingSrc* ring = nullptr)
+                        const RingSrc* ring = nullptr, bool inputs_untouched = false)
 {
     if (w1 <= w0 || n_frames < 1) return 0;
     KernelArgs a = b->args;
@@ -200,6 +201,9 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     if (force_elem) a.load_mode = PMU_LOAD_ELEM;
     static const int no_pdl = getenv("PMU_NO_PDL") ? atoi(getenv("PMU_NO_PDL")) : 0;
     a.pdl = no_pdl ? 0 : 1;
+    // inputs_untouched: the library itself enqueued nothing that writes this launch's inputs since the previous launch;
+    // with the caller's promise of the same (pmub_set_overlap) the wait for the preceding grid moves to the ROCOF step
+    a.defer_wait = (b->overlap && inputs_untouched && a.pdl && !b->debug && !b->d_timeline) ? 1 : 0;
     a.use_tmap = 0;
     if (!ring && a.load_mode == PMU_LOAD_BULK &&
         encode_window_tensor(b, a.windows, (long long)(n_frames - 1) * b->n_windows + (w1 - w0), &a.tmap))
@@ -235,7 +239,7 @@ static int frames_per_launch(const pmub_batch* b, long long n, int n_frames)
 
 // launch_range for any frame count: splits into per-frame launches when one launch cannot carry them
 static int launch_frames(pmub_batch* b, long long w0, long long w1, int n_frames, const void* dW, const void* dM,
-                         void* dF, double* d_export, cudaStream_t s, const RingSrc* ring = nullptr)
+                         void* dF, double* d_export, cudaStream_t s, const RingSrc* ring = nullptr, bool inputs_untouched = false)
 {
     const int fpl = frames_per_launch(b, w1 - w0, n_frames);
     const size_t sz = (size_t)b->dtype;
@@ -248,7 +252,7 @@ static int launch_frames(pmub_batch* b, long long w0, long long w1, int n_frames
         }
         if (launch_range(b, w0, w1, nf, ring ? nullptr : (const unsigned char*)dW + (size_t)f * b->n_windows * b->d.N * sz,
                          dM ? (const unsigned char*)dM + (size_t)f * b->n_inst * sz : nullptr,
-                         (unsigned char*)dF + (size_t)f * b->n_windows * 4 * sz, d_export, s, ring ? &r2 : nullptr))
+                         (unsigned char*)dF + (size_t)f * b->n_windows * 4 * sz, d_export, s, ring ? &r2 : nullptr, inputs_untouched))
             return -1;
     }
     return 0;
@@ -543,6 +547,14 @@ int pmub_set_stream(pmub_batch* b, void* cuda_stream)
     return 0;
 }
 
+/* See include/pmu_batch.h: the caller's promise that lets consecutive launches of this batch overlap. */
+int pmub_set_overlap(pmub_batch* b, int enable)
+{
+    if (!b) return -1;
+    b->overlap = enable != 0;
+    return 0;
+}
+
 long long pmub_launch_count(const pmub_batch* b) { return b ? b->launches : 0; }
 
 int pmub_sync(pmub_batch* b)
@@ -559,7 +571,7 @@ int pmub_estimate_frames_async(pmub_batch* b, int n_frames, const void* d_window
 {
     if (!b || !d_windows || !d_mid || !d_frames || n_frames < 1) { set_error("[pmu_estimate] ERROR: bad argument"); return -1; }
     CUDA_OK(cudaSetDevice(b->device));
-    return launch_frames(b, 0, b->n_windows, n_frames, d_windows, d_mid, d_frames, nullptr, main_stream(b));
+    return launch_frames(b, 0, b->n_windows, n_frames, d_windows, d_mid, d_frames, nullptr, main_stream(b), nullptr, true);
 }
 
 int pmub_estimate_async(pmub_batch* b, const void* d_windows, const void* d_mid, void* d_frames)
@@ -868,7 +880,8 @@ int pmub_stream_push_ex(pmub_batch* b, int n_frames, const void* samples, int sa
     RingSrc ring;
     ring.start = ((b->ring_wpos + hop - N) % cap + cap) % cap;
     ring.t0 = (b->stream_origin + b->stream_pushed + (unsigned long long)hop - (unsigned long long)N) % b->cfg.fs;
-    if (launch_frames(b, 0, (long long)n, n_frames, nullptr, dM, dF, nullptr, s_comp, &ring)) return -1;
+    // (in place: no ingest kernel, no copy of mid_fracsec before the launch)
+    if (launch_frames(b, 0, (long long)n, n_frames, nullptr, dM, dF, nullptr, s_comp, &ring, in_place && (!mid || mid_dev))) return -1;
     if (!fr_dev) CUDA_OK(cudaMemcpyAsync(frames, dF, fr_bytes * n_frames, cudaMemcpyDeviceToHost, s_comp));
     CUDA_OK(cudaEventRecord(b->ev_done[dslot], s_comp));
     b->ev_done_valid[dslot] = true;

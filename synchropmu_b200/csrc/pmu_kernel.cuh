@@ -110,6 +110,12 @@ struct KernelArgs {
     // (appended so that the offsets of everything above stay what the double kernels were tuned with)
     int pk;                      // 2: float build, two adjacent residues per lane through the packed FP32 pipe (CT = F2); else 1
     int u_per_slab;              // rows of U per slab
+    // pmub_set_overlap: the caller guarantees that nothing enqueued between this batch's previous launch and this one
+    // writes what the launch READS (windows / ring samples / mid_fracsec).  The wait for the preceding grid then moves from
+    // the top of the kernel to the first access that really depends on it - the ROCOF state of the previous frame and
+    // the frame / state stores - so the transforms of this launch start on every SM the previous launch has already
+    // left, while its last CTAs are still in their estimator tail.
+    int defer_wait;
 };
 
 struct CtrlBlock {
@@ -467,6 +473,7 @@ __device__ __forceinline__ void finish_window(const KernelArgs& a, const Tone& f
 {
     const PostParams& pp = a.post;
     const long long wf = (long long)frame * a.frame_stride + w;
+    if (a.defer_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous launch left this stream's state
     RocofState rs;
     rs.f_old = __ldcg(&a.st_fold[w]);
     rs.dl0 = __ldcg(&a.st_dl0[w]);
@@ -612,6 +619,8 @@ __device__ __noinline__ void post_batch(const KernelArgs& a, int raw_buf, long l
         __syncwarp();
         __threadfence_block();
     }
+    // ... and the previous LAUNCH's, when its wait was deferred to here (pmub_set_overlap)
+    if (a.defer_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (active) {
         RocofState rs;
         // the previous frame's state may have been written by another warp of this CTA
@@ -771,7 +780,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     for (int i = tid; i < a.post.jlo + a.post.jhi + 1; i += nthreads) sT[i] = a.trig[i];
     // Everything above reads only this estimator's own tables.  From here on the kernel touches the caller's windows,
     // the frames and the ROCOF state: wait for whatever precedes this launch in the stream (a no-op without PDL).
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!a.defer_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     if (n_local <= 0) return;
 

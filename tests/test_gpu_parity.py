@@ -1386,3 +1386,70 @@ def test_create_use_destroy_cycles_return_all_device_memory():
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < (4 << 20), "device memory shrank by %.1f MB over 25 create/use/destroy cycles" % ((free0 - free1) / 2**20)
+
+
+def test_overlapped_launches_match_serialised_ones():
+    """pmub_set_overlap: launches whose inputs are all resident beforehand may start before their predecessor has drained
+    (the kernel waits for it at the ROCOF step only).  Frames - ROCOF chain included - are bit-identical to the default
+    serialised launches: single-frame launches, 3 frames per launch, and in-place streaming pushes."""
+    import torch
+
+    cfg = configs.DEFAULT_INI
+    N, hop = configs.win_len(cfg), configs.hop(cfg)
+    n_inst, T = 1024, 12                                   # 6144 streams: every SM has a CTA
+    dev = torch.device("cuda")
+    prm = signals.three_phase_params(n_inst, seed=31)
+    pt = {k: torch.as_tensor(v, device=dev) for k, v in prm.items()}
+    wins, mids = [], []
+    for t in range(T):
+        harm = [(0.1, 75.0, 0.0)] if t % 5 == 2 else []    # some frames run the interference loop everywhere
+        x = signals.steady(cfg, t, pt["amp"], pt["freq"], pt["phase"], xp=torch, ramp=pt["ramp"], harmonics=harm, like=pt["amp"])
+        wins.append(x.reshape(n_inst, 6, N).contiguous())
+        mids.append(torch.full((n_inst,), signals.mid_fracsec(cfg, t), dtype=torch.float64, device=dev))
+    W = torch.stack(wins).contiguous()
+    M = torch.stack(mids).contiguous()
+    s = torch.cuda.Stream()
+
+    def run(overlap, fpl):
+        out = torch.zeros((T, n_inst, 6, 4), dtype=torch.float64, device=dev)
+        with BatchEstimator(cfg, n_inst, 6) as est, torch.cuda.stream(s):
+            est.set_stream(s.cuda_stream)
+            est.set_overlap(overlap)
+            for rep in range(3):                           # back to back, nothing in between
+                est.reset()
+                for t in range(0, T, fpl):
+                    if fpl == 1:
+                        est.estimate_async(W[t], M[t], out[t])
+                    else:
+                        est.estimate_frames_async(fpl, W[t:t + fpl], M[t:t + fpl], out[t:t + fpl])
+            s.synchronize()
+        return out.cpu().numpy()
+
+    for fpl in (1, 3):
+        a, b = run(False, fpl), run(True, fpl)
+        assert np.isfinite(a).all()
+        assert np.array_equal(a, b), "overlapped launches differ (frames per launch %d)" % fpl
+
+    # in-place streaming pushes over a resident record
+    F, K = 2, 5
+    span = lambda first, n: signals.steady(cfg, 0, pt["amp"], pt["freq"], pt["phase"], xp=torch, ramp=pt["ramp"],
+                                           like=pt["amp"], span=(first, n)).reshape(n_inst, 6, n).contiguous()   # noqa: E731
+    hist = span(0, N - hop)
+    rec = torch.stack([span(N - hop + j * hop, hop) for j in range(K * F)]).contiguous()
+
+    def run_stream(overlap):
+        outs = torch.zeros((K, F, n_inst, 6, 4), dtype=torch.float64, device=dev)
+        scratch = torch.zeros((K * F, n_inst, 6, 4), dtype=torch.float64, device=dev)
+        with BatchEstimator(cfg, n_inst, 6) as est, torch.cuda.stream(s):
+            est.set_stream(s.cuda_stream)
+            est.stream_begin(hop=hop, max_frames_per_push=K * F, history=hist)
+            est.stream_push(rec, None, out=scratch)        # fills the rings; the write position is back at 0
+            est.reset()
+            est.set_overlap(overlap)
+            for k in range(K):
+                est.stream_advance(F, outs[k])
+            s.synchronize()
+        return outs.cpu().numpy()
+
+    a, b = run_stream(False), run_stream(True)
+    assert np.isfinite(a).all() and np.array_equal(a, b), "overlapped in-place pushes differ"
