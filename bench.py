@@ -423,6 +423,7 @@ def stream_legs(B, est, cfg, n_inst, n_ch, tdt, npdt, harm, args):
     for i in range(warm):
         est.stream_advance(F, d_out)
     torch.cuda.synchronize()
+    est.reset()       # ROCOF memory only (a window across the seam may have left a NaN frequency in a stream's delay line)
     launches0 = est.launches
     ms = B.timed_launches(lambda i: est.stream_advance(F, d_out), n_push)
     est.sync()

@@ -152,14 +152,17 @@ int pmub_stream_push(pmub_batch *b, int n_frames, const void *new_samples, const
 #define PMUB_PUSH_ASYNC 1u
 /* PMUB_PUSH_IN_PLACE: `samples` is ignored (may be NULL) - device code of the caller has already written the n_frames * hop
  * new samples of every stream into the rings, starting at the write position pmub_stream_ring_info reports (ring of stream
- * w = base + w * cap_samples, in float_p; positions wrap at cap_samples).  No ingest pass at all: the estimator launch is
- * the only kernel. */
+ * w = base + w * pmub_stream_ring_pitch(b), in float_p; positions [0, cap_samples), wrapping at cap_samples).  No ingest
+ * pass: the estimator launch is the only kernel (plans with several slabs per window keep a mirror of each ring's first
+ * win_len samples behind its end, which the library brings up to date with a small kernel first). */
 #define PMUB_PUSH_IN_PLACE 2u
 int pmub_stream_set_scale(pmub_batch *b, const double *scale);
 int pmub_stream_push_ex(pmub_batch *b, int n_frames, const void *samples, int sample_format,
                         const void *mid_fracsec, void *frames, unsigned flags, unsigned long long *ticket);
 int pmub_stream_wait(pmub_batch *b, unsigned long long ticket);
 int pmub_stream_ring_info(pmub_batch *b, void **base, long long *cap_samples, long long *write_pos);
+/* samples between consecutive ring rows (>= cap_samples; -1 before pmub_stream_begin): row w starts at base + w * pitch */
+long long pmub_stream_ring_pitch(const pmub_batch *b);
 int pmub_sync(pmub_batch *b);
 /* Run on the caller's CUDA stream (cudaStream_t passed as void*); NULL = own stream. */
 int pmub_set_stream(pmub_batch *b, void *cuda_stream);

@@ -172,6 +172,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.pmub_sync.argtypes = [vp]
     lib.pmub_set_stream.argtypes = [vp, vp]
     lib.pmub_set_overlap.argtypes = [vp, C.c_int]
+    lib.pmub_stream_ring_pitch.argtypes = [vp]
+    lib.pmub_stream_ring_pitch.restype = C.c_longlong
     lib.pmub_launch_count.argtypes = [vp]
     lib.pmub_launch_count.restype = C.c_longlong
     lib.pmub_reset.argtypes = [vp]
@@ -446,6 +448,10 @@ class BatchEstimator:
         base, cap, pos = C.c_void_p(), C.c_longlong(), C.c_longlong()
         self._check(self.lib.pmub_stream_ring_info(self._h, C.byref(base), C.byref(cap), C.byref(pos)), "pmub_stream_ring_info")
         return int(base.value), int(cap.value), int(pos.value)
+
+    def stream_ring_pitch(self) -> int:
+        """Samples between consecutive ring rows (>= the ring capacity): row ``w`` starts at ``base + w * pitch``."""
+        return int(self.lib.pmub_stream_ring_pitch(self._h))
 
     def stream_advance(self, n_frames: int, out, mid_fracsec=None, asynchronous: bool = True):
         """``n_frames`` more frames from samples the caller's device code already wrote into the rings

@@ -52,6 +52,8 @@ struct pmub_batch {
     // streaming front end (pmub_stream_*): per-stream sample rings resident in HBM
     unsigned char* d_ring;      // float_p [n_windows][ring_cap]
     long long ring_cap;         // samples per stream ring (multiple of hop, >= win_len + (max_frames-1)*hop)
+    long long ring_pitch;       // samples between ring rows: ring_cap, or ring_cap + win_len (mirrored rings, see ring_mirror)
+    bool ring_mirror;           // the first win_len samples of every ring are kept a second time behind its end
     long long ring_wpos;        // next write position
     int hop, stream_max_frames;
     unsigned long long stream_origin, stream_pushed;  // absolute index of sample 0; samples pushed so far
@@ -107,12 +109,42 @@ static_assert(sizeof(CUtensorMap) == sizeof(PmuTensorMap), "tensor map size");
 
 // Describe `rows` windows at `base` as the tensor [rows][M][L] with a box of one slab [1][M][W].  Returns false when the
 // geometry does not qualify (then the producer issues one bulk copy per row).
-static bool encode_window_tensor(const pmub_batch* b, const void* base, long long rows, PmuTensorMap* out)
+static bool plan_uses_tensor_maps(const pmub_batch* b)
 {
     const pmu::Plan& p = b->plan;
     static const int off = getenv("PMU_NO_TENSOR_MAP") ? atoi(getenv("PMU_NO_TENSOR_MAP")) : 0;
     const bool whole = (p.nslab == 1 && p.pitch == p.L);   // one plain bulk copy per window already
-    if (off || p.M < 2 || whole || !p.aligned16 || p.pitch > 256 || p.W > p.pitch || rows < 1 || rows > 0x7fffffffll) return false;
+    return !(off || p.M < 2 || whole || !p.aligned16 || p.pitch > 256 || p.W > p.pitch) && tmap_encoder() != nullptr;
+}
+
+// The rings of the streaming front end as the tensor [streams][M][ring_pitch] whose rows are L samples apart: with the
+// mirror behind each ring's end a window is win_len contiguous samples from any start position, and a slab of it is the
+// box [1][M][W] at column start + slab * W.  (Row stride < row extent: the M rows of a window overlap in the
+// descriptor; cuTensorMapEncodeTiled accepts it and the copy engine just computes addresses.)
+static bool encode_ring_tensor(const pmub_batch* b, const void* base, long long rows, PmuTensorMap* out)
+{
+    const pmu::Plan& p = b->plan;
+    if (!b->ring_mirror || !plan_uses_tensor_maps(b) || rows < 1 || rows > 0x7fffffffll) return false;
+    tmap_encode_fn enc = tmap_encoder();
+    const cuuint64_t s = (cuuint64_t)b->dtype;
+    if (!enc || ((uintptr_t)base & 15u) || ((cuuint64_t)b->ring_pitch * s) % 16) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)b->ring_pitch, (cuuint64_t)p.M, (cuuint64_t)rows};
+    const cuuint64_t gstride[2] = {(cuuint64_t)p.L * s, (cuuint64_t)b->ring_pitch * s};
+    const cuuint32_t box[3] = {(cuuint32_t)p.pitch, (cuuint32_t)p.M, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUtensorMap m;
+    const CUresult r = enc(&m, b->dtype == PMUB_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                           const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    memcpy(out, &m, sizeof m);
+    return true;
+}
+
+static bool encode_window_tensor(const pmub_batch* b, const void* base, long long rows, PmuTensorMap* out)
+{
+    const pmu::Plan& p = b->plan;
+    if (!plan_uses_tensor_maps(b) || rows < 1 || rows > 0x7fffffffll) return false;
     tmap_encode_fn enc = tmap_encoder();
     if (!enc || ((uintptr_t)base & 15u)) return false;
     const cuuint64_t s = (cuuint64_t)b->dtype;
@@ -155,8 +187,9 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     KernelArgs a = b->args;
     const size_t sz = (size_t)b->dtype;
     if (ring) {
-        a.windows = b->d_ring + (size_t)w0 * (size_t)b->ring_cap * sz;
+        a.windows = b->d_ring + (size_t)w0 * (size_t)b->ring_pitch * sz;
         a.ring_cap = b->ring_cap;
+        a.ring_pitch = b->ring_pitch;
         a.ring_start = ring->start;
         a.hop = b->hop;
         a.fs = (int)b->cfg.fs;
@@ -195,7 +228,7 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     }
     // TMA bulk copies need 16-byte aligned sources; otherwise per-element cp.async
     bool ok16 = b->plan.aligned16 && (((uintptr_t)a.windows) % 16 == 0);
-    if (ring) ok16 = ok16 && ((size_t)b->ring_cap * sz) % 16 == 0 && ((size_t)b->hop * sz) % 16 == 0;
+    if (ring) ok16 = ok16 && ((size_t)b->ring_cap * sz) % 16 == 0 && ((size_t)b->ring_pitch * sz) % 16 == 0 && ((size_t)b->hop * sz) % 16 == 0;
     a.load_mode = ok16 ? PMU_LOAD_BULK : PMU_LOAD_ELEM;
     static const int force_elem = getenv("PMU_FORCE_ELEM_LOAD") ? atoi(getenv("PMU_FORCE_ELEM_LOAD")) : 0;
     if (force_elem) a.load_mode = PMU_LOAD_ELEM;
@@ -208,6 +241,7 @@ static int launch_range(pmub_batch* b, long long w0, long long w1, int n_frames,
     if (!ring && a.load_mode == PMU_LOAD_BULK &&
         encode_window_tensor(b, a.windows, (long long)(n_frames - 1) * b->n_windows + (w1 - w0), &a.tmap))
         a.use_tmap = 1;
+    if (ring && a.load_mode == PMU_LOAD_BULK && encode_ring_tensor(b, a.windows, w1 - w0, &a.tmap)) a.use_tmap = 1;
     int grid = grid_for(b, a.n_windows);
     if (b->plan.M == 0) {   // general kernel: one warp per window, plan.n_cons active warps per CTA
         a.warp_per_window = 0;
@@ -280,7 +314,7 @@ static int ensure_cap(unsigned char** p, size_t* cap, size_t need)
 template <typename RingT, typename SrcT>
 __global__ void ring_scatter_kernel(RingT* __restrict__ ring, const SrcT* __restrict__ src, const double* __restrict__ scale,
                                     long long n_streams, long long w0, long long w1, int n_frames, int hop, long long cap,
-                                    long long wpos)
+                                    long long wpos, long long pitch, int mirror_len)
 {
     // one warp per (frame, stream) row of `hop` consecutive samples: coalesced on both sides, one division per row
     const int lane = threadIdx.x & 31;
@@ -292,13 +326,15 @@ __global__ void ring_scatter_kernel(RingT* __restrict__ ring, const SrcT* __rest
         const long long w = w0 + (row - (long long)f * n_w);
         const long long p0 = (wpos + (long long)f * hop) % cap;
         const SrcT* __restrict__ s = src + ((long long)f * n_streams + w) * hop;
-        RingT* __restrict__ d = ring + w * cap;
+        RingT* __restrict__ d = ring + w * pitch;
         const double sc = scale ? scale[w] : 1.0;
         for (int j = lane; j < hop; j += 32) {
             long long p = p0 + j;
             if (p >= cap) p -= cap;
             const SrcT v = s[j];
-            d[p] = scale ? (RingT)(sc * (double)v) : (RingT)v;
+            const RingT r = scale ? (RingT)(sc * (double)v) : (RingT)v;
+            d[p] = r;
+            if (p < mirror_len) d[cap + p] = r;     // mirrored rings: the first win_len samples once more behind the end
         }
     }
 }
@@ -313,11 +349,48 @@ static cudaError_t launch_scatter(pmub_batch* b, const void* src, const double* 
     if (blocks < 1) blocks = 1;
     if (b->dtype == PMUB_F64)
         ring_scatter_kernel<double, SrcT><<<blocks, 256, 0, s>>>((double*)b->d_ring, (const SrcT*)src, scale, b->n_windows, w0, w1,
-                                                                  n_frames, b->hop, b->ring_cap, b->ring_wpos);
+                                                                  n_frames, b->hop, b->ring_cap, b->ring_wpos, b->ring_pitch,
+                                                                  b->ring_mirror ? (int)b->d.N : 0);
     else
         ring_scatter_kernel<float, SrcT><<<blocks, 256, 0, s>>>((float*)b->d_ring, (const SrcT*)src, scale, b->n_windows, w0, w1,
-                                                                 n_frames, b->hop, b->ring_cap, b->ring_wpos);
+                                                                 n_frames, b->hop, b->ring_cap, b->ring_wpos, b->ring_pitch,
+                                                                 b->ring_mirror ? (int)b->d.N : 0);
     return cudaGetLastError();
+}
+
+// Mirrored rings: bring the mirror up to date after `len` samples were written from ring position `pos` on by something
+// other than the scatter kernel (a 2-D copy, the history at pmub_stream_begin, a device-side producer writing in place).
+template <typename RingT>
+__global__ void ring_mirror_kernel(RingT* __restrict__ ring, long long w0, long long w1, long long cap, long long pitch,
+                                   int mirror_len, long long pos, long long len)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = w0 + ((((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5); w < w1; w += warps) {
+        RingT* __restrict__ d = ring + w * pitch;
+        for (long long j = lane; j < len; j += 32) {
+            long long p = pos + j;
+            if (p >= cap) p -= cap;
+            if (p < mirror_len) d[cap + p] = d[p];
+        }
+    }
+}
+
+// returns true when a kernel was enqueued
+static bool refresh_mirror(pmub_batch* b, long long w0, long long w1, long long pos, long long len, cudaStream_t s)
+{
+    if (!b->ring_mirror || len <= 0) return false;
+    const long long N = b->d.N, cap = b->ring_cap;
+    pos %= cap;
+    if (pos >= N && pos + len <= cap) return false;       // nothing of [pos, pos + len) lies in the mirrored part
+    int blocks = (int)((w1 - w0 + 7) / 8);
+    if (blocks > b->num_sms * 16) blocks = b->num_sms * 16;
+    if (blocks < 1) blocks = 1;
+    if (b->dtype == PMUB_F64)
+        ring_mirror_kernel<double><<<blocks, 256, 0, s>>>((double*)b->d_ring, w0, w1, cap, b->ring_pitch, (int)N, pos, len);
+    else
+        ring_mirror_kernel<float><<<blocks, 256, 0, s>>>((float*)b->d_ring, w0, w1, cap, b->ring_pitch, (int)N, pos, len);
+    return true;
 }
 
 static bool is_device_ptr(const void* p)
@@ -683,15 +756,21 @@ int pmub_stream_begin(pmub_batch* b, unsigned hop, unsigned max_frames_per_push,
     long long cap = N + (long long)(max_frames_per_push - 1) * hop;
     cap = (cap + hop - 1) / hop * hop;                  // whole hops: a pushed block never wraps
     if (b->d_ring) { cudaFree(b->d_ring); b->d_ring = nullptr; }
-    CUDA_OK(cudaMalloc(&b->d_ring, (size_t)b->n_windows * (size_t)cap * sz));
-    CUDA_OK(cudaMemset(b->d_ring, 0, (size_t)b->n_windows * (size_t)cap * sz));
+    // plans that load their slabs as tensor-map tiles get mirrored rings (a window is then contiguous wherever it starts)
+    b->ring_mirror = b->plan.M != 0 && plan_uses_tensor_maps(b) && ((size_t)hop * sz) % 16 == 0;
+    long long pitch = cap;
+    if (b->ring_mirror) pitch = (cap + N + 3) / 4 * 4;    // rows stay 16-byte aligned for either sample size
+    CUDA_OK(cudaMalloc(&b->d_ring, (size_t)b->n_windows * (size_t)pitch * sz));
+    CUDA_OK(cudaMemset(b->d_ring, 0, (size_t)b->n_windows * (size_t)pitch * sz));
     b->ring_cap = cap;
+    b->ring_pitch = pitch;
     b->hop = (int)hop;
     b->stream_max_frames = (int)max_frames_per_push;
     const long long hist = N - hop;                     // samples needed before the first push completes a window
     if (history && hist > 0)
-        CUDA_OK(cudaMemcpy2D(b->d_ring, (size_t)cap * sz, history, (size_t)hist * sz, (size_t)hist * sz, (size_t)b->n_windows,
+        CUDA_OK(cudaMemcpy2D(b->d_ring, (size_t)pitch * sz, history, (size_t)hist * sz, (size_t)hist * sz, (size_t)b->n_windows,
                              cudaMemcpyDefault));
+    if (history && hist > 0 && refresh_mirror(b, 0, b->n_windows, 0, hist, 0)) CUDA_OK(cudaDeviceSynchronize());
     b->ring_wpos = hist % cap;
     b->stream_origin = first_sample_index;
     b->stream_pushed = (unsigned long long)hist;
@@ -747,12 +826,14 @@ int pmub_stream_push(pmub_batch* b, int n_frames, const void* new_samples, const
                 const long long p = (b->ring_wpos + (long long)f * hop) % cap;
                 const long long n1 = (cap - p < hop) ? cap - p : hop;
                 const unsigned char* src = (const unsigned char*)new_samples + ((size_t)f * n + (size_t)w0) * (size_t)hop * sz;
-                CUDA_OK(cudaMemcpy2DAsync(b->d_ring + ((size_t)w0 * (size_t)cap + (size_t)p) * sz, (size_t)cap * sz, src,
+                const size_t rp = (size_t)b->ring_pitch;
+                CUDA_OK(cudaMemcpy2DAsync(b->d_ring + ((size_t)w0 * rp + (size_t)p) * sz, rp * sz, src,
                                           (size_t)hop * sz, (size_t)n1 * sz, (size_t)(w1 - w0), cudaMemcpyDefault, s));
                 if (n1 < hop)
-                    CUDA_OK(cudaMemcpy2DAsync(b->d_ring + (size_t)w0 * (size_t)cap * sz, (size_t)cap * sz, src + (size_t)n1 * sz,
+                    CUDA_OK(cudaMemcpy2DAsync(b->d_ring + (size_t)w0 * rp * sz, rp * sz, src + (size_t)n1 * sz,
                                               (size_t)hop * sz, (size_t)(hop - n1) * sz, (size_t)(w1 - w0), cudaMemcpyDefault, s));
             }
+            refresh_mirror(b, w0, w1, b->ring_wpos, (long long)n_frames * hop, s);
         } else {
             // narrow rows: contiguous copies into a staging area (host input), then a scatter kernel
             const unsigned char* src = (const unsigned char*)new_samples;
@@ -880,8 +961,13 @@ int pmub_stream_push_ex(pmub_batch* b, int n_frames, const void* samples, int sa
     RingSrc ring;
     ring.start = ((b->ring_wpos + hop - N) % cap + cap) % cap;
     ring.t0 = (b->stream_origin + b->stream_pushed + (unsigned long long)hop - (unsigned long long)N) % b->cfg.fs;
+    // samples written in place by the caller's device code: mirrored rings need their mirror brought up to date
+    bool own_kernel_before = false;
+    if (in_place) own_kernel_before = refresh_mirror(b, 0, (long long)n, b->ring_wpos, (long long)n_frames * hop, s_comp);
     // (in place: no ingest kernel, no copy of mid_fracsec before the launch)
-    if (launch_frames(b, 0, (long long)n, n_frames, nullptr, dM, dF, nullptr, s_comp, &ring, in_place && (!mid || mid_dev))) return -1;
+    if (launch_frames(b, 0, (long long)n, n_frames, nullptr, dM, dF, nullptr, s_comp, &ring,
+                      in_place && !own_kernel_before && (!mid || mid_dev)))
+        return -1;
     if (!fr_dev) CUDA_OK(cudaMemcpyAsync(frames, dF, fr_bytes * n_frames, cudaMemcpyDeviceToHost, s_comp));
     CUDA_OK(cudaEventRecord(b->ev_done[dslot], s_comp));
     b->ev_done_valid[dslot] = true;
@@ -903,6 +989,10 @@ int pmub_stream_ring_info(pmub_batch* b, void** base, long long* cap_samples, lo
     if (write_pos) *write_pos = b->ring_wpos;
     return 0;
 }
+
+// Samples between consecutive ring rows (>= the ring capacity: some plans keep a mirror of each ring's head behind its end,
+// maintained by the library - a producer writes positions [0, capacity) of row w at base + w * pitch only).
+long long pmub_stream_ring_pitch(const pmub_batch* b) { return (b && b->d_ring) ? b->ring_pitch : -1; }
 
 // Block until the push that returned `ticket` has delivered its frames.
 int pmub_stream_wait(pmub_batch* b, unsigned long long ticket)

@@ -116,6 +116,11 @@ struct KernelArgs {
     // the frame / state stores - so the transforms of this launch start on every SM the previous launch has already
     // left, while its last CTAs are still in their estimator tail.
     int defer_wait;
+    // streaming front end: samples between consecutive ring rows (>= ring_cap).  Plans whose slabs are tensor-map tiles keep
+    // a MIRROR of each ring's first win_len samples behind its end (positions cap ... cap + win_len - 1), so that every
+    // window is contiguous in memory and one tiled copy per slab works for rings too (the tensor's row stride L is
+    // smaller than its row extent: rows of one window overlap in the descriptor, which the copy engine does not mind).
+    long long ring_pitch;
 };
 
 struct CtrlBlock {
@@ -817,7 +822,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 if (a.ring_cap == 0) {
                     src = reinterpret_cast<const InT*>(a.windows) + ((size_t)f * a.frame_stride + (size_t)(w_begin + tw)) * a.N;
                 } else {
-                    src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + tw) * a.ring_cap;
+                    src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + tw) * a.ring_pitch;
                     start = ring_pos;
                 }
                 if (whole) {
@@ -827,7 +832,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                             bulk_g2s(dst, src, (uint32_t)(win_bytes * cnt), &ctrl->full[st]);
                         } else {
                             for (int c = 0; c < cnt; ++c)
-                                bulk_segment<InT>(dst + (size_t)c * win_bytes, src + (size_t)c * a.ring_cap, start, a.ring_cap, 0, a.N,
+                                bulk_segment<InT>(dst + (size_t)c * win_bytes, src + (size_t)c * a.ring_pitch, start, a.ring_cap, 0, a.N,
                                                   &ctrl->full[st]);
                         }
                     }
@@ -835,7 +840,10 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                     // TMA-tiled: the copy engine walks the M rows of the slab itself
                     if (lane == 0) {
                         mbar_expect_tx(&ctrl->full[st], (uint32_t)(pitch * sizeof(InT)) * M);
-                        tma_load_slab(dst, &a.tmap, sl * a.W, (int)((long long)f * a.frame_stride + w_begin + t), &ctrl->full[st]);
+                        if (a.ring_cap == 0)
+                            tma_load_slab(dst, &a.tmap, sl * a.W, (int)((long long)f * a.frame_stride + w_begin + t), &ctrl->full[st]);
+                        else   // mirrored ring: the window is contiguous from its start position
+                            tma_load_slab(dst, &a.tmap, (int)ring_pos + sl * a.W, (int)(w_begin + t), &ctrl->full[st]);
                     }
                 } else if (WP == 1) {
                     const int a_lo = sl * a.W;
@@ -868,7 +876,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                 if (a.ring_cap == 0) {
                     src = reinterpret_cast<const InT*>(a.windows) + ((size_t)f * a.frame_stride + (size_t)(w_begin + tw)) * a.N;
                 } else {
-                    src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + tw) * a.ring_cap;
+                    src = reinterpret_cast<const InT*>(a.windows) + (size_t)(w_begin + tw) * a.ring_pitch;
                     start = ring_pos;
                 }
                 if constexpr (WP == 1) {
@@ -882,7 +890,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
                         }
                 } else {
                     // natural pitch: the stage holds the cnt windows back to back, exactly as they lie in memory
-                    const size_t wstride = a.ring_cap == 0 ? (size_t)a.N : (size_t)a.ring_cap;
+                    const size_t wstride = a.ring_cap == 0 ? (size_t)a.N : (size_t)a.ring_pitch;
                     for (int c = 0; c < cnt; ++c)
                         for (int e = lane; e < a.N; e += PMU_WARP) {
                             long long p = start + e;

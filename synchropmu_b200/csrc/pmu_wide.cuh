@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(PMU_WIDE_THREADS) pmu_wide_kernel(const __grid
         if (a.ring_cap == 0) {
             src = reinterpret_cast<const InT*>(a.windows) + (size_t)w * N;
         } else {
-            src = reinterpret_cast<const InT*>(a.windows) + (size_t)w * a.ring_cap;
+            src = reinterpret_cast<const InT*>(a.windows) + (size_t)w * a.ring_pitch;
             start = a.ring_start % a.ring_cap;
         }
         __syncwarp();

@@ -663,12 +663,16 @@ def _long_streams(cfg, n_streams, total, seed):
     (configs.CFG5_600, "f64", 4, True),
     (configs.P_CLASS_INI, "f64", 3, False),
     (configs.DEFAULT_INI, "f32", 2, False),
+    # several slabs per window: mirrored rings, one tensor-map tile per slab (M-class float; the reference's 16384-sample point)
+    (configs.M_CLASS_INI, "f32", 3, True),
+    (configs.TEST2_16CYC, "f64", 2, False),
     (dict(configs.DEFAULT_INI, fs=4750, n_cycles=3, n_bins=7), "f64", 2, False),   # odd hop: per-element loader
     # hop does not divide win_len (768 samples, hop 512): pushed blocks cross the end of the ring - wide rows go in
     # as two 2-D copies (f64, 4 KB per row), narrow ones through the scatter kernel (f32)
     (dict(configs.DEFAULT_INI, f0=60, fs=15360, n_cycles=3, frame_rate=30, n_bins=8), "f64", 8, True),
     (dict(configs.DEFAULT_INI, f0=60, fs=15360, n_cycles=3, frame_rate=30, n_bins=8), "f32", 3, False),
-], ids=["default_F1", "default_F3", "mclass_F2", "cfg5_F4", "pclass_F3", "float_F2", "oddhop_F2", "hop_not_dividing_N_F8",
+], ids=["default_F1", "default_F3", "mclass_F2", "cfg5_F4", "pclass_F3", "float_F2", "mclass_float_F3", "test2_F2", "oddhop_F2",
+        "hop_not_dividing_N_F8",
         "hop_not_dividing_N_f32"])
 def test_stream_push_equals_explicit_windows(cfg, dtype, F, given_mid):
     dt = DT[dtype]
@@ -719,16 +723,18 @@ def test_stream_push_explicit_odd_hop_that_does_not_divide_the_window():
     assert np.array_equal(got, want)
 
 
-def test_stream_in_place_ring_writes_equal_pushes():
-    """A device-side producer writes the new samples straight into the rings (pmub_stream_ring_info) and calls
-    stream_advance (PMUB_PUSH_IN_PLACE, no ingest kernel): same frames as handing the same samples to stream_push."""
+@pytest.mark.parametrize("cfgname", ["config.ini", "m_class_config.ini"])
+def test_stream_in_place_ring_writes_equal_pushes(cfgname):
+    """A device-side producer writes the new samples straight into the rings (pmub_stream_ring_info / _ring_pitch) and
+    calls stream_advance (PMUB_PUSH_IN_PLACE, no ingest kernel): same frames as handing the same samples to stream_push.
+    (M-class: several slabs per window, so the rings carry a mirror that the library refreshes itself.)"""
     torch = pytest.importorskip("torch")
 
     class Ring:     # a torch view of the library's rings through __cuda_array_interface__
-        def __init__(self, ptr, n, cap):
-            self.__cuda_array_interface__ = dict(shape=(n, cap), typestr="<f8", data=(ptr, False), version=3)
+        def __init__(self, ptr, n, pitch):
+            self.__cuda_array_interface__ = dict(shape=(n, pitch), typestr="<f8", data=(ptr, False), version=3)
 
-    cfg = configs.DEFAULT_INI
+    cfg = configs.NAMED[cfgname]
     n_inst, C_, F = 13, 6, 3
     n = n_inst * C_
     N, hop = configs.win_len(cfg), configs.hop(cfg)
@@ -739,7 +745,9 @@ def test_stream_in_place_ring_writes_equal_pushes():
         a.stream_begin(hop=0, max_frames_per_push=F, history=hist)
         b.stream_begin(hop=0, max_frames_per_push=F, history=hist)
         base, cap, _ = b.stream_ring_info()
-        ring = torch.as_tensor(Ring(base, n, cap), device="cuda")
+        pitch = b.stream_ring_pitch()
+        assert pitch >= cap and (pitch > cap) == (cfgname == "m_class_config.ini")
+        ring = torch.as_tensor(Ring(base, n, pitch), device="cuda")
         xd = torch.as_tensor(x, device="cuda")
         out = torch.empty((F, n_inst, C_, 4), dtype=torch.float64, device="cuda")
         for p in range(pushes):
@@ -756,12 +764,14 @@ def test_stream_in_place_ring_writes_equal_pushes():
             assert np.max(np.abs(got[..., 1] - want[..., 1])) < 1e-11
 
 
-@pytest.mark.parametrize("fmt", ["i16", "f32", "native_async"])
+@pytest.mark.parametrize("fmt", ["i16", "f32", "native_async", "i16_mclass", "native_async_mclass"])
 def test_stream_push_narrow_formats_and_async_pushes_equal_explicit_windows(fmt):
     """pmub_stream_push_ex: int16 ADC counts (x per-stream scale) and float samples are promoted on the device, exactly,
     so the frames are those of explicit double windows holding the promoted values; asynchronous pushes from two
-    alternating buffers give the frames of synchronous ones."""
-    cfg = configs.DEFAULT_INI
+    alternating buffers give the frames of synchronous ones.  (`_mclass`: a plan with mirrored rings, the ingest kernel
+    writes the mirror.)"""
+    cfg = configs.M_CLASS_INI if fmt.endswith("_mclass") else configs.DEFAULT_INI
+    fmt = fmt.replace("_mclass", "")
     n_inst, C_, F = 19, 6, 2
     N, hop = configs.win_len(cfg), configs.hop(cfg)
     pushes = 7

@@ -53,6 +53,8 @@ torch.cuda.synchronize()
 def timed(fn):
     for i in range(warm):
         fn(i)
+    torch.cuda.synchronize()
+    est.reset()      # ROCOF memory only: a window across the replay's seam may have left a NaN in a stream's delay line
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(s)
     for i in range(warm, K):
