@@ -746,7 +746,9 @@ def test_stream_in_place_ring_writes_equal_pushes(cfgname):
         b.stream_begin(hop=0, max_frames_per_push=F, history=hist)
         base, cap, _ = b.stream_ring_info()
         pitch = b.stream_ring_pitch()
-        assert pitch >= cap and (pitch > cap) == (cfgname == "m_class_config.ini")
+        import os
+        mirrored = cfgname == "m_class_config.ini" and os.environ.get("PMU_NO_TENSOR_MAP", "0") in ("", "0")
+        assert pitch >= cap and (pitch > cap) == mirrored     # (the starved-resources runs switch tensor maps off)
         ring = torch.as_tensor(Ring(base, n, pitch), device="cuda")
         xd = torch.as_tensor(x, device="cuda")
         out = torch.empty((F, n_inst, C_, 4), dtype=torch.float64, device="cuda")
