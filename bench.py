@@ -318,6 +318,51 @@ class Bench:
             del x
         return rec
 
+    def stream_leg(self, wl_name, dtype, F, n_push):
+        """The streaming front end on another configuration, samples resident in the HBM rings (one record continuous in
+        time, pushed once through the ingest kernel, then replayed in place: see stream_legs): {value, frac, ...}."""
+        from synchropmu_b200 import BatchEstimator
+
+        torch = self.torch
+        wl = WORKLOADS[wl_name]
+        cfg = configs.NAMED[wl["cfg"]]
+        n_inst, n_ch = wl["n_inst"], wl["n_ch"]
+        tdt = torch.float64 if dtype == "f64" else torch.float32
+        npdt = np.float64 if dtype == "f64" else np.float32
+        N, hop = configs.win_len(cfg), configs.hop(cfg)
+        warm = max(3, -(-(N // hop - 1) // F))                # the warm-up pushes cover the replay's seam
+        K = warm + n_push
+        history = self.make_record(cfg, n_inst, n_ch, tdt, 0, 1, [], samples_per_row=N - hop)[0]
+        rec = self.make_record(cfg, n_inst, n_ch, tdt, N - hop, K * F, [])
+        d_out = torch.empty((F, n_inst, n_ch, 4), dtype=tdt, device=self.dev)
+        est = BatchEstimator(cfg, n_inst, n_ch, dtype=npdt, device=self.local_rank)
+        est.set_stream(self.stream.cuda_stream)
+        est.stream_begin(hop=hop, max_frames_per_push=K * F, history=history)
+        for i in range(warm):
+            est.stream_push(rec[i * F:(i + 1) * F], None, out=d_out, asynchronous=True)
+        torch.cuda.synchronize()
+        ms_ingest = self.timed_launches(lambda i: est.stream_push(rec[(warm + i) * F:(warm + i + 1) * F], None, out=d_out,
+                                                                  asynchronous=True), n_push)
+        est.sync()
+        for i in range(warm):
+            est.stream_advance(F, d_out)
+        torch.cuda.synchronize()
+        est.reset()
+        ms = self.timed_launches(lambda i: est.stream_advance(F, d_out), n_push)
+        est.sync()
+        finite = bool(torch.isfinite(d_out).all().item())
+        n_est = n_inst * n_ch * F
+        value = self.world * n_est * n_push / (ms * 1e-3)
+        bpe = configs.bytes_per_estimate(cfg, 8 if dtype == "f64" else 4, n_ch)
+        res = dict(value=value, unit=UNIT, frac_of_bytes_requested=value / self.world * bpe / 1e9 / self.peak, ms_per_push=ms / n_push,
+                   pushes=n_push, frames_per_push=F, with_ingest=self.world * n_est * n_push / (ms_ingest * 1e-3),
+                   ring_pitch_samples=est.stream_ring_pitch(), ring_capacity_samples=est.stream_ring_info()[1], win_len=N, hop=hop,
+                   dtype=dtype, outputs_finite=finite, workload=wl["desc"] + ", streaming front end, samples in the HBM rings")
+        est.close()
+        del rec, history, d_out
+        torch.cuda.empty_cache()
+        return res
+
     def timed_launches(self, fn, steps):
         """CUDA-event time of `steps` calls of fn(i) on self.stream, max over ranks, in ms."""
         torch = self.torch
@@ -772,6 +817,11 @@ def main():
                 workloads[name] = B.device_leg(wl_name, dt_name, trig, f_leg, args.extra_steps)
             except Exception as e:   # a leg that cannot run is reported, it does not take the headline down
                 workloads[name] = dict(error=str(e)[:300])
+        # the streaming front end on a plan with several slabs per window (mirrored rings, tensor-map tiles)
+        try:
+            workloads["mclass_f64_stream"] = B.stream_leg("mclass", "f64", 8, 8)
+        except Exception as e:
+            workloads["mclass_f64_stream"] = dict(error=str(e)[:300])
 
     if rank != 0:
         if dist is not None:

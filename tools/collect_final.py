@@ -43,5 +43,5 @@ for f in ("r2_bench_final.json", "r2_bench_default_400steps.json"):
     print("   stream_device        %.4g (with ingest %.4g), %.0f B DRAM per estimate" % (sd["value"], sd["with_ingest"]["value"],
                                                                                      sd["roofline"].get("traffic_bytes_per_estimate") or 0))
     for k, v in d["workloads"].items():
-        print("   %-28s %.4g frac %.3f" % (k, v.get("value", 0), v.get("frac", 0)))
+        print("   %-28s %.4g frac %.3f" % (k, v.get("value", 0), v.get("frac", v.get("frac_of_bytes_requested", 0))))
     print("   cpu_baseline         %.4g on %d cores" % (d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"]))
