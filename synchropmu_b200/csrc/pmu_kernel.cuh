@@ -257,8 +257,8 @@ typedef FastDivT<false> FastDiv;
 template <bool PLAIN>
 struct BatchMapT {
     int nb, q, rem;  // batches, base size, number of batches with q+1 windows
-    FastDivT<PLAIN> by_q, by_q1;
-    __device__ __forceinline__ void init(int n, int cap = PMU_WARP)
+    FastDivT<PLAIN> by_q, by_q1, by_F;
+    __device__ __forceinline__ void init(int n, int cap = PMU_WARP, int n_frames = 1)
     {
         nb = (n + cap - 1) / cap;
         if (nb < 1) nb = 1;
@@ -266,21 +266,26 @@ struct BatchMapT {
         rem = n - q * nb;
         by_q.init((unsigned)q);
         by_q1.init((unsigned)(q + 1));
+        by_F.init((unsigned)n_frames);
     }
-    // group-major item order of a launch with F frames: item -> (frame, pass).  Plain divisions: this runs once per
-    // window in streaming launches only, and keeping four more magic numbers alive costs the 24-bin kernels spills.
+    // group-major item order of a launch with F frames: item -> (frame, pass).
+    //   item = (group * F + frame) * size + slot  within the groups of one size  =>  item / size = group * F + frame
+    // (two multiply-high divisions by the dividers the batch map keeps anyway; the two plain 32-bit divisions this used
+    //  to be were ~ 55 instructions per window, 4 % of a streaming launch)
     __device__ __forceinline__ void item_group_major(int item, int F, int* f, int* t) const
     {
         const int big_items = rem * (q + 1) * F;
+        unsigned slot, fr;
         if (item < big_items) {
-            const int g = item / ((q + 1) * F), r = item - g * (q + 1) * F;
-            *f = r / (q + 1);
-            *t = g * (q + 1) + (r - *f * (q + 1));
+            const unsigned u = by_q1.div((unsigned)item, &slot);
+            const unsigned g = by_F.div(u, &fr);
+            *f = (int)fr;
+            *t = (int)g * (q + 1) + (int)slot;
         } else {
-            const int i2 = item - big_items;
-            const int gg = i2 / (q * F), r = i2 - gg * q * F;
-            *f = r / q;
-            *t = rem * (q + 1) + gg * q + (r - *f * q);
+            const unsigned u = by_q.div((unsigned)(item - big_items), &slot);
+            const unsigned gg = by_F.div(u, &fr);
+            *f = (int)fr;
+            *t = rem * (q + 1) + (int)gg * q + (int)slot;
         }
     }
     __device__ __forceinline__ void locate(int t, int* g, int* slot, int* size, int* first) const
@@ -911,7 +916,7 @@ __global__ void __launch_bounds__(PMU_BLOCK_THREADS, 1) pmu_fused_kernel(const _
     unsigned long long* tl = a.timeline ? a.timeline + ((size_t)blockIdx.x * (PMU_BLOCK_THREADS / PMU_WARP) + warp) * 4 : nullptr;
     if (tl && lane == 0) { tl[0] = global_ns(); tl[1] = 0; }
     BatchMapT<(KC >= 24)> bm;             // batches of <= 32 streams = <= 32 / WP passes
-    bm.init(n_packs, PMU_WARP / WP);
+    bm.init(n_packs, PMU_WARP / WP, a.n_frames);
     FastDivT<(KC >= 24)> by_nlocal, by_nstage;
     by_nlocal.init((unsigned)n_packs);
     const int sub = lane / G;             // which stream of the pass this lane works on (0 when WP == 1)
