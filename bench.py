@@ -19,8 +19,10 @@ Prints ONE JSON line (rank 0):
   workloads     the other configurations, each a short device-timed run with its own roofline fraction:
                 config 5 (600-sample windows, 1M/8 channels per GPU), M-class (3072 samples), the float build,
                 config 3 / M-class with EVERY stream triggering the interference iterations, the reference's
-                test2.c point (16 cycles @ 51.2 kHz = 16384 samples, 18 bins)
-  stream_device the streaming front end with its sample rings resident in HBM (device-timed)
+                test2.c point (16 cycles @ 51.2 kHz = 16384 samples, 18 bins), M-class through the streaming front end
+  single_frame_launch   one frame per kernel launch (+ `overlapped`: the same with pmub_set_overlap)
+  stream_device the streaming front end with its sample rings resident in HBM, fed from one record continuous in time
+                (device-timed; `with_ingest`: the record pushed as device blocks, `sustained`: the in-place replay for >= 1 s)
   e2e           the same metric through the synchronous C ABI call with pinned HOST buffers (H2D + D2H inside)
   e2e_stream    ... through the streaming front end (only the new samples cross PCIe), double and int16 ingest
   cpu_baseline  the reference CPU path on this box's host cores (a bounded sample)
