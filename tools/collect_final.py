@@ -30,8 +30,8 @@ c = Counter(r[ik].split("(")[0][:60] for r in data[:first])
 (P / "r2_launches_ncu.csv").write_text(
     "# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline "
     "--no-workloads --no-sustained\n# the %d launches before the first estimator launch are torch element-wise kernels building the "
-    "synthetic windows in HBM: %s\n# from the first estimator launch on (3 warm-up + 4 timed launches of 8 frames, then 5 + 20 "
-    "single-frame launches), verbatim:\n" % (first, dict(c)) + "\n".join(",".join('"%s"' % x for x in r) for r in [hdr] + data[first:]) + "\n")
+    "synthetic windows in HBM: %s\n# from the first estimator launch on (3 warm-up + 4 timed launches of 8 frames, a finiteness check, then 5 + 20 "
+    "single-frame launches and the same 5 + 20 with pmub_set_overlap), verbatim:\n" % (first, dict(c)) + "\n".join(",".join('"%s"' % x for x in r) for r in [hdr] + data[first:]) + "\n")
 print("tree hash", bench.kernel_source_hash(), "traffic file", json.load(open(P / "traffic_per_launch.json"))["kernel_source_hash"])
 for f in ("r2_bench_final.json", "r2_bench_default_400steps.json"):
     d = json.loads((P / f).read_text())
